@@ -1,0 +1,565 @@
+// dockauv_capi.cu -- C ABI (include/dockauv.h) over the sm_100a step kernels.
+//
+// No torch types, no global state besides a thread-local error string.  All device memory that crosses the
+// boundary is caller-owned; the handle owns only its small ray table, the statistics vector and (lazily) the
+// device staging buffers + streams of the host-buffer entry point.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "dockauv_launch.h"
+
+using namespace dockauv;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(DOCKAUV_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static const int kHostStreams = 3;
+
+struct DockauvHandle {
+    DockauvParams params;
+    int64_t n_envs = 0;
+    int device = 0;
+    int n_obs = 0;
+    bool bound = false;
+    KParams<double> kd;
+    KParams<float> kf;
+    void *ray_tab = nullptr;
+    double *stats = nullptr;
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    // host pipeline
+    cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t hev[kHostStreams] = {nullptr, nullptr, nullptr};
+    void *st_actions = nullptr;
+    size_t st_actions_bytes = 0;
+    float *st_obs = nullptr;
+    void *st_reward = nullptr;
+    uint8_t *st_done = nullptr, *st_cond = nullptr;
+};
+
+static int pooled_dim(int n, int b) { return (n + b - 1) / b; }
+
+extern "C" int dockauv_abi_version(void) { return DOCKAUV_ABI_VERSION; }
+extern "C" const char *dockauv_last_error(void) { return g_err; }
+extern "C" size_t dockauv_sizeof_params(void) { return sizeof(DockauvParams); }
+
+extern "C" int dockauv_n_obs(const DockauvParams *p) {
+    if (!p || p->block_reduce <= 0) return DOCKAUV_EINVAL;
+    return 16 + pooled_dim(p->n_vert, p->block_reduce) * pooled_dim(p->n_horiz, p->block_reduce);
+}
+
+template <typename T>
+static void fill_kparams(const DockauvParams &s, int64_t n_envs, KParams<T> &k) {
+    memset(&k, 0, sizeof(k));
+    k.n_envs = n_envs;
+    k.env_begin = 0;
+    k.env_end = n_envs;
+    k.n_u = s.n_u;
+    k.n_caps = s.n_capsules;
+    k.n_sph = s.n_spheres;
+    k.n_synth_sph = s.n_synthetic_spheres;
+    k.scenario = s.scenario;
+    k.max_timesteps = s.max_timesteps;
+    k.reward_set = s.reward_set;
+    k.n_rays = s.n_rays;
+    k.n_vert = s.n_vert;
+    k.n_horiz = s.n_horiz;
+    k.block = s.block_reduce;
+    k.n_hr = pooled_dim(s.n_horiz, s.block_reduce);
+    k.n_rr = pooled_dim(s.n_vert, s.block_reduce) * k.n_hr;
+    k.n_obs = 16 + k.n_rr;
+    k.action_factor_is_scalar = s.action_factor_is_scalar;
+    k.seed = s.seed;
+    k.env_id0 = s.env_id0;
+    k.m = (T)s.m;
+    for (int i = 0; i < 3; i++) k.r_G[i] = (T)s.r_G[i];
+    for (int i = 0; i < 9; i++) k.I_b[i] = (T)s.I_b[i];
+    for (int i = 0; i < 6; i++) k.MA[i] = (T)s.MA_diag[i];
+    for (int i = 0; i < 36; i++) k.M_inv[i] = (T)s.M_inv[i];
+    for (int i = 0; i < 10; i++) {
+        k.D_lin[i] = (T)s.D_lin[i];
+        k.D_quad[i] = (T)s.D_quad[i];
+        k.D_lift[i] = (T)s.D_lift[i];
+    }
+    k.G_WB = (T)s.G_WB;
+    for (int i = 0; i < 3; i++) k.G_r[i] = (T)s.G_r[i];
+    for (int i = 0; i < 6 * DOCKAUV_MAX_U; i++) k.B[i] = (T)s.B[i];
+    for (int i = 0; i < 4; i++) k.lauv_B[i] = (T)s.lauv_B[i];
+    for (int i = 0; i < DOCKAUV_MAX_U; i++) {
+        k.u_lo[i] = (T)s.u_lo[i];
+        k.u_span[i] = (T)(s.u_hi[i] - s.u_lo[i]);
+        k.arf[i] = (T)s.action_reward_factors[i];
+        k.arf_f32[i] = (float)s.action_reward_factors[i];
+    }
+    k.lp_alpha = (T)s.lp_alpha;
+    k.h = (T)s.h;
+    k.safety_radius = (T)s.safety_radius;
+    k.max_dist_from_goal = (T)s.max_dist_from_goal;
+    k.max_attitude = (T)s.max_attitude;
+    k.dist_goal_reached_tol = (T)s.dist_goal_reached_tol;
+    k.u_max = (T)s.u_max; k.v_max = (T)s.v_max; k.w_max = (T)s.w_max;
+    k.p_max = (T)s.p_max; k.q_max = (T)s.q_max; k.r_max = (T)s.r_max;
+    k.log_den_obs = (T)std::log(s.dist_goal_reached_tol / s.max_dist_from_goal);
+    k.log_den_rew = (T)std::log(std::fmax(s.dist_goal_reached_tol, 0.001) / s.max_dist_from_goal);
+    k.w_d = (T)s.w_d; k.w_delta_psi = (T)s.w_delta_psi; k.w_delta_theta = (T)s.w_delta_theta;
+    k.w_phi = (T)s.w_phi; k.w_theta = (T)s.w_theta; k.w_Thetadot = (T)s.w_Thetadot; k.w_oa = (T)s.w_oa;
+    for (int i = 0; i < 5; i++) k.w_done[i] = (T)s.w_done[i];
+    k.cur_mu = (T)s.cur_mu;
+    k.cur_sigma = (T)s.cur_sigma;
+    k.has_noise = s.cur_sigma > 0.0;
+    k.radar_max_dist = (T)s.radar_max_dist;
+    double sb = 0.0;
+    for (int i = 0; i < s.n_rays; i++) {
+        for (int c = 0; c < 3; c++) k.rd_b[3 * i + c] = (T)s.rd_b[3 * i + c];
+        k.beta_oa[i] = (T)s.beta_oa[i];
+        sb += s.beta_oa[i];
+    }
+    k.sum_beta_oa = (T)sb;
+}
+
+extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device, DockauvHandle **out) {
+    if (!p || !out) return fail(DOCKAUV_EINVAL, "null argument");
+    *out = nullptr;
+    if (p->abi_version != DOCKAUV_ABI_VERSION)
+        return fail(DOCKAUV_EINVAL, "ABI version mismatch: caller %d, library %d", p->abi_version, DOCKAUV_ABI_VERSION);
+    if (n_envs <= 0) return fail(DOCKAUV_EINVAL, "n_envs must be positive");
+    if (p->precision != DOCKAUV_F64 && p->precision != DOCKAUV_F32) return fail(DOCKAUV_EINVAL, "bad precision");
+    if (p->vehicle == DOCKAUV_VEHICLE_BLUEROV2) {
+        if (p->n_u != 6 && p->n_u != 8) return fail(DOCKAUV_EINVAL, "BlueROV2 needs n_u = 6 (joystick) or 8 (direct)");
+    } else if (p->vehicle == DOCKAUV_VEHICLE_LAUV) {
+        if (p->n_u != 3) return fail(DOCKAUV_EINVAL, "LAUV needs n_u = 3");
+    } else {
+        return fail(DOCKAUV_EINVAL, "unknown vehicle %d", p->vehicle);
+    }
+    if (p->n_capsules < 0 || p->n_capsules > DOCKAUV_MAX_CAPSULES || p->n_spheres < 0 ||
+        p->n_spheres > DOCKAUV_MAX_SPHERES)
+        return fail(DOCKAUV_EINVAL, "obstacle counts out of range");
+    if (p->n_rays <= 0 || p->n_rays > DOCKAUV_MAX_RAYS || p->n_rays != p->n_vert * p->n_horiz || p->block_reduce <= 0)
+        return fail(DOCKAUV_EINVAL, "bad radar geometry (n_rays=%d, %d x %d, block %d)", p->n_rays, p->n_vert,
+                    p->n_horiz, p->block_reduce);
+    if (p->reward_set != 1 && p->reward_set != 2) return fail(DOCKAUV_EINVAL, "reward_set must be 1 or 2");
+    if (p->scenario < 0 || p->scenario > DOCKAUV_SCN_OBSTACLES_NOCAP) return fail(DOCKAUV_EINVAL, "bad scenario");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(DOCKAUV_ECUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(DOCKAUV_EINVAL, "device %d out of range (0..%d)", device, n_dev - 1);
+    DeviceGuard guard(device);
+    DockauvHandle *h = new (std::nothrow) DockauvHandle();
+    if (!h) return fail(DOCKAUV_EINVAL, "out of host memory");
+    h->params = *p;
+    h->n_envs = n_envs;
+    h->device = device;
+    h->n_obs = dockauv_n_obs(p);
+    fill_kparams<double>(*p, n_envs, h->kd);
+    fill_kparams<float>(*p, n_envs, h->kf);
+    // ray table in global memory: rd_b[3][n_rays] then beta_oa[n_rays], in the handle's precision
+    {
+        const int n = p->n_rays;
+        const size_t esz = p->precision == DOCKAUV_F64 ? 8 : 4;
+        std::vector<char> host(esz * 4 * n);
+        for (int i = 0; i < n; i++)
+            for (int c = 0; c < 4; c++) {
+                double v = c < 3 ? p->rd_b[3 * i + c] : p->beta_oa[i];
+                if (esz == 8) ((double *)host.data())[c * n + i] = v;
+                else ((float *)host.data())[c * n + i] = (float)v;
+            }
+        cudaError_t e1 = cudaMalloc(&h->ray_tab, host.size());
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMemcpy(h->ray_tab, host.data(), host.size(), cudaMemcpyHostToDevice) : e1;
+        cudaError_t e3 = e2 == cudaSuccess ? cudaMalloc((void **)&h->stats, sizeof(double) * DOCKAUV_N_STATS) : e2;
+        cudaError_t e4 = e3 == cudaSuccess ? cudaMemset(h->stats, 0, sizeof(double) * DOCKAUV_N_STATS) : e3;
+        if (e4 != cudaSuccess) {
+            if (h->ray_tab) cudaFree(h->ray_tab);
+            if (h->stats) cudaFree(h->stats);
+            delete h;
+            return fail(DOCKAUV_ECUDA, "device allocation failed: %s", cudaGetErrorString(e4));
+        }
+        h->kd.ray_tab = (const double *)h->ray_tab;
+        h->kf.ray_tab = (const float *)h->ray_tab;
+        h->kd.stats = h->stats;
+        h->kf.stats = h->stats;
+    }
+    *out = h;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_destroy(DockauvHandle *h) {
+    if (!h) return DOCKAUV_OK;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    if (h->ray_tab) cudaFree(h->ray_tab);
+    if (h->stats) cudaFree(h->stats);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int s = 0; s < kHostStreams; s++) {
+        if (h->hs[s]) cudaStreamDestroy(h->hs[s]);
+        if (h->hev[s]) cudaEventDestroy(h->hev[s]);
+    }
+    if (h->st_actions) cudaFree(h->st_actions);
+    if (h->st_obs) cudaFree(h->st_obs);
+    if (h->st_reward) cudaFree(h->st_reward);
+    if (h->st_done) cudaFree(h->st_done);
+    if (h->st_cond) cudaFree(h->st_cond);
+    delete h;
+    return DOCKAUV_OK;
+}
+
+template <typename T>
+static void bind_k(KParams<T> &k, const DockauvBuffers &b) {
+    k.state = (T *)b.state;
+    k.u_prev = (T *)b.u_prev;
+    k.goal = (T *)b.goal;
+    k.heading_goal = (T *)b.heading_goal;
+    k.current = (T *)b.current;
+    k.capsules = (T *)b.capsules;
+    k.spheres = (T *)b.spheres;
+    k.ep_return = (T *)b.ep_return;
+    k.t_steps = b.t_steps;
+    k.episode = b.episode;
+}
+
+extern "C" int dockauv_bind(DockauvHandle *h, const DockauvBuffers *b) {
+    if (!h || !b) return fail(DOCKAUV_EINVAL, "null argument");
+    if (!b->state || !b->u_prev || !b->goal || !b->heading_goal || !b->current || !b->ep_return || !b->t_steps ||
+        !b->episode)
+        return fail(DOCKAUV_EINVAL, "a required state buffer is null");
+    if ((h->params.n_capsules > 0 && !b->capsules) || (h->params.n_spheres > 0 && !b->spheres))
+        return fail(DOCKAUV_EINVAL, "obstacle buffer is null but the handle has obstacles");
+    bind_k<double>(h->kd, *b);
+    bind_k<float>(h->kf, *b);
+    h->bound = true;
+    return DOCKAUV_OK;
+}
+
+// ------------------------------------------------------------------------------------------- launch dispatch
+static bool scenario_has_current(int scn) {
+    return scn == DOCKAUV_SCN_SIMPLE_CURRENT || scn == DOCKAUV_SCN_CAPSULE_CURRENT || scn == DOCKAUV_SCN_OBSTACLES_CURRENT;
+}
+
+static int resolve_layout(const DockauvHandle *h) {
+    int layout = h->params.layout;
+    if (layout == DOCKAUV_LAYOUT_AUTO)
+        layout = (h->params.n_capsules + h->params.n_spheres) > 0 ? DOCKAUV_LAYOUT_WARP_RAYS
+                                                                  : DOCKAUV_LAYOUT_THREAD_PER_ENV;
+    return layout;
+}
+
+template <typename T>
+static void set_io(KParams<T> &k, const void *actions, bool act_f32, const void *noise, const DockauvStepOut &o,
+                   const DockauvDebugOut *d, int auto_reset) {
+    k.actions = actions;
+    k.noise = (const T *)noise;
+    k.obs = o.obs;
+    k.terminal_obs = o.terminal_obs;
+    k.reward = (T *)o.reward;
+    k.ep_return_out = (T *)o.ep_return_out;
+    k.done = o.done;
+    k.cond_bits = o.cond_bits;
+    k.ep_len_out = o.ep_len_out;
+    k.auto_reset = auto_reset ? 1 : 0;
+    k.act_f32 = act_f32 ? 1 : 0;
+    k.dbg_ray_dist = d ? (T *)d->ray_dist : nullptr;
+    k.dbg_reward_arr = d ? (T *)d->reward_arr : nullptr;
+    k.dbg_euler_dot = d ? (T *)d->euler_dot : nullptr;
+    k.dbg_nu_c = d ? (T *)d->nu_c : nullptr;
+    k.dbg_nav = d ? (T *)d->nav : nullptr;
+    k.dbg_obs = d ? (T *)d->obs_f64 : nullptr;
+}
+
+static int step_range(DockauvHandle *h, const void *actions, int action_dtype, const void *noise,
+                      const DockauvStepOut *out, const DockauvDebugOut *dbg, int auto_reset, int64_t begin,
+                      int64_t end, cudaStream_t st) {
+    const bool actf32 = action_dtype == DOCKAUV_ACT_F32;
+    const int layout = resolve_layout(h);
+    // the current is "on" when the scenario spawns one, the caller asked for it, or noise is configured
+    const bool has_current = scenario_has_current(h->params.scenario) || h->params.force_current != 0 ||
+                             h->params.cur_sigma > 0.0;
+    cudaError_t e;
+    if (h->params.precision == DOCKAUV_F64) {
+        KParams<double> k = h->kd;
+        set_io<double>(k, actions, actf32, noise, *out, dbg, auto_reset);
+        k.env_begin = begin;
+        k.env_end = end;
+        k.has_current = has_current;
+        e = launch_step<double>(k, h->params.vehicle, layout, st);
+    } else {
+        KParams<float> k = h->kf;
+        set_io<float>(k, actions, actf32, noise, *out, dbg, auto_reset);
+        k.env_begin = begin;
+        k.env_end = end;
+        k.has_current = has_current;
+        e = launch_step<float>(k, h->params.vehicle, layout, st);
+    }
+    if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_set_seed(DockauvHandle *h, uint64_t seed) {
+    if (!h) return fail(DOCKAUV_EINVAL, "null handle");
+    h->params.seed = seed;
+    h->kd.seed = seed;
+    h->kf.seed = seed;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_reset(DockauvHandle *h, const uint8_t *mask_dev, void *stream) {
+    if (!h) return fail(DOCKAUV_EINVAL, "null handle");
+    if (!h->bound) return fail(DOCKAUV_ESTATE, "dockauv_bind must be called before dockauv_reset");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->params.precision == DOCKAUV_F64) CUDA_TRY(launch_reset<double>(h->kd, mask_dev, st));
+    else CUDA_TRY(launch_reset<float>(h->kf, mask_dev, st));
+    h->launches += 1;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_step(DockauvHandle *h, const void *actions_dev, int action_dtype, const void *noise_dev,
+                            const DockauvStepOut *out, const DockauvDebugOut *dbg, int auto_reset, void *stream) {
+    if (!h || !actions_dev || !out) return fail(DOCKAUV_EINVAL, "null argument");
+    if (!h->bound) return fail(DOCKAUV_ESTATE, "dockauv_bind must be called before dockauv_step");
+    if (!out->obs || !out->reward || !out->done) return fail(DOCKAUV_EINVAL, "obs, reward and done outputs are required");
+    if (action_dtype != DOCKAUV_ACT_F32 && action_dtype != DOCKAUV_ACT_F64) return fail(DOCKAUV_EINVAL, "bad action dtype");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->timing) {
+        if (!h->ev0) {
+            CUDA_TRY(cudaEventCreate(&h->ev0));
+            CUDA_TRY(cudaEventCreate(&h->ev1));
+        }
+        CUDA_TRY(cudaEventRecord(h->ev0, st));
+    }
+    int rc = step_range(h, actions_dev, action_dtype, noise_dev, out, dbg, auto_reset, 0, h->n_envs, st);
+    if (rc != DOCKAUV_OK) return rc;
+    if (h->timing) {
+        CUDA_TRY(cudaEventRecord(h->ev1, st));
+        h->ev_valid = true;
+    }
+    return DOCKAUV_OK;
+}
+
+// ------------------------------------------------------------------------------------------- host-buffer step
+static int ensure_host_pipeline(DockauvHandle *h, size_t action_bytes) {
+    for (int s = 0; s < kHostStreams; s++) {
+        if (!h->hs[s]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hs[s], cudaStreamNonBlocking));
+        if (!h->hev[s]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev[s], cudaEventDisableTiming));
+    }
+    const size_t esz = h->params.precision == DOCKAUV_F64 ? 8 : 4;
+    if (h->st_actions_bytes < action_bytes) {
+        if (h->st_actions) CUDA_TRY(cudaFree(h->st_actions));
+        h->st_actions = nullptr;
+        CUDA_TRY(cudaMalloc(&h->st_actions, action_bytes));
+        h->st_actions_bytes = action_bytes;
+    }
+    if (!h->st_obs) CUDA_TRY(cudaMalloc((void **)&h->st_obs, sizeof(float) * h->n_obs * (size_t)h->n_envs));
+    if (!h->st_reward) CUDA_TRY(cudaMalloc(&h->st_reward, esz * (size_t)h->n_envs));
+    if (!h->st_done) CUDA_TRY(cudaMalloc((void **)&h->st_done, (size_t)h->n_envs));
+    if (!h->st_cond) CUDA_TRY(cudaMalloc((void **)&h->st_cond, (size_t)h->n_envs));
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_step_host(DockauvHandle *h, const void *actions_host, int action_dtype, float *obs_host,
+                                 void *reward_host, uint8_t *done_host, uint8_t *cond_bits_host, int auto_reset) {
+    if (!h || !actions_host || !obs_host || !reward_host || !done_host) return fail(DOCKAUV_EINVAL, "null argument");
+    if (!h->bound) return fail(DOCKAUV_ESTATE, "dockauv_bind must be called before dockauv_step_host");
+    if (action_dtype != DOCKAUV_ACT_F32 && action_dtype != DOCKAUV_ACT_F64) return fail(DOCKAUV_EINVAL, "bad action dtype");
+    DeviceGuard guard(h->device);
+    const int64_t N = h->n_envs;
+    const size_t asz = (action_dtype == DOCKAUV_ACT_F32 ? 4 : 8) * (size_t)h->params.n_u;
+    const size_t esz = h->params.precision == DOCKAUV_F64 ? 8 : 4;
+    int rc = ensure_host_pipeline(h, asz * (size_t)N);
+    if (rc != DOCKAUV_OK) return rc;
+    // chunks: multiples of 4096 envs, at most 12 per call so copies of chunk c+1 overlap the kernel of chunk c
+    int64_t chunk = (N + 11) / 12;
+    chunk = ((chunk + 4095) / 4096) * 4096;
+    if (chunk < 16384) chunk = 16384;
+    DockauvStepOut out;
+    memset(&out, 0, sizeof(out));
+    out.obs = h->st_obs;
+    out.reward = h->st_reward;
+    out.done = h->st_done;
+    out.cond_bits = h->st_cond;
+    int c = 0;
+    for (int64_t b = 0; b < N; b += chunk, c++) {
+        const int64_t e = b + chunk < N ? b + chunk : N;
+        cudaStream_t st = h->hs[c % kHostStreams];
+        CUDA_TRY(cudaMemcpyAsync((char *)h->st_actions + asz * b, (const char *)actions_host + asz * b, asz * (e - b),
+                                 cudaMemcpyHostToDevice, st));
+        rc = step_range(h, h->st_actions, action_dtype, nullptr, &out, nullptr, auto_reset, b, e, st);
+        if (rc != DOCKAUV_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(obs_host + (size_t)h->n_obs * b, h->st_obs + (size_t)h->n_obs * b,
+                                 sizeof(float) * h->n_obs * (e - b), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync((char *)reward_host + esz * b, (char *)h->st_reward + esz * b, esz * (e - b),
+                                 cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(done_host + b, h->st_done + b, (size_t)(e - b), cudaMemcpyDeviceToHost, st));
+        if (cond_bits_host)
+            CUDA_TRY(cudaMemcpyAsync(cond_bits_host + b, h->st_cond + b, (size_t)(e - b), cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kHostStreams; s++) CUDA_TRY(cudaStreamSynchronize(h->hs[s]));
+    return DOCKAUV_OK;
+}
+
+// ------------------------------------------------------------------------------------------- statistics
+extern "C" int dockauv_stats_ptr(DockauvHandle *h, double **stats_dev) {
+    if (!h || !stats_dev) return fail(DOCKAUV_EINVAL, "null argument");
+    *stats_dev = h->stats;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_get_stats(DockauvHandle *h, double *stats_host, void *stream) {
+    if (!h || !stats_host) return fail(DOCKAUV_EINVAL, "null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(stats_host, h->stats, sizeof(double) * DOCKAUV_N_STATS, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_clear_stats(DockauvHandle *h, void *stream) {
+    if (!h) return fail(DOCKAUV_EINVAL, "null handle");
+    DeviceGuard guard(h->device);
+    CUDA_TRY(cudaMemsetAsync(h->stats, 0, sizeof(double) * DOCKAUV_N_STATS, (cudaStream_t)stream));
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_launch_count(DockauvHandle *h, int64_t *n) {
+    if (!h || !n) return fail(DOCKAUV_EINVAL, "null argument");
+    *n = h->launches;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_enable_timing(DockauvHandle *h, int enabled) {
+    if (!h) return fail(DOCKAUV_EINVAL, "null handle");
+    h->timing = enabled != 0;
+    h->ev_valid = false;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_last_step_ms(DockauvHandle *h, float *ms) {
+    if (!h || !ms) return fail(DOCKAUV_EINVAL, "null argument");
+    if (!h->ev_valid) return fail(DOCKAUV_ESTATE, "no timed step recorded (dockauv_enable_timing + dockauv_step first)");
+    DeviceGuard guard(h->device);
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return DOCKAUV_OK;
+}
+
+// ------------------------------------------------------------------------------------------- roofline denominators
+template <typename T>
+__global__ void fma_peak_kernel(T *out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+            x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+        }
+    }
+    T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == (T)123456.789) out[0] = s;   // keeps the chains alive, never true in practice
+}
+
+template <typename T>
+static int measure_fma(double *tflops) {
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    T *out = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&out, sizeof(T)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int threads = 256, blocks = sms * 8, iters = 4096;
+    fma_peak_kernel<T><<<blocks, threads>>>(out, 64, (T)1.0000001, (T)1e-9);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        fma_peak_kernel<T><<<blocks, threads>>>(out, iters, (T)1.0000001, (T)1e-9);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_measure_peaks(int device, double *fp64_tflops, double *fp32_tflops, double *copy_gbs) {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev)
+        return fail(DOCKAUV_ECUDA, "no usable CUDA device %d", device);
+    DeviceGuard guard(device);
+    int rc;
+    if (fp64_tflops && (rc = measure_fma<double>(fp64_tflops)) != DOCKAUV_OK) return rc;
+    if (fp32_tflops && (rc = measure_fma<float>(fp32_tflops)) != DOCKAUV_OK) return rc;
+    if (copy_gbs) {
+        const size_t bytes = (size_t)1 << 30;
+        void *a = nullptr, *b = nullptr;
+        CUDA_TRY(cudaMalloc(&a, bytes));
+        CUDA_TRY(cudaMalloc(&b, bytes));
+        CUDA_TRY(cudaMemset(a, 1, bytes));
+        cudaEvent_t e0, e1;
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        double best = 0.0;
+        for (int rep = 0; rep < 6; rep++) {
+            CUDA_TRY(cudaEventRecord(e0));
+            CUDA_TRY(cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice));
+            CUDA_TRY(cudaEventRecord(e1));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            double gbs = 2.0 * (double)bytes / (ms * 1e-3) / 1e9;
+            if (rep > 0 && gbs > best) best = gbs;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(a);
+        cudaFree(b);
+        *copy_gbs = best;
+    }
+    return DOCKAUV_OK;
+}

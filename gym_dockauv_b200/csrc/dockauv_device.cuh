@@ -1,0 +1,384 @@
+// dockauv_device.cuh -- per-env device functions of the docking-AUV step (sm_100a).
+//
+// Formulation is matrix-free: the 6x6 Coriolis and damping matrices of the reference
+// (gym_dockauv/objects/statespace.py:199-351) are never materialised, C(nu) nu is four cross products, D(nu) nu
+// is a handful of FMAs, and the dead sixth Runge-Kutta stage (utils/odesolver45.py:23-27) is not evaluated.
+// Position does not feed back into the ODE right-hand side, so only Theta (3) and nu_r (6) carry stage
+// vectors; position is accumulated straight into the 4th-order result.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "dockauv_kparams.h"
+
+namespace dockauv {
+
+// ------------------------------------------------------------------------------------------- math traits
+template <typename T>
+struct Mth;
+
+template <>
+struct Mth<double> {
+    static constexpr double pi = 3.141592653589793;
+    static constexpr double two_pi = 6.283185307179586;
+    static constexpr double half_pi = 1.5707963267948966;
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
+    static __device__ __forceinline__ double nan() { return CUDART_NAN; }
+    static __device__ __forceinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double fmod_(double x, double y) { return fmod(x, y); }
+    static __device__ __forceinline__ double hypot_(double x, double y) { return hypot(x, y); }
+    static __device__ __forceinline__ double cos_(double x) { return cos(x); }
+    static __device__ __forceinline__ double sin_(double x) { return sin(x); }
+};
+
+template <>
+struct Mth<float> {
+    static constexpr float pi = 3.14159265358979f;
+    static constexpr float two_pi = 6.28318530717959f;
+    static constexpr float half_pi = 1.57079632679490f;
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+    static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
+    static __device__ __forceinline__ void sincos_(float x, float *s, float *c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float fmod_(float x, float y) { return fmodf(x, y); }
+    static __device__ __forceinline__ float hypot_(float x, float y) { return hypotf(x, y); }
+    static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
+    static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
+};
+
+// np.clip: minimum(maximum(x, lo), hi) -- NaN propagates
+template <typename T>
+__device__ __forceinline__ T clipv(T x, T lo, T hi) {
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+// geomutils.py:4-11  ssa(x) = (x + pi) % (2 pi) - pi with numpy's floor-mod.  For |x| < 3 pi the modulo is a
+// single conditional add/subtract (bit-identical to fmod there); the general path handles anything else.
+template <typename T>
+__device__ __forceinline__ T ssa(T x) {
+    const T pi = Mth<T>::pi, two_pi = Mth<T>::two_pi;
+    T a = x + pi;
+    if (Mth<T>::abs_(x) < T(9.0)) {
+        if (a >= two_pi) a -= two_pi;
+        else if (a < T(0)) a += two_pi;
+        return a - pi;
+    }
+    T mod = Mth<T>::fmod_(a, two_pi);
+    if (mod != T(0)) {
+        if (mod < T(0)) mod += two_pi;
+    } else {
+        mod = T(0);
+    }
+    return mod - pi;
+}
+
+// ------------------------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+// uniform double in [0,1): draw `idx` of the stream keyed by (seed, global env id, episode); one Philox block
+// yields two draws (even idx -> words 0,1; odd idx -> words 2,3).
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t idx) {
+    uint32_t c[4] = {(uint32_t)env_id, (uint32_t)(env_id >> 32), episode, idx >> 1};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t hi = (idx & 1) ? c[2] : c[0], lo = (idx & 1) ? c[3] : c[1];
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// standard normal from the per-step stream (Box-Muller); counter word 3 = 0x80000000 | t_steps keeps it apart
+// from the reset stream of the same episode.
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t t_steps) {
+    uint32_t c[4] = {(uint32_t)env_id, (uint32_t)(env_id >> 32), episode, 0x80000000u | t_steps};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    double u1 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6) + 1.0) * (1.0 / 9007199254740992.0);
+    double u2 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+}
+
+// ------------------------------------------------------------------------------------------- dynamics
+template <typename T>
+__device__ __forceinline__ void cross3(const T a[3], const T b[3], T o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// Kinetic part of auvsim.py:152-158:  nu_dot = M^-1 (B(nu) u - D(nu) nu - C(nu) nu - G(eta)).
+//   tau : BlueROV2 -> precomputed B u (B is constant, BlueROV2.py:74-75); LAUV -> the low-passed command u[3]
+//   sphi, cphi, sth, cth : sin/cos of roll and pitch
+template <typename T, int VEH>
+__device__ __forceinline__ void nu_dot(const KParams<T> &p, const T nu[6], const T tau[6], T sphi, T cphi, T sth,
+                                       T cth, T out[6]) {
+    const T *n1 = nu, *n2 = nu + 3;
+    T f[6];
+    // control forces
+    if (VEH == DOCKAUV_VEHICLE_BLUEROV2) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) f[i] = tau[i];
+    } else {   // LAUV.py:59-67
+        T u2 = nu[0] * nu[0];
+        f[0] = tau[0];
+        f[1] = p.lauv_B[0] * u2 * tau[1];
+        f[2] = p.lauv_B[1] * u2 * tau[2];
+        f[3] = T(0);
+        f[4] = p.lauv_B[2] * u2 * tau[2];
+        f[5] = p.lauv_B[3] * u2 * tau[1];
+    }
+    // D(nu) nu, statespace.py:337-351 / LAUV.py:69-101.  D[i][j] = -(lin + quad |nu_j| + lift |u|)
+    {
+        T an[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) an[i] = Mth<T>::abs_(nu[i]);
+        T d[6];
+        if (VEH == DOCKAUV_VEHICLE_BLUEROV2) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) d[i] = -(p.D_lin[i] + p.D_quad[i] * an[i]) * nu[i];
+        } else {
+            T au = an[0];
+#pragma unroll
+            for (int i = 0; i < 6; i++) d[i] = -(p.D_lin[i] + p.D_quad[i] * an[i] + p.D_lift[i] * au) * nu[i];
+            d[1] += -(p.D_lin[6] + p.D_quad[6] * an[5] + p.D_lift[6] * au) * nu[5];
+            d[2] += -(p.D_lin[7] + p.D_quad[7] * an[4] + p.D_lift[7] * au) * nu[4];
+            d[4] += -(p.D_lin[8] + p.D_quad[8] * an[2] + p.D_lift[8] * au) * nu[2];
+            d[5] += -(p.D_lin[9] + p.D_quad[9] * an[1] + p.D_lift[9] * au) * nu[1];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) f[i] -= d[i];
+    }
+    // C(nu) nu = C_RB nu + C_A nu, statespace.py:224-227, 271-274
+    {
+        T c1[3], rgn2[3], t[3], rgc1[3], ibn2[3], t2[3];
+        cross3(n2, n1, c1);                 // nu2 x nu1
+        cross3(p.r_G, n2, rgn2);            // r_G x nu2
+        cross3(n2, rgn2, t);                // nu2 x (r_G x nu2)
+        cross3(p.r_G, c1, rgc1);            // r_G x (nu2 x nu1)
+#pragma unroll
+        for (int i = 0; i < 3; i++) ibn2[i] = p.I_b[3 * i] * n2[0] + p.I_b[3 * i + 1] * n2[1] + p.I_b[3 * i + 2] * n2[2];
+        cross3(ibn2, n2, t2);               // (I_b nu2) x nu2
+        T a1[3] = {p.MA[0] * n1[0], p.MA[1] * n1[1], p.MA[2] * n1[2]};
+        T a2[3] = {p.MA[3] * n2[0], p.MA[4] * n2[1], p.MA[5] * n2[2]};
+        T a1n2[3], a1n1[3], a2n2[3];
+        cross3(a1, n2, a1n2);
+        cross3(a1, n1, a1n1);
+        cross3(a2, n2, a2n2);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            f[i] -= p.m * (c1[i] - t[i]) - a1n2[i];
+            f[3 + i] -= p.m * rgc1[i] - t2[i] - a1n1[i] - a2n2[i];
+        }
+    }
+    // G(eta), statespace.py:387-396
+    {
+        T cc = cth * cphi, cs = cth * sphi;
+        f[0] -= p.G_WB * sth;
+        f[1] -= -p.G_WB * cs;
+        f[2] -= -p.G_WB * cc;
+        f[3] -= -p.G_r[1] * cc + p.G_r[2] * cs;
+        f[4] -= p.G_r[2] * sth + p.G_r[0] * cc;
+        f[5] -= -p.G_r[0] * cs - p.G_r[1] * sth;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        T s = p.M_inv[6 * i] * f[0];
+#pragma unroll
+        for (int k = 1; k < 6; k++) s += p.M_inv[6 * i + k] * f[k];
+        out[i] = s;
+    }
+}
+
+// Rzyx (geomutils.py:40-43) from precomputed sines / cosines, row-major
+template <typename T>
+__device__ __forceinline__ void rzyx(T sphi, T cphi, T sth, T cth, T spsi, T cpsi, T R[9]) {
+    R[0] = cpsi * cth; R[1] = -spsi * cphi + cpsi * sth * sphi; R[2] = spsi * sphi + cpsi * cphi * sth;
+    R[3] = spsi * cth; R[4] = cpsi * cphi + sphi * sth * spsi;  R[5] = -cpsi * sphi + sth * spsi * cphi;
+    R[6] = -sth;       R[7] = cth * sphi;                       R[8] = cth * cphi;
+}
+
+// One evaluation of the reduced right-hand side (auvsim.py:110-160) at y = (Theta, nu_r).
+//   k[0:3] = T(phi, theta) nu2 (geomutils.py:72-75), k[3:9] = nu_dot;  if WPOS, pacc += wpos * R(Theta) (nu1 + nu_c).
+template <typename T, int VEH, bool WPOS>
+__device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T tau[6], const T nu_c[3], T wpos,
+                                     T pacc[3], T k[9]) {
+    T sphi, cphi, sth, cth;
+    Mth<T>::sincos_(y[0], &sphi, &cphi);
+    Mth<T>::sincos_(y[1], &sth, &cth);
+    const T *nu = y + 3;
+    T inv_cth = T(1) / cth;
+    T tth = sth * inv_cth;
+    T qs = sphi * nu[4] + cphi * nu[5];
+    k[0] = nu[3] + tth * qs;
+    k[1] = cphi * nu[4] - sphi * nu[5];
+    k[2] = qs * inv_cth;
+    if (WPOS) {
+        T spsi, cpsi, R[9];
+        Mth<T>::sincos_(y[2], &spsi, &cpsi);
+        rzyx(sphi, cphi, sth, cth, spsi, cpsi, R);
+        T v[3] = {nu[0] + nu_c[0], nu[1] + nu_c[1], nu[2] + nu_c[2]};
+#pragma unroll
+        for (int i = 0; i < 3; i++) pacc[i] += wpos * (R[3 * i] * v[0] + R[3 * i + 1] * v[1] + R[3 * i + 2] * v[2]);
+    }
+    nu_dot<T, VEH>(p, nu, tau, sphi, cphi, sth, cth, k + 3);
+}
+
+// utils/odesolver45.py:18-26 on the reduced state; the 4th-order result is written back to pos / y.
+template <typename T, int VEH>
+__device__ __forceinline__ void rkf45_step(const KParams<T> &p, T pos[3], T y[9], const T tau[6], const T nu_c[3]) {
+    const T h = p.h;
+    T k1[9], k2[9], k3[9], k4[9], k5[9], yt[9];
+    T pacc[3] = {T(0), T(0), T(0)};
+    rhs9<T, VEH, true>(p, y, tau, nu_c, h * T(25.0 / 216.0), pacc, k1);
+    {
+        const T a = h * T(0.25);
+#pragma unroll
+        for (int i = 0; i < 9; i++) yt[i] = y[i] + a * k1[i];
+    }
+    rhs9<T, VEH, false>(p, yt, tau, nu_c, T(0), pacc, k2);   // b2 = 0: no position contribution
+    {
+        const T a = h * T(3.0 / 32.0), b = h * T(9.0 / 32.0);
+#pragma unroll
+        for (int i = 0; i < 9; i++) yt[i] = y[i] + a * k1[i] + b * k2[i];
+    }
+    rhs9<T, VEH, true>(p, yt, tau, nu_c, h * T(1408.0 / 2565.0), pacc, k3);
+    {
+        const T a = h * T(1932.0 / 2197.0), b = h * T(-7200.0 / 2197.0), c = h * T(7296.0 / 2197.0);
+#pragma unroll
+        for (int i = 0; i < 9; i++) yt[i] = y[i] + a * k1[i] + b * k2[i] + c * k3[i];
+    }
+    rhs9<T, VEH, true>(p, yt, tau, nu_c, h * T(2197.0 / 4104.0), pacc, k4);
+    {
+        const T a = h * T(439.0 / 216.0), b = h * T(-8.0), c = h * T(3680.0 / 513.0), d = h * T(-845.0 / 4104.0);
+#pragma unroll
+        for (int i = 0; i < 9; i++) yt[i] = y[i] + a * k1[i] + b * k2[i] + c * k3[i] + d * k4[i];
+    }
+    rhs9<T, VEH, true>(p, yt, tau, nu_c, h * T(-1.0 / 5.0), pacc, k5);
+    {
+        const T a = h * T(25.0 / 216.0), c = h * T(1408.0 / 2565.0), d = h * T(2197.0 / 4104.0), e = h * T(-1.0 / 5.0);
+#pragma unroll
+        for (int i = 0; i < 9; i++) y[i] = y[i] + (a * k1[i] + c * k3[i] + d * k4[i] + e * k5[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) pos[i] += pacc[i];
+}
+
+// ------------------------------------------------------------------------------------------- radar geometry
+// Ray-independent part of the ray/capsule test (all rays of one env share the origin, sensor.py:123-129).
+template <typename T>
+struct CapPre {
+    T ba[3], oa[3], oc2[3];   // top-bot, pos-bot, pos-top
+    T baba, baoa, c, c2a, c2b, r;
+};
+
+template <typename T>
+__device__ __forceinline__ void capsule_pre(const T pos[3], const T bot[3], const T top[3], T r, CapPre<T> &q) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        q.ba[i] = top[i] - bot[i];
+        q.oa[i] = pos[i] - bot[i];
+        q.oc2[i] = pos[i] - top[i];
+    }
+    q.baba = q.ba[0] * q.ba[0] + q.ba[1] * q.ba[1] + q.ba[2] * q.ba[2];
+    q.baoa = q.oa[0] * q.ba[0] + q.oa[1] * q.ba[1] + q.oa[2] * q.ba[2];
+    T oaoa = q.oa[0] * q.oa[0] + q.oa[1] * q.oa[1] + q.oa[2] * q.oa[2];
+    T r2 = r * r;
+    q.c = q.baba * oaoa - q.baoa * q.baoa - r2 * q.baba;
+    q.c2a = oaoa - r2;
+    q.c2b = q.oc2[0] * q.oc2[0] + q.oc2[1] * q.oc2[1] + q.oc2[2] * q.oc2[2] - r2;
+    q.r = r;
+}
+
+// shape.py:341-390 for one ray: infinite-cylinder root, body hit if 0 < y < baba, else end-cap sphere.
+// Returns -inf for "no intersection" and a negative distance for "behind" exactly like the reference.
+template <typename T>
+__device__ __forceinline__ T ray_capsule(const CapPre<T> &q, const T rd[3]) {
+    T bard = rd[0] * q.ba[0] + rd[1] * q.ba[1] + rd[2] * q.ba[2];
+    T rdoa = rd[0] * q.oa[0] + rd[1] * q.oa[1] + rd[2] * q.oa[2];
+    T a = q.baba - bard * bard;
+    T b = q.baba * rdoa - q.baoa * bard;
+    T h = b * b - a * q.c;
+    T res = -Mth<T>::inf();
+    if (h > T(0)) {
+        T t = (-b - Mth<T>::sqrt_(h)) / a;
+        T y = q.baoa + t * bard;
+        if (y > T(0) && y < q.baba) {
+            res = t;
+        } else {
+            T b2, c2;
+            if (y >= T(0)) {
+                b2 = rd[0] * q.oc2[0] + rd[1] * q.oc2[1] + rd[2] * q.oc2[2];
+                c2 = q.c2b;
+            } else if (y <= T(0)) {
+                b2 = rdoa;
+                c2 = q.c2a;
+            } else {   // y is NaN: the reference leaves oc = 0
+                b2 = T(0);
+                c2 = -q.r * q.r;
+            }
+            T h2 = b2 * b2 - c2;
+            res = (h2 > T(0)) ? (-b2 - Mth<T>::sqrt_(h2)) : T(0);
+        }
+        if (res == T(0)) res = -Mth<T>::inf();
+    }
+    return res;
+}
+
+// shape.py:252-263 for one ray and one sphere: nearest root, -inf if the line misses
+template <typename T>
+__device__ __forceinline__ T ray_sphere(const T oc[3], T c, const T rd[3]) {
+    T b = oc[0] * rd[0] + oc[1] * rd[1] + oc[2] * rd[2];
+    T h = b * b - c;
+    return (h < T(0)) ? -Mth<T>::inf() : (-b - Mth<T>::sqrt_(h));
+}
+
+// shape.py:393-417 dist_line_point(po, l1, l2) with l1 = bot, l2 = top
+template <typename T>
+__device__ __forceinline__ T dist_segment_point(const T pos[3], const T bot[3], const T top[3]) {
+    T l[3] = {top[0] - bot[0], top[1] - bot[1], top[2] - bot[2]};
+    T n = Mth<T>::sqrt_(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    T d[3] = {l[0] / n, l[1] / n, l[2] / n};
+    T s = (bot[0] - pos[0]) * d[0] + (bot[1] - pos[1]) * d[1] + (bot[2] - pos[2]) * d[2];
+    T t = (pos[0] - top[0]) * d[0] + (pos[1] - top[1]) * d[1] + (pos[2] - top[2]) * d[2];
+    T hh = s;
+    if (t > hh || t != t) hh = t;
+    if (T(0) > hh) hh = T(0);
+    T q[3] = {pos[0] - bot[0], pos[1] - bot[1], pos[2] - bot[2]};
+    T c[3];
+    cross3(q, d, c);
+    return Mth<T>::hypot_(hh, Mth<T>::sqrt_(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]));
+}
+
+// docking3d.py:712-723 given lg = log(x / x_max) (shared with observe()) -- the epsilon guard only matters
+// when x < 1e-3
+template <typename T>
+__device__ __forceinline__ T log_precision(T x, T x_max, T log_den) {
+    T xx = (x != x) ? x : (x > T(0.001) ? x : T(0.001));
+    return T(1) - clipv(Mth<T>::log_(xx / x_max) / log_den, T(0), T(1));
+}
+
+// docking3d.py:742-765 with x_des = 0, exponents 4, no reversal (call sites :523-548, :571-582)
+template <typename T>
+__device__ __forceinline__ T cont_goal_constraints(T x, T x_max, T lp_delta_d) {
+    T log_den_x = Mth<T>::log_(T(0.001) / x_max);
+    T rx = Mth<T>::abs_(T(0) - log_precision(x, x_max, log_den_x));
+    T rd = Mth<T>::abs_(T(0) - lp_delta_d);
+    T rx2 = rx * rx, rd2 = rd * rd;
+    return (rx2 * rx2) * (rd2 * rd2);
+}
+
+}  // namespace dockauv

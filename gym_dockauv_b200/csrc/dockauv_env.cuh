@@ -1,0 +1,206 @@
+// dockauv_env.cuh -- env-level pieces shared by the step kernels: reset, command filter, current, the
+// non-radar part of observe / is_done / reward_step, episode statistics.
+#pragma once
+#include "dockauv_device.cuh"
+
+namespace dockauv {
+
+// ------------------------------------------------------------------------------------------- reset
+// BaseDocking3d.reset (docking3d.py:222-322) + <Scenario>.generate_environment (:803-988) for env i.
+// Distributions are the reference's; the random stream is Philox4x32-10 keyed by (seed, global env id,
+// episode) instead of the reference's global MT19937 (DESIGN.md "reset").  Draw slots: 0 heading, 1-3
+// position, 4-6 attitude, 7 goal angle, 8 goal depth, 9 pillar phase, 10-11 current direction, 12 current
+// speed, 13+3s.. synthetic sphere s.
+template <typename T>
+__device__ void reset_env(const KParams<T> &p, int64_t i) {
+    const int64_t N = p.n_envs;
+    const uint64_t gid = p.env_id0 + (uint64_t)i;
+    const uint32_t ep = (uint32_t)p.episode[i];
+    p.episode[i] = (int32_t)(ep + 1);
+    const double PI = 3.141592653589793;
+    auto U = [&](uint32_t idx) { return philox_uniform(p.seed, gid, ep, idx); };
+
+    double goal[3] = {0.0, 0.0, 0.0};
+    double heading = (U(0) - 0.5) * PI;                                   // :814
+    double r[3] = {U(1) - 0.5, U(2) - 0.5, U(3) - 0.5};                   // :694-696
+    {
+        double sg = (r[2] > 0.0) - (r[2] < 0.0);
+        r[2] = fabs(r[0] + r[1]) / 3 * sg;
+    }
+    double sc = 15.0 / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    double pos[3] = {r[0] * sc, r[1] * sc, r[2] * sc};
+    double max_att = (double)p.max_attitude;
+    double att[3] = {(U(4) - 0.5) * 2 * (max_att * 0.7), (U(5) - 0.5) * 2 * (max_att * 0.7),
+                     (U(6) - 0.5) * 2 * PI};                               // :699-703
+    const int scn = p.scenario;
+    int kc = 0;
+    if (scn >= DOCKAUV_SCN_CAPSULE) {                                      // :860-886
+        double theta = U(7) * 2 * PI;
+        double radius = 1.0 + (double)p.safety_radius;
+        double s, c;
+        sincos(theta, &s, &c);
+        goal[0] = c * radius;
+        goal[1] = s * radius;
+        goal[2] = (U(8) - 0.5) * 4.0;
+        // vec_line_point(goal, top=(0,0,-2), bot=(0,0,2)) = (-gx, -gy, 0)  (shape.py:420-433)
+        heading = (double)ssa<double>(atan2(0.0 - goal[1], 0.0 - goal[0]));
+        if (scn != DOCKAUV_SCN_OBSTACLES_NOCAP && kc < p.n_caps) {
+            const double cap[7] = {0, 0, 2.0, 0, 0, -2.0, 1.0};          // bot = 2*position - top, shape.py:105-108
+#pragma unroll
+            for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+            kc++;
+        }
+    }
+    if (scn >= DOCKAUV_SCN_OBSTACLES) {                                    // :919-946
+        double theta = U(9) * 2 * PI;
+        double half = 2.0 * (double)p.max_dist_from_goal / 2.0;
+        for (int k = 0; k < 4 && kc < p.n_caps; k++) {
+            double s, c;
+            sincos(theta, &s, &c);
+            double x = c * 6, y = s * 6;
+            theta += 2 * PI / 4;
+            const double cap[7] = {x, y, half, x, y, -half, 1.0};
+#pragma unroll
+            for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+            kc++;
+        }
+    }
+    for (; kc < p.n_caps; kc++) {   // unused capsule slots: park far away with zero radius (never hit, never collide)
+        const double cap[7] = {1e6, 1e6, 1e6, 1e6, 1e6, 1e6 + 1.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+    }
+    double cur[5] = {0, 0, 0, 0, 0};
+    if (scn == DOCKAUV_SCN_SIMPLE_CURRENT || scn == DOCKAUV_SCN_CAPSULE_CURRENT || scn == DOCKAUV_SCN_OBSTACLES_CURRENT) {
+        cur[1] = (U(10) - 0.5) * 2 * (PI / 2);                             // :843-848, :903-907, :983-987
+        cur[2] = (U(11) - 0.5) * 2 * PI;
+        double speed = (scn == DOCKAUV_SCN_SIMPLE_CURRENT) ? U(12) * 1.0 : 0.5;
+        cur[0] = 0.5;
+        cur[3] = cur[4] = speed;
+    }
+    int ks = 0;
+    for (; ks < p.n_synth_sph && ks < p.n_sph; ks++) {   // BASELINE C4 extension: random unit spheres
+        double z = 2 * U(13 + 3 * ks) - 1;
+        double az = 2 * PI * U(14 + 3 * ks);
+        double rr = 4.0 + 6.0 * U(15 + 3 * ks);
+        double q = sqrt(1 - z * z), s, c;
+        sincos(az, &s, &c);
+        p.spheres[(int64_t)(ks * 4 + 0) * N + i] = (T)(rr * q * c);
+        p.spheres[(int64_t)(ks * 4 + 1) * N + i] = (T)(rr * q * s);
+        p.spheres[(int64_t)(ks * 4 + 2) * N + i] = (T)(rr * z);
+        p.spheres[(int64_t)(ks * 4 + 3) * N + i] = (T)1.0;
+    }
+    for (; ks < p.n_sph; ks++) {
+        p.spheres[(int64_t)(ks * 4 + 0) * N + i] = (T)1e6;
+        p.spheres[(int64_t)(ks * 4 + 1) * N + i] = (T)1e6;
+        p.spheres[(int64_t)(ks * 4 + 2) * N + i] = (T)1e6;
+        p.spheres[(int64_t)(ks * 4 + 3) * N + i] = (T)0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        p.state[(int64_t)c * N + i] = (T)pos[c];
+        p.state[(int64_t)(3 + c) * N + i] = (T)att[c];
+        p.goal[(int64_t)c * N + i] = (T)goal[c];
+    }
+#pragma unroll
+    for (int c = 6; c < 12; c++) p.state[(int64_t)c * N + i] = T(0);     // auvsim.py:55-65
+    for (int k = 0; k < p.n_u; k++) p.u_prev[(int64_t)k * N + i] = T(0);
+    p.heading_goal[i] = (T)heading;
+#pragma unroll
+    for (int c = 0; c < 5; c++) p.current[(int64_t)c * N + i] = (T)cur[c];
+    p.t_steps[i] = 0;
+    p.ep_return[i] = T(0);
+}
+
+template <typename T>
+__global__ void reset_kernel(const __grid_constant__ KParams<T> p, const uint8_t *mask) {
+    int64_t i = p.env_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.env_end) return;
+    if (mask != nullptr && mask[i] == 0) return;
+    reset_env<T>(p, i);
+}
+
+// ------------------------------------------------------------------------------------------- step pieces
+// Everything the non-radar part of one step hands to the radar / finalisation part.
+template <typename T>
+struct StepCarry {
+    T pos[3];          // post-step position
+    T R[9];            // post-step Rzyx
+    T partial_reward;  // reward terms that do not depend on the radar or the collision flag, summed later
+    T rarr[13];        // reward_arr (only [0..5], [7] filled here)
+    uint32_t cond;     // bits 0..3
+    T delta_d;
+};
+
+// action -> low-passed command (auvsim.py:67-87, lowpassfilter.py:29-42) and the action penalty
+// (docking3d.py:584-585).  Returns -(sum((|a|/n_u)^2 * w)).
+template <typename T, int NU>
+__device__ __forceinline__ T command_and_penalty(const KParams<T> &p, int64_t i, T u[NU]) {
+    const int64_t N = p.n_envs;
+    T pen;
+    if (p.act_f32) {
+        const float *a = (const float *)p.actions + i * NU;
+        float pen32 = 0.0f;
+        double pen64 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NU; k++) {
+            float ak = a[k];
+            float c = ak < -1.0f ? -1.0f : (ak > 1.0f ? 1.0f : ak);
+            float frac = (c + 1.0f) / 2.0f;                       // numpy keeps this in float32
+            T x = p.u_lo[k] + p.u_span[k] * (T)frac;
+            T up = p.u_prev[(int64_t)k * N + i];
+            u[k] = p.lp_alpha * x + (T(1) - p.lp_alpha) * up;
+            // numpy evaluates (|a| / n_u) ** 2 * w and the sum in float32 with one rounding per operation:
+            // explicit _rn intrinsics keep the compiler from contracting them into FMAs
+            float q = __fdiv_rn(fabsf(ak), (float)NU);
+            q = __fmul_rn(q, q);
+            pen32 = __fadd_rn(pen32, __fmul_rn(q, p.arf_f32[k]));
+            pen64 += (double)q * (double)p.arf[k];
+        }
+        pen = p.action_factor_is_scalar ? (T)pen32 : (T)pen64;
+    } else {
+        const double *a = (const double *)p.actions + i * NU;
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < NU; k++) {
+            T ak = (T)a[k];
+            T frac = (clipv(ak, T(-1), T(1)) + T(1)) / T(2);
+            T x = p.u_lo[k] + p.u_span[k] * frac;
+            T up = p.u_prev[(int64_t)k * N + i];
+            u[k] = p.lp_alpha * x + (T(1) - p.lp_alpha) * up;
+            T q = Mth<T>::abs_(ak) / T(NU);
+            s += (q * q) * p.arf[k];
+        }
+        pen = s;
+    }
+    return -pen;
+}
+
+// np.sum over the 13 reward terms in numpy's pairwise order for n = 13 (8 unrolled accumulators combined
+// as a tree, then the 5 remaining terms added sequentially).
+template <typename T>
+__device__ __forceinline__ T reward_sum13(const T r[13]) {
+    T s = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (int k = 8; k < 13; k++) s += r[k];
+    return s;
+}
+
+// block-level episode statistics: shared accumulators, one global atomic per statistic per block
+struct BlockStats {
+    double *s;   // shared double[DOCKAUV_N_STATS]
+    __device__ __forceinline__ void init() {
+        if (threadIdx.x < DOCKAUV_N_STATS) s[threadIdx.x] = 0.0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void add(int k, double v) { atomicAdd(&s[k], v); }
+    // n_steps = env-steps this block performed (added once per block, not per thread)
+    __device__ __forceinline__ void flush(double *g, int n_steps) {
+        __syncthreads();
+        if (threadIdx.x == 0) s[DOCKAUV_STAT_ENV_STEPS] = (double)n_steps;
+        __syncthreads();
+        if (threadIdx.x < DOCKAUV_N_STATS && s[threadIdx.x] != 0.0) atomicAdd(&g[threadIdx.x], s[threadIdx.x]);
+    }
+};
+
+}  // namespace dockauv

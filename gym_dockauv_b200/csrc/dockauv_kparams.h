@@ -1,0 +1,61 @@
+// dockauv_kparams.h -- device-side parameter block (passed by value as a __grid_constant__ kernel argument, so
+// every field sits in the constant bank and uniform reads broadcast to the whole warp).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/dockauv.h"
+
+namespace dockauv {
+
+template <typename T>
+struct KParams {
+    // sizes / switches
+    int64_t n_envs;
+    int64_t env_begin, env_end;   // half-open range of envs this launch works on (chunked host pipeline)
+    int32_t n_u, n_caps, n_sph, n_synth_sph, scenario;
+    int32_t max_timesteps, reward_set;
+    int32_t n_rays, n_vert, n_horiz, block, n_hr, n_rr, n_obs;   // n_hr = pooled columns, n_rr = pooled rays
+    int32_t action_factor_is_scalar, auto_reset, has_current, has_noise, act_f32;
+    uint64_t seed, env_id0;
+    // vehicle
+    T m, r_G[3], I_b[9], MA[6], M_inv[36];
+    T D_lin[10], D_quad[10], D_lift[10];
+    T G_WB, G_r[3];
+    T B[6 * DOCKAUV_MAX_U];
+    T lauv_B[4];
+    T u_lo[DOCKAUV_MAX_U], u_span[DOCKAUV_MAX_U];   // u_span = u_hi - u_lo
+    T lp_alpha, h, safety_radius;
+    // env
+    T max_dist_from_goal, max_attitude, dist_goal_reached_tol;
+    T inv_u_max, u_max, v_max, w_max, p_max, q_max, r_max;
+    T log_den_obs;    // log(dist_goal_reached_tol / max_dist_from_goal), docking3d.py:465-466
+    T log_den_rew;    // log(max(tol, 1e-3) / max_dist), docking3d.py:723
+    T w_d, w_delta_psi, w_delta_theta, w_phi, w_theta, w_Thetadot, w_oa;
+    T w_done[5];
+    T arf[DOCKAUV_MAX_U];
+    float arf_f32[DOCKAUV_MAX_U];
+    T cur_mu, cur_sigma;
+    T radar_max_dist, sum_beta_oa;
+    // persistent state (SoA, env fastest)
+    T *state, *u_prev, *goal, *heading_goal, *current, *capsules, *spheres, *ep_return;
+    int32_t *t_steps, *episode;
+    // inputs
+    const void *actions;
+    const T *noise;
+    // outputs
+    float *obs, *terminal_obs;
+    T *reward, *ep_return_out;
+    uint8_t *done, *cond_bits;
+    int32_t *ep_len_out;
+    // debug outputs
+    T *dbg_ray_dist, *dbg_reward_arr, *dbg_euler_dot, *dbg_nu_c, *dbg_nav, *dbg_obs;
+    // stats accumulator (double[DOCKAUV_N_STATS])
+    double *stats;
+    // ray table in global memory (lane-indexed reads in the warp layout): rd_b[3][n_rays], beta_oa[n_rays]
+    const T *ray_tab;
+    // ray table in the constant bank (uniform reads in the thread-per-env layout)
+    T rd_b[DOCKAUV_MAX_RAYS * 3];
+    T beta_oa[DOCKAUV_MAX_RAYS];
+};
+
+}  // namespace dockauv

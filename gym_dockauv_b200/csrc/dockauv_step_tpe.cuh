@@ -1,0 +1,356 @@
+// dockauv_step_tpe.cuh -- layout DOCKAUV_LAYOUT_THREAD_PER_ENV: one thread carries one env through the whole
+// step (docking3d.py:346-402).  Ray directions and every constant come from the constant bank (uniform
+// reads); per-env capsule pre-computations live in a small local array.  This is the simple layout used for
+// scenarios without obstacles (BASELINE config C2) and as the cross-check of the warp-cooperative radar layout.
+#pragma once
+#include "dockauv_env.cuh"
+
+namespace dockauv {
+
+// Dynamics + everything that does not need the radar.  Shared by both layouts.
+//   returns false for an env index beyond the batch.
+template <typename T, int VEH, int NU>
+__device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T &spsi_out, T &cpsi_out,
+                                              float obs16[16], T att_out[3]) {
+    const int64_t N = p.n_envs;
+    T pos[3], y[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
+#pragma unroll
+    for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
+
+    // ---- ocean current: Current.sim (current.py:78-96) then nu_c from the PRE-step attitude (docking3d.py:348-349)
+    T nu_c[3] = {T(0), T(0), T(0)};
+    if (p.has_current) {
+        T Vc = p.current[i];
+        T alpha = p.current[N + i], beta = p.current[2 * N + i];
+        T vmin = p.current[3 * N + i], vmax = p.current[4 * N + i];
+        T w = T(0);
+        if (p.has_noise) {
+            w = (p.noise != nullptr) ? p.noise[i]
+                                     : (T)((double)p.cur_sigma *
+                                           philox_normal(p.seed, p.env_id0 + (uint64_t)i, (uint32_t)p.episode[i],
+                                                         (uint32_t)p.t_steps[i]));
+        }
+        T Vc_dot = -p.cur_mu * Vc + w;
+        Vc = Vc + Vc_dot * p.h;
+        Vc = clipv(Vc, vmin, vmax);
+        p.current[i] = Vc;
+        T sa, ca, sb, cb;
+        Mth<T>::sincos_(alpha, &sa, &ca);
+        Mth<T>::sincos_(beta, &sb, &cb);
+        T vn[3] = {Vc * ca * cb, Vc * sb, Vc * sa * cb};                 // current.py:71-73
+        T s0, c0, s1, c1, s2, c2, R[9];
+        Mth<T>::sincos_(y[0], &s0, &c0);
+        Mth<T>::sincos_(y[1], &s1, &c1);
+        Mth<T>::sincos_(y[2], &s2, &c2);
+        rzyx(s0, c0, s1, c1, s2, c2, R);
+#pragma unroll
+        for (int c = 0; c < 3; c++) nu_c[c] = R[c] * vn[0] + R[3 + c] * vn[1] + R[6 + c] * vn[2];   // R^T v
+    }
+
+    // ---- command
+    T u[NU];
+    T penalty = command_and_penalty<T, NU>(p, i, u);
+#pragma unroll
+    for (int k = 0; k < NU; k++) p.u_prev[(int64_t)k * N + i] = u[k];
+    T tau[6];
+    if (VEH == DOCKAUV_VEHICLE_BLUEROV2) {
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            T s = T(0);
+#pragma unroll
+            for (int k = 0; k < NU; k++) s += p.B[r * NU + k] * u[k];
+            tau[r] = s;
+        }
+    } else {
+        tau[0] = u[0]; tau[1] = u[1]; tau[2] = u[2]; tau[3] = tau[4] = tau[5] = T(0);
+    }
+
+    // ---- integrate (auvsim.py:89-108)
+    rkf45_step<T, VEH>(p, pos, y, tau, nu_c);
+#pragma unroll
+    for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) p.state[(int64_t)c * N + i] = pos[c];
+#pragma unroll
+    for (int c = 0; c < 9; c++) p.state[(int64_t)(3 + c) * N + i] = y[c];
+
+    // ---- post-step quantities: Theta_dot (auvsim.py:108, only euler_dot is consumed) and Rzyx for the radar
+    T sphi, cphi, sth, cth, spsi, cpsi;
+    Mth<T>::sincos_(y[0], &sphi, &cphi);
+    Mth<T>::sincos_(y[1], &sth, &cth);
+    Mth<T>::sincos_(y[2], &spsi, &cpsi);
+    T ed[3];
+    {
+        const T *nu = y + 3;
+        T inv_cth = T(1) / cth, tth = sth * inv_cth;
+        T qs = sphi * nu[4] + cphi * nu[5];
+        ed[0] = nu[3] + tth * qs;
+        ed[1] = cphi * nu[4] - sphi * nu[5];
+        ed[2] = qs * inv_cth;
+    }
+    rzyx(sphi, cphi, sth, cth, spsi, cpsi, cy.R);
+#pragma unroll
+    for (int c = 0; c < 3; c++) cy.pos[c] = pos[c];
+    spsi_out = spsi;
+    cpsi_out = cpsi;
+#pragma unroll
+    for (int c = 0; c < 3; c++) att_out[c] = y[c];
+
+    // ---- navigation errors (docking3d.py:404-413)
+    T diff[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) diff[c] = p.goal[(int64_t)c * N + i] - pos[c];
+    T dxy2 = diff[0] * diff[0] + diff[1] * diff[1];
+    T delta_d = Mth<T>::sqrt_(dxy2 + diff[2] * diff[2]);
+    T delta_theta = y[1] + ssa<T>(Mth<T>::atan2_(diff[2], Mth<T>::sqrt_(dxy2)));
+    T delta_psi = ssa<T>(Mth<T>::atan2_(diff[1], diff[0]) - y[2]);
+    cy.delta_d = delta_d;
+
+    // ---- observe (docking3d.py:462-488), entries 0..15
+    const T *nu = y + 3;
+    T o[16];
+    T lg = Mth<T>::log_(delta_d / p.max_dist_from_goal);
+    o[0] = clipv(T(1) - lg / p.log_den_obs, T(0), T(1));
+    o[1] = clipv(delta_theta / Mth<T>::half_pi, T(-1), T(1));
+    o[2] = clipv(delta_psi / Mth<T>::pi, T(-1), T(1));
+    o[3] = clipv(nu[0] / p.u_max, T(-1), T(1));
+    o[4] = clipv(nu[1] / p.v_max, T(-1), T(1));
+    o[5] = clipv(nu[2] / p.w_max, T(-1), T(1));
+    o[6] = clipv(y[0] / p.max_attitude, T(-1), T(1));
+    o[7] = clipv(y[1] / p.max_attitude, T(-1), T(1));
+    o[8] = clipv(spsi, T(-1), T(1));
+    o[9] = clipv(cpsi, T(-1), T(1));
+    o[10] = clipv(nu[3] / p.p_max, T(-1), T(1));
+    o[11] = clipv(nu[4] / p.q_max, T(-1), T(1));
+    o[12] = clipv(nu[5] / p.r_max, T(-1), T(1));
+    o[13] = clipv(nu_c[0] / T(2), T(-1), T(1));
+    o[14] = clipv(nu_c[1] / T(2), T(-1), T(1));
+    o[15] = clipv(nu_c[2] / T(2), T(-1), T(1));
+#pragma unroll
+    for (int c = 0; c < 16; c++) obs16[c] = (float)o[c];
+
+    // ---- is_done conditions 0..3 (docking3d.py:606-615; t_steps is the value before the increment)
+    int32_t t_steps = p.t_steps[i];
+    uint32_t cond = 0;
+    cond |= (delta_d < p.dist_goal_reached_tol) ? 1u : 0u;
+    cond |= (delta_d > p.max_dist_from_goal) ? 2u : 0u;
+    cond |= ((Mth<T>::abs_(y[0]) > p.max_attitude) || (Mth<T>::abs_(y[1]) > p.max_attitude)) ? 4u : 0u;
+    cond |= (t_steps >= p.max_timesteps) ? 8u : 0u;
+    cy.cond = cond;
+
+    // ---- reward terms that need no radar (docking3d.py:512-558, 584-588)
+    T *r = cy.rarr;
+    T lp_d;
+    {
+        // log_precision(delta_d, tol, max): shares the logarithm with obs[0] unless the epsilon guard bites
+        T lgr = (delta_d < T(0.001)) ? Mth<T>::log_(T(0.001) / p.max_dist_from_goal) : lg;
+        lp_d = T(1) - clipv(lgr / p.log_den_rew, T(0), T(1));
+    }
+    r[0] = -p.w_d * lp_d;
+    if (p.reward_set == 1) {
+        T a = delta_theta / Mth<T>::half_pi, b = delta_psi / Mth<T>::pi;
+        r[1] = -p.w_delta_theta * (a * a);
+        r[2] = -p.w_delta_psi * (b * b);
+    } else {
+        r[1] = -p.w_delta_theta * cont_goal_constraints<T>(Mth<T>::abs_(delta_theta), Mth<T>::half_pi, lp_d);
+        r[2] = -p.w_delta_psi * cont_goal_constraints<T>(Mth<T>::abs_(delta_psi), Mth<T>::pi, lp_d);
+    }
+    {
+        T a = y[0] / Mth<T>::half_pi, b = y[1] / Mth<T>::half_pi;
+        r[3] = -p.w_phi * (a * a);
+        r[4] = -p.w_theta * (b * b);
+        T nrm = Mth<T>::sqrt_(ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]) / p.p_max;
+        r[5] = -p.w_Thetadot * (nrm * nrm);
+    }
+    r[6] = lp_d;   // parked here for reward_set 2 (overwritten by the obstacle-avoidance term)
+    r[7] = penalty;
+
+    {
+        if (p.dbg_euler_dot)
+            for (int c = 0; c < 3; c++) p.dbg_euler_dot[(int64_t)c * N + i] = ed[c];
+        if (p.dbg_nu_c)
+            for (int c = 0; c < 3; c++) p.dbg_nu_c[(int64_t)c * N + i] = nu_c[c];
+        if (p.dbg_nav) {
+            p.dbg_nav[i] = delta_d;
+            p.dbg_nav[N + i] = delta_theta;
+            p.dbg_nav[2 * N + i] = delta_psi;
+        }
+        if (p.dbg_obs)
+            for (int c = 0; c < 16; c++) p.dbg_obs[(int64_t)c * N + i] = o[c];
+    }
+}
+
+// Final bookkeeping of one env once the radar term `r_oa` (Reward.obstacle_avoidance, docking3d.py:767-792) and
+// the collision flag are known: reward (docking3d.py:560-595), done, counters (:380-385), statistics and the
+// SB3-VecEnv style auto-reset.  Returns the done flag.
+template <typename T>
+__device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T r_oa, bool collision,
+                                            BlockStats &bs) {
+    const int64_t N = p.n_envs;
+    T *r = cy.rarr;
+    T lp_d = r[6];
+    if (p.reward_set == 1) r[6] = -p.w_oa * r_oa;
+    else r[6] = -p.w_oa * cont_goal_constraints<T>(Mth<T>::abs_(r_oa), T(1), lp_d);
+    uint32_t cond = cy.cond | (collision ? 16u : 0u);
+#pragma unroll
+    for (int k = 0; k < 5; k++) r[8 + k] = ((cond >> k) & 1u) ? p.w_done[k] : T(0);
+    T reward = reward_sum13<T>(r);
+    bool done = cond != 0;
+    p.reward[i] = reward;
+    p.done[i] = done ? 1 : 0;
+    if (p.cond_bits) p.cond_bits[i] = (uint8_t)cond;
+    T ep_ret = p.ep_return[i] + reward;
+    int32_t t_new = p.t_steps[i] + 1;
+    if (p.dbg_reward_arr)
+        for (int k = 0; k < 13; k++) p.dbg_reward_arr[(int64_t)k * N + i] = r[k];
+    if (done) {
+        if (p.ep_return_out) p.ep_return_out[i] = ep_ret;
+        if (p.ep_len_out) p.ep_len_out[i] = t_new;
+        bs.add(DOCKAUV_STAT_EPISODES, 1.0);
+        bs.add(DOCKAUV_STAT_SUM_RETURN, (double)ep_ret);
+        bs.add(DOCKAUV_STAT_SUM_LENGTH, (double)t_new);
+        for (int k = 0; k < 5; k++)
+            if ((cond >> k) & 1u) bs.add(DOCKAUV_STAT_COND0 + k, 1.0);
+        bs.add(DOCKAUV_STAT_SUM_FINAL_DELTA_D, (double)cy.delta_d);
+    }
+    if (reward != reward) bs.add(DOCKAUV_STAT_NAN_ENVS, 1.0);
+    if (done && p.auto_reset) {
+        reset_env<T>(p, i);
+    } else {
+        p.ep_return[i] = ep_ret;
+        p.t_steps[i] = t_new;
+    }
+    return done;
+}
+
+// Writes one observation row (and the terminal-observation row of a finished episode).
+template <typename T>
+__device__ __forceinline__ void write_obs_row(const KParams<T> &p, int64_t i, const float *row, int n, int offset,
+                                              bool done) {
+    float *dst = p.obs + i * p.n_obs + offset;
+    if (done && p.terminal_obs) {
+        float *t = p.terminal_obs + i * p.n_obs + offset;
+        for (int c = 0; c < n; c++) t[c] = row[c];
+    }
+    if (done && p.auto_reset) {
+        for (int c = 0; c < n; c++) dst[c] = 0.0f;      // reset() returns the all-zero observation
+    } else {
+        for (int c = 0; c < n; c++) dst[c] = row[c];
+    }
+}
+
+template <typename T, int VEH, int NU>
+__global__ void __launch_bounds__(128) step_tpe_kernel(const __grid_constant__ KParams<T> p) {
+    __shared__ double s_stats[DOCKAUV_N_STATS];
+    BlockStats bs{s_stats};
+    bs.init();
+    const int64_t N = p.n_envs;
+    const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * blockDim.x;
+    const int64_t i = i0 + threadIdx.x;
+    if (i < p.env_end) {
+        StepCarry<T> cy;
+        T spsi, cpsi, att[3];
+        float obs16[16];
+        step_dynamics<T, VEH, NU>(p, i, cy, spsi, cpsi, obs16, att);
+
+        // ---- obstacles: ray-independent pre-computation + body collision (docking3d.py:444-460)
+        const T R_safe = p.safety_radius;
+        bool collision = false;
+        CapPre<T> cp[DOCKAUV_MAX_CAPSULES];
+        T soc[DOCKAUV_MAX_SPHERES][3], sc[DOCKAUV_MAX_SPHERES];
+        for (int k = 0; k < p.n_sph; k++) {
+            T cen[3], rad;
+            for (int c = 0; c < 3; c++) cen[c] = p.spheres[(int64_t)(k * 4 + c) * N + i];
+            rad = p.spheres[(int64_t)(k * 4 + 3) * N + i];
+            T d2 = T(0);
+            for (int c = 0; c < 3; c++) {
+                soc[k][c] = cy.pos[c] - cen[c];
+                d2 += soc[k][c] * soc[k][c];
+            }
+            sc[k] = d2 - rad * rad;
+            collision |= (Mth<T>::sqrt_(d2) <= R_safe + rad);              // shape.py:182-192
+        }
+        for (int k = 0; k < p.n_caps; k++) {
+            T bot[3], top[3], rad;
+            for (int c = 0; c < 3; c++) {
+                bot[c] = p.capsules[(int64_t)(k * 7 + c) * N + i];
+                top[c] = p.capsules[(int64_t)(k * 7 + 3 + c) * N + i];
+            }
+            rad = p.capsules[(int64_t)(k * 7 + 6) * N + i];
+            capsule_pre<T>(cy.pos, bot, top, rad, cp[k]);
+            collision |= (dist_segment_point<T>(cy.pos, bot, top) <= rad + R_safe);   // shape.py:195-210
+        }
+
+        // ---- radar: rays, min positive distance over obstacles, clamp, 2x2 max-pool, OA reward
+        const int n_r = p.n_rays, n_h = p.n_horiz, blk = p.block;
+        const T dmax = p.radar_max_dist;
+        const bool any_obstacle = (p.n_caps + p.n_sph) > 0;
+        T pooled[DOCKAUV_MAX_RAYS / 4 + 32];
+        for (int c = 0; c < p.n_rr; c++) pooled[c] = T(0);     // block_reduce pads with cval = 0
+        T oa_dot = T(0);
+        for (int ir = 0; ir < n_r; ir++) {
+            T d = dmax;
+            if (any_obstacle) {
+                const T *b = p.rd_b + 3 * ir;
+                T rd[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) rd[c] = cy.R[3 * c] * b[0] + cy.R[3 * c + 1] * b[1] + cy.R[3 * c + 2] * b[2];
+                T best = Mth<T>::inf(), first = T(0);
+                bool have_first = false;
+                for (int k = 0; k < p.n_caps; k++) {
+                    T v = ray_capsule<T>(cp[k], rd);
+                    if (!have_first) { first = v; have_first = true; }
+                    if (v > T(0) && v < best) best = v;
+                }
+                if (p.n_sph > 0) {
+                    T sbest = Mth<T>::inf(), sfirst = T(0);
+                    for (int k = 0; k < p.n_sph; k++) {
+                        T v = ray_sphere<T>(soc[k], sc[k], rd);
+                        if (k == 0) sfirst = v;
+                        if (v > T(0) && v < sbest) sbest = v;
+                    }
+                    T v = (sbest < Mth<T>::inf()) ? sbest : sfirst;   // shape.py:264
+                    if (!have_first) { first = v; have_first = true; }
+                    if (v > T(0) && v < best) best = v;
+                }
+                d = (best < Mth<T>::inf()) ? best : first;             // docking3d.py:438-439
+                if (d < T(0) || d > dmax) d = dmax;                    // sensor.py:117
+            }
+            if (p.dbg_ray_dist) p.dbg_ray_dist[(int64_t)ir * N + i] = d;
+            int iv = ir / n_h, ih = ir - iv * n_h;
+            int pc = (iv / blk) * p.n_hr + ih / blk;
+            // np.max semantics: NaN propagates
+            T cur = pooled[pc];
+            pooled[pc] = (d != d || cur != cur) ? (d + cur) : (d > cur ? d : cur);
+            T c = clipv(T(1) - d / dmax, T(0), T(1));
+            T q = (T(1) - c) * (T(1) - c);
+            T mx = (q != q) ? q : (q > T(0.001) ? q : T(0.001));
+            oa_dot += mx * p.beta_oa[ir];
+        }
+        T r_oa = p.sum_beta_oa / oa_dot - T(1);
+
+        bool done = step_finish<T>(p, i, cy, r_oa, collision, bs);
+
+        // ---- observation row
+        write_obs_row<T>(p, i, obs16, 16, 0, done);
+        {
+            float *dst = p.obs + i * p.n_obs + 16;
+            float *tdst = (done && p.terminal_obs) ? p.terminal_obs + i * p.n_obs + 16 : nullptr;
+            bool zero = done && p.auto_reset;
+            for (int c = 0; c < p.n_rr; c++) {
+                T v = clipv(pooled[c] / dmax, T(0), T(1));
+                if (p.dbg_obs) p.dbg_obs[(int64_t)(16 + c) * N + i] = v;
+                if (tdst) tdst[c] = (float)v;
+                dst[c] = zero ? 0.0f : (float)v;
+            }
+        }
+    }
+    {
+        int64_t left = p.env_end - i0;
+        bs.flush(p.stats, (int)(left < (int64_t)blockDim.x ? left : (int64_t)blockDim.x));
+    }
+}
+
+}  // namespace dockauv

