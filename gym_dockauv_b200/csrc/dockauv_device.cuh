@@ -18,6 +18,14 @@ namespace dockauv {
 template <typename T>
 struct Mth;
 
+// The library sincos() carries a large Payne-Hanek slow path; inlining it at every call site made the step kernels
+// > 170 KB of SASS (instruction-cache misses were 11 % of the stall samples).  One out-of-line copy instead.
+static __device__ __noinline__ double2 sincos_outlined(double x) {
+    double s, c;
+    sincos(x, &s, &c);
+    return make_double2(s, c);
+}
+
 template <>
 struct Mth<double> {
     static constexpr double pi = 3.141592653589793;
@@ -25,7 +33,11 @@ struct Mth<double> {
     static constexpr double half_pi = 1.5707963267948966;
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
     static __device__ __forceinline__ double nan() { return CUDART_NAN; }
-    static __device__ __forceinline__ void sincos_(double x, double *s, double *c) { sincos(x, s, c); }
+    static __device__ __forceinline__ void sincos_(double x, double *s, double *c) {
+        const double2 r = sincos_outlined(x);
+        *s = r.x;
+        *c = r.y;
+    }
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
@@ -60,24 +72,37 @@ __device__ __forceinline__ T clipv(T x, T lo, T hi) {
     return x < lo ? lo : (x > hi ? hi : x);
 }
 
-// geomutils.py:4-11  ssa(x) = (x + pi) % (2 pi) - pi with numpy's floor-mod.  For |x| < 3 pi the modulo is a
-// single conditional add/subtract (bit-identical to fmod there); the general path handles anything else.
+// general path of ssa (numpy floor-mod via fmod); cold: only angles beyond +-3 pi (blown-up LAUV states) get here
 template <typename T>
-__device__ __forceinline__ T ssa(T x) {
+static __device__ __noinline__ T ssa_general(T x) {
     const T pi = Mth<T>::pi, two_pi = Mth<T>::two_pi;
-    T a = x + pi;
-    if (Mth<T>::abs_(x) < T(9.0)) {
-        if (a >= two_pi) a -= two_pi;
-        else if (a < T(0)) a += two_pi;
-        return a - pi;
-    }
-    T mod = Mth<T>::fmod_(a, two_pi);
+    T mod = Mth<T>::fmod_(x + pi, two_pi);
     if (mod != T(0)) {
         if (mod < T(0)) mod += two_pi;
     } else {
         mod = T(0);
     }
     return mod - pi;
+}
+
+// geomutils.py:4-11  ssa(x) = (x + pi) % (2 pi) - pi with numpy's floor-mod.  For |x| < 3 pi the modulo is a
+// single conditional add/subtract (bit-identical to fmod there); the general path handles anything else.
+template <typename T>
+__device__ __forceinline__ T ssa(T x) {
+    const T pi = Mth<T>::pi, two_pi = Mth<T>::two_pi;
+    if (Mth<T>::abs_(x) < T(9.0)) {
+        T a = x + pi;
+        if (a >= two_pi) a -= two_pi;
+        else if (a < T(0)) a += two_pi;
+        return a - pi;
+    }
+    return ssa_general<T>(x);
+}
+
+// cold-path logarithm (epsilon guards that practically never trigger): out of line to keep the hot code small
+template <typename T>
+static __device__ __noinline__ T log_cold(T x) {
+    return Mth<T>::log_(x);
 }
 
 // ------------------------------------------------------------------------------------------- Philox4x32-10

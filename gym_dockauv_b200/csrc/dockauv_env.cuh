@@ -12,7 +12,7 @@ namespace dockauv {
 // position, 4-6 attitude, 7 goal angle, 8 goal depth, 9 pillar phase, 10-11 current direction, 12 current
 // speed, 13+3s.. synthetic sphere s.
 template <typename T>
-__device__ void reset_env(const KParams<T> &p, int64_t i) {
+static __device__ __noinline__ void reset_env(const KParams<T> &p, int64_t i) {
     const int64_t N = p.n_envs;
     const uint64_t gid = p.env_id0 + (uint64_t)i;
     const uint32_t ep = (uint32_t)p.episode[i];

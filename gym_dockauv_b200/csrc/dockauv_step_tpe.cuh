@@ -145,7 +145,7 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     T lp_d;
     {
         // log_precision(delta_d, tol, max): shares the logarithm with obs[0] unless the epsilon guard bites
-        T lgr = (delta_d < T(0.001)) ? Mth<T>::log_(T(0.001) / p.max_dist_from_goal) : lg;
+        T lgr = (delta_d < T(0.001)) ? log_cold<T>(T(0.001) / p.max_dist_from_goal) : lg;
         lp_d = T(1) - clipv(lgr / p.log_den_rew, T(0), T(1));
     }
     r[0] = -p.w_d * lp_d;

@@ -1,44 +1,43 @@
 // dockauv_step_warp.cuh -- layout DOCKAUV_LAYOUT_WARP_RAYS.
 //
-// One CTA of 128 threads owns 128 consecutive envs.
+// One CTA of 128 threads owns 128 consecutive envs; each warp works only on the 32 envs of its own lanes, so the
+// phases below are separated by __syncwarp() only.
 //   phase A (thread per env) : current, command filter, RKF45, angle wrap, nav errors, obs[0:16], done bits 0..3 and
 //                              the radar-independent reward terms; the post-step pose goes to shared memory.
-//   phase B (warp per env)   : each warp walks over the 32 envs its own threads just integrated.  Lanes 0..K-1
-//                              load one obstacle each, do the ray-independent algebra and the body-collision
-//                              test, and park the result in a per-warp shared scratch; then every lane casts
-//                              its rays (ray = lane + 32 j) against the obstacles that are within radar range
-//                              (uniform loop, broadcast shared reads), the per-ray minimum is lane-local, the
-//                              obstacle-avoidance sum is a shuffle reduction and the 2x2 max-pool goes through
-//                              the per-warp scratch.
-//   phase C (thread per env) : reward, done, counters, statistics, auto-reset; then the CTA streams its
-//                              128 x n_obs float32 observation tile to HBM with fully coalesced stores.
+//   phase B (warp per env)   : the 32 envs are taken in sub-batches of 32 / slots envs (slots = 8 or 16 obstacle
+//                              slots per env).  Pass 1 of a sub-batch uses ALL lanes, one (env, obstacle) pair per
+//                              lane: coalesced-by-sector obstacle loads, the ray-independent algebra, the
+//                              body-collision test and the radar-range cull; two ballots publish the collision and
+//                              in-range bits of the whole sub-batch.  Pass 2 walks over the envs of the sub-batch:
+//                              every lane casts its rays (ray = lane + 32 j) against the in-range obstacles (uniform
+//                              loop, broadcast shared reads); the per-ray minimum is lane-local, the
+//                              obstacle-avoidance sum is a shuffle reduction whose result stays in a register of
+//                              the env's owner lane, the 2x2 max-pool goes through a per-warp scratch.
+//   phase C (thread per env) : reward, done, counters, statistics, auto-reset; then each warp streams the
+//                              observation rows of its envs to HBM (one coalesced store per row).
 #pragma once
 #include "dockauv_step_tpe.cuh"
 
 namespace dockauv {
 
 constexpr int kWarpEnvs = 128;       // envs (= threads) per CTA
-constexpr int kPreCap = 12;          // shared words per capsule: ba[3] oa[3] baba baoa c c2a c2b (+1 pad)
-constexpr int kPreSph = 4;           // shared words per sphere: oc[3] c
+constexpr int kPreStride = 13;       // shared words per (env, obstacle) record; odd -> at most 2-way write conflicts
+                                     // capsule: ba[3] oa[3] baba baoa c c2a c2b ; sphere: oc[3] c
 
 template <typename T>
 struct WarpSmem {
-    // layout of the dynamic shared memory block (all offsets in bytes, computed on host and device alike)
-    int pose_off, oa_off, obs_off, pre_off, ray_off, flag_off, total;
+    // layout of the dynamic shared memory block (offsets in bytes, computed on host and device alike)
+    int pose_off, obs_off, pre_off, ray_off, total;
     int obs_stride;     // floats per staged observation row (odd -> conflict-free column writes)
-    int pre_stride;     // T words per warp of obstacle scratch
     int ray_stride;     // T words per warp of ray-distance scratch
     __host__ __device__ WarpSmem(int n_obs, int n_rays) {
         int off = 0;
         pose_off = off; off += kWarpEnvs * 12 * (int)sizeof(T);
-        oa_off = off;   off += kWarpEnvs * (int)sizeof(T);
-        pre_stride = DOCKAUV_MAX_CAPSULES * kPreCap + DOCKAUV_MAX_SPHERES * kPreSph;
-        pre_off = off;  off += 4 * pre_stride * (int)sizeof(T);
+        pre_off = off;  off += 4 * 32 * kPreStride * (int)sizeof(T);
         ray_stride = (n_rays + 1) & ~1;
         ray_off = off;  off += 4 * ray_stride * (int)sizeof(T);
         obs_stride = n_obs | 1;
         obs_off = off;  off += kWarpEnvs * obs_stride * (int)sizeof(float);
-        flag_off = off; off += 2 * kWarpEnvs;
         off = (off + 15) & ~15;
         total = off + DOCKAUV_N_STATS * (int)sizeof(double);
     }
@@ -56,12 +55,7 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const WarpSmem<T> L(p.n_obs, p.n_rays);
     T *s_pose = reinterpret_cast<T *>(smem_raw + L.pose_off);
-    T *s_oa = reinterpret_cast<T *>(smem_raw + L.oa_off);
-    T *s_pre_all = reinterpret_cast<T *>(smem_raw + L.pre_off);
-    T *s_ray_all = reinterpret_cast<T *>(smem_raw + L.ray_off);
     float *s_obs = reinterpret_cast<float *>(smem_raw + L.obs_off);
-    unsigned char *s_col = smem_raw + L.flag_off;
-    unsigned char *s_done = s_col + kWarpEnvs;
     BlockStats bs{reinterpret_cast<double *>(smem_raw + L.total - DOCKAUV_N_STATS * (int)sizeof(double))};
     bs.init();
 
@@ -72,6 +66,8 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
     const bool active = i < p.env_end;
     int64_t left64 = p.env_end - i0;
     const int n_here = (int)(left64 < (int64_t)kWarpEnvs ? left64 : (int64_t)kWarpEnvs);
+    const int e_warp = warp * 32;                         // first env (CTA-local) of this warp
+    const int n_warp = max(0, min(32, n_here - e_warp));  // envs this warp really has
 
     // ------------------------------------------------------------------ phase A
     StepCarry<T> cy;
@@ -89,12 +85,14 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
     __syncwarp();
 
     // ------------------------------------------------------------------ phase B
+    T my_oa_dot = p.sum_beta_oa;     // owner-lane copies of the per-env radar results (neutral values: r_oa = 0)
+    bool my_col = false;
     {
-        T *s_pre = s_pre_all + warp * L.pre_stride;
-        T *s_ray = s_ray_all + warp * L.ray_stride;
+        T *s_pre = reinterpret_cast<T *>(smem_raw + L.pre_off) + warp * 32 * kPreStride;
+        T *s_ray = reinterpret_cast<T *>(smem_raw + L.ray_off) + warp * L.ray_stride;
         const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
         const int n_r = p.n_rays;
-        const T dmax = p.radar_max_dist, R_safe = p.safety_radius;
+        const T dmax = p.radar_max_dist, inv_dmax = T(1) / dmax, R_safe = p.safety_radius;
         const T cull = dmax * T(1.000001);
         // this lane's rays: body-frame direction and obstacle-avoidance weight stay in registers
         T rb[RPL][3], bw[RPL];
@@ -106,181 +104,229 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
             for (int c = 0; c < 3; c++) rb[j][c] = ok ? p.ray_tab[c * n_r + ir] : T(0);
             bw[j] = ok ? p.ray_tab[3 * n_r + ir] : T(0);
         }
-        const int e_begin = warp * 32;
-        const int e_end = min(e_begin + 32, n_here);
-        for (int e = e_begin; e < e_end; e++) {
-            const int64_t ie = i0 + e;
-            const T *pose = s_pose + e * 12;
-            // ---- ray-independent algebra + body collision, one obstacle per lane
+        // pooling fast path (2x2 blocks, at most one pooled cell per lane): source slots of this lane's cell
+        const bool fast_pool = (p.block == 2) && (p.n_rr <= 32);
+        int pidx[4] = {-1, -1, -1, -1};
+        if (fast_pool && lane < p.n_rr) {
+            const int pr = lane / p.n_hr, pcol = lane - pr * p.n_hr;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int rv = 2 * pr + (q >> 1), rh = 2 * pcol + (q & 1);
+                if (rv < p.n_vert && rh < p.n_horiz) pidx[q] = rv * p.n_horiz + rh;
+            }
+        }
+        // obstacle slot of this lane in pass 1
+        const int slots = n_obst <= 8 ? 8 : 16;
+        const int epp = 32 / slots;                        // envs per sub-batch
+        const unsigned slot_mask = (1u << slots) - 1u;
+        const int my_slot = lane & (slots - 1), my_sub = lane / slots;
+        const bool slot_is_cap = my_slot < n_caps, slot_used = my_slot < n_obst;
+        const T *obst_row = slot_is_cap ? p.capsules + (int64_t)(my_slot * 7) * N
+                                        : p.spheres + (int64_t)((my_slot - n_caps) * 4) * N;
+
+        for (int eb = 0; eb < n_warp; eb += epp) {
+            // ---- pass 1: one (env, obstacle) pair per lane
             bool hit_body = false, in_range = false;
-            if (lane < n_obst) {
-                T pos[3] = {pose[0], pose[1], pose[2]};
-                if (lane < n_caps) {
-                    T bot[3], top[3], rad;
+            {
+                const int e = eb + my_sub;
+                if (slot_used && e < n_warp) {
+                    const T *pose = s_pose + (e_warp + e) * 12;
+                    const T pos[3] = {pose[0], pose[1], pose[2]};
+                    const T *g = obst_row + (i0 + e_warp + e);
+                    T *w = s_pre + lane * kPreStride;
+                    if (slot_is_cap) {
+                        T bot[3], top[3], rad;
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        bot[c] = p.capsules[(int64_t)(lane * 7 + c) * N + ie];
-                        top[c] = p.capsules[(int64_t)(lane * 7 + 3 + c) * N + ie];
-                    }
-                    rad = p.capsules[(int64_t)(lane * 7 + 6) * N + ie];
-                    CapPre<T> q;
-                    capsule_pre<T>(pos, bot, top, rad, q);
-                    T *w = s_pre + lane * kPreCap;
-                    w[0] = q.ba[0]; w[1] = q.ba[1]; w[2] = q.ba[2];
-                    w[3] = q.oa[0]; w[4] = q.oa[1]; w[5] = q.oa[2];
-                    w[6] = q.baba; w[7] = q.baoa; w[8] = q.c; w[9] = q.c2a; w[10] = q.c2b;
-                    T dist = dist_segment_point<T>(pos, bot, top);
-                    hit_body = dist <= rad + R_safe;                       // shape.py:195-210
-                    in_range = !(dist - rad > cull);
-                } else {
-                    const int k = lane - n_caps;
-                    T oc[3], rad, d2 = T(0);
+                        for (int c = 0; c < 3; c++) {
+                            bot[c] = g[(int64_t)c * N];
+                            top[c] = g[(int64_t)(3 + c) * N];
+                        }
+                        rad = g[(int64_t)6 * N];
+                        CapPre<T> q;
+                        capsule_pre<T>(pos, bot, top, rad, q);
+                        w[0] = q.ba[0]; w[1] = q.ba[1]; w[2] = q.ba[2];
+                        w[3] = q.oa[0]; w[4] = q.oa[1]; w[5] = q.oa[2];
+                        w[6] = q.baba; w[7] = q.baoa; w[8] = q.c; w[9] = q.c2a; w[10] = q.c2b;
+                        T dist = dist_segment_point<T>(pos, bot, top);
+                        hit_body = dist <= rad + R_safe;                       // shape.py:195-210
+                        in_range = !(dist - rad > cull);
+                    } else {
+                        T oc[3], rad, d2 = T(0);
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        oc[c] = pos[c] - p.spheres[(int64_t)(k * 4 + c) * N + ie];
-                        d2 += oc[c] * oc[c];
+                        for (int c = 0; c < 3; c++) {
+                            oc[c] = pos[c] - g[(int64_t)c * N];
+                            d2 += oc[c] * oc[c];
+                        }
+                        rad = g[(int64_t)3 * N];
+                        w[0] = oc[0]; w[1] = oc[1]; w[2] = oc[2]; w[3] = d2 - rad * rad;
+                        T dist = Mth<T>::sqrt_(d2);
+                        hit_body = dist <= R_safe + rad;                       // shape.py:182-192
+                        in_range = !(dist - rad > cull);
                     }
-                    rad = p.spheres[(int64_t)(k * 4 + 3) * N + ie];
-                    T *w = s_pre + DOCKAUV_MAX_CAPSULES * kPreCap + k * kPreSph;
-                    w[0] = oc[0]; w[1] = oc[1]; w[2] = oc[2]; w[3] = d2 - rad * rad;
-                    T dist = Mth<T>::sqrt_(d2);
-                    hit_body = dist <= R_safe + rad;                       // shape.py:182-192
-                    in_range = !(dist - rad > cull);
                 }
             }
-            const unsigned col_mask = __ballot_sync(0xffffffffu, hit_body);
-            unsigned near_mask = __ballot_sync(0xffffffffu, in_range);
+            const unsigned colb = __ballot_sync(0xffffffffu, hit_body);
+            const unsigned nearb = __ballot_sync(0xffffffffu, in_range);
+            {   // the owner lane of each env of this sub-batch keeps its collision flag for phase C
+                const int s = lane - eb;
+                if (s >= 0 && s < epp) my_col = ((colb >> (slots * s)) & slot_mask) != 0u;
+            }
             __syncwarp();
 
-            // ---- cast this lane's rays
-            T R[9];
+            // ---- pass 2: cast rays, env by env
+            for (int s = 0; s < epp && eb + s < n_warp; s++) {
+                const int e = eb + s;
+                const int64_t ie = i0 + e_warp + e;
+                const T *pose = s_pose + (e_warp + e) * 12;
+                const unsigned near_mask = (nearb >> (slots * s)) & slot_mask;
+                T R[9];
 #pragma unroll
-            for (int c = 0; c < 9; c++) R[c] = pose[3 + c];
-            T rd[RPL][3], best[RPL], first[RPL];
-#pragma unroll
-            for (int j = 0; j < RPL; j++) {
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    rd[j][c] = R[3 * c] * rb[j][0] + R[3 * c + 1] * rb[j][1] + R[3 * c + 2] * rb[j][2];
-                best[j] = Mth<T>::inf();
-                first[j] = -Mth<T>::inf();
-            }
-            unsigned cap_mask = near_mask & ((1u << n_caps) - 1u);
-            unsigned sph_mask = (n_caps < 32 ? (near_mask >> n_caps) : 0u) & ((1u << n_sph) - 1u);
-            while (cap_mask) {
-                const int k = __ffs(cap_mask) - 1;
-                cap_mask &= cap_mask - 1;
-                const T *w = s_pre + k * kPreCap;
-                CapPre<T> q;
-                q.ba[0] = w[0]; q.ba[1] = w[1]; q.ba[2] = w[2];
-                q.oa[0] = w[3]; q.oa[1] = w[4]; q.oa[2] = w[5];
-                q.baba = w[6]; q.baoa = w[7]; q.c = w[8]; q.c2a = w[9]; q.c2b = w[10];
-#pragma unroll
-                for (int c = 0; c < 3; c++) q.oc2[c] = q.oa[c] - q.ba[c];
-                q.r = T(0);
+                for (int c = 0; c < 9; c++) R[c] = pose[3 + c];
+                T rd[RPL][3], best[RPL], first[RPL];
 #pragma unroll
                 for (int j = 0; j < RPL; j++) {
-                    T v = ray_capsule<T>(q, rd[j]);
-                    if (k == 0) first[j] = v;
-                    if (v > T(0) && v < best[j]) best[j] = v;
-                }
-            }
-            if (n_sph > 0) {
-                T sbest[RPL], sfirst[RPL];
 #pragma unroll
-                for (int j = 0; j < RPL; j++) {
-                    sbest[j] = Mth<T>::inf();
-                    sfirst[j] = -Mth<T>::inf();
+                    for (int c = 0; c < 3; c++)
+                        rd[j][c] = R[3 * c] * rb[j][0] + R[3 * c + 1] * rb[j][1] + R[3 * c + 2] * rb[j][2];
+                    best[j] = Mth<T>::inf();
+                    first[j] = -Mth<T>::inf();
                 }
-                while (sph_mask) {
-                    const int k = __ffs(sph_mask) - 1;
-                    sph_mask &= sph_mask - 1;
-                    const T *w = s_pre + DOCKAUV_MAX_CAPSULES * kPreCap + k * kPreSph;
-                    T oc[3] = {w[0], w[1], w[2]};
-                    T c = w[3];
+                const T *pre_env = s_pre + (s * slots) * kPreStride;
+                unsigned cap_mask = near_mask & ((1u << n_caps) - 1u);
+                unsigned sph_mask = (near_mask >> n_caps) & ((1u << n_sph) - 1u);
+                while (cap_mask) {
+                    const int k = __ffs(cap_mask) - 1;
+                    cap_mask &= cap_mask - 1;
+                    const T *w = pre_env + k * kPreStride;
+                    CapPre<T> q;
+                    q.ba[0] = w[0]; q.ba[1] = w[1]; q.ba[2] = w[2];
+                    q.oa[0] = w[3]; q.oa[1] = w[4]; q.oa[2] = w[5];
+                    q.baba = w[6]; q.baoa = w[7]; q.c = w[8]; q.c2a = w[9]; q.c2b = w[10];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) q.oc2[c] = q.oa[c] - q.ba[c];
+                    q.r = T(0);
 #pragma unroll
                     for (int j = 0; j < RPL; j++) {
-                        T v = ray_sphere<T>(oc, c, rd[j]);
-                        if (k == 0) sfirst[j] = v;
-                        if (v > T(0) && v < sbest[j]) sbest[j] = v;
+                        T v = ray_capsule<T>(q, rd[j]);
+                        if (k == 0) first[j] = v;
+                        if (v > T(0) && v < best[j]) best[j] = v;
                     }
                 }
+                if (n_sph > 0) {
+                    T sbest[RPL], sfirst[RPL];
 #pragma unroll
-                for (int j = 0; j < RPL; j++) {
-                    T v = (sbest[j] < Mth<T>::inf()) ? sbest[j] : sfirst[j];   // shape.py:264
-                    if (n_caps == 0) first[j] = v;
-                    if (v > T(0) && v < best[j]) best[j] = v;
-                }
-            }
-            // ---- clamp (sensor.py:117), obstacle-avoidance partial sum (docking3d.py:792), stash for pooling
-            T oa_part = T(0);
-#pragma unroll
-            for (int j = 0; j < RPL; j++) {
-                const int ir = lane + 32 * j;
-                if (ir < n_r) {
-                    T d = dmax;
-                    if (n_obst > 0) {
-                        d = (best[j] < Mth<T>::inf()) ? best[j] : first[j];      // docking3d.py:438-439
-                        if (d < T(0) || d > dmax) d = dmax;
+                    for (int j = 0; j < RPL; j++) {
+                        sbest[j] = Mth<T>::inf();
+                        sfirst[j] = -Mth<T>::inf();
                     }
-                    s_ray[ir] = d;
-                    if (p.dbg_ray_dist) p.dbg_ray_dist[(int64_t)ir * N + ie] = d;
-                    T c = clipv(T(1) - d / dmax, T(0), T(1));
-                    T qq = (T(1) - c) * (T(1) - c);
-                    T mx = (qq != qq) ? qq : (qq > T(0.001) ? qq : T(0.001));
-                    oa_part += mx * bw[j];
-                }
-            }
-            const T oa_dot = warp_sum<T>(oa_part);
-            __syncwarp();
-            // ---- 2x2 max-pool with zero padding (sensor.py:131-137) -> obs[16:]
-            for (int pc = lane; pc < p.n_rr; pc += 32) {
-                const int pr = pc / p.n_hr, pcol = pc - pr * p.n_hr;
-                T mx = T(0);
-                bool nan = false;
-                for (int dv = 0; dv < p.block; dv++)
-                    for (int dh = 0; dh < p.block; dh++) {
-                        const int rv = pr * p.block + dv, rh = pcol * p.block + dh;
-                        if (rv < p.n_vert && rh < p.n_horiz) {
-                            T v = s_ray[rv * p.n_horiz + rh];
-                            nan |= (v != v);
-                            mx = v > mx ? v : mx;
+                    while (sph_mask) {
+                        const int k = __ffs(sph_mask) - 1;
+                        sph_mask &= sph_mask - 1;
+                        const T *w = pre_env + (n_caps + k) * kPreStride;
+                        T oc[3] = {w[0], w[1], w[2]};
+                        T c = w[3];
+#pragma unroll
+                        for (int j = 0; j < RPL; j++) {
+                            T v = ray_sphere<T>(oc, c, rd[j]);
+                            if (k == 0) sfirst[j] = v;
+                            if (v > T(0) && v < sbest[j]) sbest[j] = v;
                         }
                     }
-                T o = nan ? Mth<T>::nan() : clipv(mx / dmax, T(0), T(1));
-                s_obs[e * L.obs_stride + 16 + pc] = (float)o;
-                if (p.dbg_obs) p.dbg_obs[(int64_t)(16 + pc) * N + ie] = o;
+#pragma unroll
+                    for (int j = 0; j < RPL; j++) {
+                        T v = (sbest[j] < Mth<T>::inf()) ? sbest[j] : sfirst[j];   // shape.py:264
+                        if (n_caps == 0) first[j] = v;
+                        if (v > T(0) && v < best[j]) best[j] = v;
+                    }
+                }
+                // ---- clamp (sensor.py:117), obstacle-avoidance partial sum (docking3d.py:792), stash for pooling
+                T oa_part = T(0);
+#pragma unroll
+                for (int j = 0; j < RPL; j++) {
+                    const int ir = lane + 32 * j;
+                    if (ir < n_r) {
+                        T d = dmax;
+                        if (n_obst > 0) {
+                            d = (best[j] < Mth<T>::inf()) ? best[j] : first[j];      // docking3d.py:438-439
+                            if (d < T(0) || d > dmax) d = dmax;
+                        }
+                        s_ray[ir] = d;
+                        if (p.dbg_ray_dist) p.dbg_ray_dist[(int64_t)ir * N + ie] = d;
+                        T c = clipv(T(1) - d * inv_dmax, T(0), T(1));
+                        T qq = (T(1) - c) * (T(1) - c);
+                        T mx = (qq != qq) ? qq : (qq > T(0.001) ? qq : T(0.001));
+                        oa_part += mx * bw[j];
+                    }
+                }
+                const T oa_dot = warp_sum<T>(oa_part);
+                if (lane == e) my_oa_dot = oa_dot;
+                __syncwarp();
+                // ---- 2x2 max-pool with zero padding (sensor.py:131-137) -> obs[16:]
+                float *orow = s_obs + (e_warp + e) * L.obs_stride + 16;
+                if (fast_pool) {
+                    if (lane < p.n_rr) {
+                        T mx = T(0);
+                        bool nan = false;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (pidx[q] >= 0) {
+                                T v = s_ray[pidx[q]];
+                                nan |= (v != v);
+                                mx = v > mx ? v : mx;
+                            }
+                        }
+                        T o = nan ? Mth<T>::nan() : clipv(mx * inv_dmax, T(0), T(1));
+                        orow[lane] = (float)o;
+                        if (p.dbg_obs) p.dbg_obs[(int64_t)(16 + lane) * N + ie] = o;
+                    }
+                } else {
+                    for (int pc = lane; pc < p.n_rr; pc += 32) {
+                        const int pr = pc / p.n_hr, pcol = pc - pr * p.n_hr;
+                        T mx = T(0);
+                        bool nan = false;
+                        for (int dv = 0; dv < p.block; dv++)
+                            for (int dh = 0; dh < p.block; dh++) {
+                                const int rv = pr * p.block + dv, rh = pcol * p.block + dh;
+                                if (rv < p.n_vert && rh < p.n_horiz) {
+                                    T v = s_ray[rv * p.n_horiz + rh];
+                                    nan |= (v != v);
+                                    mx = v > mx ? v : mx;
+                                }
+                            }
+                        T o = nan ? Mth<T>::nan() : clipv(mx * inv_dmax, T(0), T(1));
+                        orow[pc] = (float)o;
+                        if (p.dbg_obs) p.dbg_obs[(int64_t)(16 + pc) * N + ie] = o;
+                    }
+                }
+                __syncwarp();
             }
-            if (lane == 0) {
-                s_oa[e] = p.sum_beta_oa / oa_dot - T(1);
-                s_col[e] = col_mask != 0u;
-            }
-            __syncwarp();
         }
     }
 
     // ------------------------------------------------------------------ phase C
+    bool done = false;
     if (active) {
-        bool done = step_finish<T>(p, i, cy, s_oa[tid], s_col[tid] != 0, bs);
-        s_done[tid] = done;
+        const T r_oa = p.sum_beta_oa / my_oa_dot - T(1);      // docking3d.py:792
+        done = step_finish<T>(p, i, cy, r_oa, my_col, bs);
     }
-    bs.flush(p.stats, n_here);   // contains the __syncthreads that also publishes s_obs / s_done
-
-    // ---- stream the observation tile out: rows are contiguous in HBM, so the copy is a flat coalesced store
+    __syncwarp();
+    // ---- each warp streams the observation rows of its own envs: one coalesced store per row segment
     {
         const int n_obs = p.n_obs;
-        const int total = n_here * n_obs;
-        float *gobs = p.obs + i0 * n_obs;
-        float *gterm = p.terminal_obs ? p.terminal_obs + i0 * n_obs : nullptr;
         const bool ar = p.auto_reset != 0;
-        for (int f = tid; f < total; f += kWarpEnvs) {
-            const int row = f / n_obs, col = f - row * n_obs;
-            const float v = s_obs[row * L.obs_stride + col];
-            const bool dn = s_done[row] != 0;
-            if (dn && gterm) gterm[f] = v;
-            gobs[f] = (dn && ar) ? 0.0f : v;     // reset() hands back the all-zero observation (docking3d.py:269,322)
+        const unsigned done_mask = __ballot_sync(0xffffffffu, done);
+        for (int e = 0; e < n_warp; e++) {
+            const bool dn = (done_mask >> e) & 1u;
+            const float *row = s_obs + (e_warp + e) * L.obs_stride;
+            float *gobs = p.obs + (i0 + e_warp + e) * n_obs;
+            for (int c = lane; c < n_obs; c += 32) {
+                const float v = row[c];
+                if (dn && p.terminal_obs) p.terminal_obs[(i0 + e_warp + e) * n_obs + c] = v;
+                gobs[c] = (dn && ar) ? 0.0f : v;   // reset() hands back the all-zero observation (docking3d.py:269,322)
+            }
         }
     }
+    bs.flush(p.stats, n_here);
 }
 
 template <typename T, int VEH, int NU, int RPL>
