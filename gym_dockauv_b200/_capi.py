@@ -5,7 +5,8 @@ import os
 
 from .params import ABI_VERSION, DockauvBuffers, DockauvDebugOut, DockauvParams, DockauvStepOut
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libdockauv_b200.so")
+LIB_PATH = os.environ.get("DOCKAUV_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
+                                                        "libdockauv_b200.so")   # DOCKAUV_LIB: tuning builds only
 
 # every symbol include/dockauv.h declares: (restype, argtypes)
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
-LIB_PATH = os.path.join(LIB_DIR, "libdockauv_b200.so")
+LIB_PATH = os.environ.get("DOCKAUV_LIB_OUT") or os.path.join(LIB_DIR, "libdockauv_b200.so")   # override: tuning builds
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 UNITS = ["dockauv_capi.cu", "dockauv_kernels_f64.cu", "dockauv_kernels_f32.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -55,7 +55,9 @@ def build_library(force=False, verbose=False):
 
     def compile_unit(unit):
         obj = os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", host_cxx, *NVCC_FLAGS, "-c", os.path.join(CSRC, unit), "-o", obj]
+        extra = os.environ.get("DOCKAUV_NVCC_EXTRA", "").split()
+        obj = os.path.join(OBJ_DIR, os.path.basename(LIB_PATH) + "." + unit.replace(".cu", ".o"))
+        cmd = [nvcc, "-ccbin", host_cxx, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, unit), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)

@@ -368,7 +368,10 @@ template <typename T>
 __device__ __forceinline__ T ray_sphere(const T oc[3], T c, const T rd[3]) {
     T b = oc[0] * rd[0] + oc[1] * rd[1] + oc[2] * rd[2];
     T h = b * b - c;
-    return (h < T(0)) ? -Mth<T>::inf() : (-b - Mth<T>::sqrt_(h));
+    // the square root is evaluated for every lane (the select is if-converted); feeding it 1 instead of a negative
+    // h keeps misses off the library's slow path (sqrt of a negative goes through the out-of-line NaN handler)
+    T r = -b - Mth<T>::sqrt_(h < T(0) ? T(1) : h);
+    return (h < T(0)) ? -Mth<T>::inf() : r;
 }
 
 // shape.py:393-417 dist_line_point(po, l1, l2) with l1 = bot, l2 = top
@@ -376,7 +379,8 @@ template <typename T>
 __device__ __forceinline__ T dist_segment_point(const T pos[3], const T bot[3], const T top[3]) {
     T l[3] = {top[0] - bot[0], top[1] - bot[1], top[2] - bot[2]};
     T n = Mth<T>::sqrt_(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
-    T d[3] = {l[0] / n, l[1] / n, l[2] / n};
+    // axis-aligned capsules have zero components; 0 / n is exact but takes the library's slow division path
+    T d[3] = {l[0] == T(0) ? l[0] : l[0] / n, l[1] == T(0) ? l[1] : l[1] / n, l[2] == T(0) ? l[2] : l[2] / n};
     T s = (bot[0] - pos[0]) * d[0] + (bot[1] - pos[1]) * d[1] + (bot[2] - pos[2]) * d[2];
     T t = (pos[0] - top[0]) * d[0] + (pos[1] - top[1]) * d[1] + (pos[2] - top[2]) * d[2];
     T hh = s;

@@ -186,20 +186,36 @@ __device__ __forceinline__ T reward_sum13(const T r[13]) {
     return s;
 }
 
-// block-level episode statistics: shared accumulators, one global atomic per statistic per block
-struct BlockStats {
-    double *s;   // shared double[DOCKAUV_N_STATS]
-    __device__ __forceinline__ void init() {
-        if (threadIdx.x < DOCKAUV_N_STATS) s[threadIdx.x] = 0.0;
-        __syncthreads();
-    }
-    __device__ __forceinline__ void add(int k, double v) { atomicAdd(&s[k], v); }
-    // n_steps = env-steps this block performed (added once per block, not per thread)
-    __device__ __forceinline__ void flush(double *g, int n_steps) {
-        __syncthreads();
-        if (threadIdx.x == 0) s[DOCKAUV_STAT_ENV_STEPS] = (double)n_steps;
-        __syncthreads();
-        if (threadIdx.x < DOCKAUV_N_STATS && s[threadIdx.x] != 0.0) atomicAdd(&g[threadIdx.x], s[threadIdx.x]);
+// Episode statistics of one warp: each lane remembers the outcome of its env; if any episode of the warp ended,
+// a shuffle reduction folds the contributions and lane 0 issues one global atomic per non-zero statistic.
+struct WarpStats {
+    bool done = false, nan = false;
+    uint32_t cond = 0;
+    int32_t length = 0;
+    double ep_return = 0.0, delta_d = 0.0;
+
+    // n_steps = env-steps to account for (callers pass the CTA's count from one warp only, 0 from the others:
+    // one same-address atomic per CTA instead of one per warp)
+    __device__ __forceinline__ void flush(double *g, int n_steps) const {
+        const int lane = threadIdx.x & 31;
+        if (__any_sync(0xffffffffu, done)) {
+            double v[DOCKAUV_STAT_ENV_STEPS];
+            v[DOCKAUV_STAT_EPISODES] = done ? 1.0 : 0.0;
+            v[DOCKAUV_STAT_SUM_RETURN] = done ? ep_return : 0.0;
+            v[DOCKAUV_STAT_SUM_LENGTH] = done ? (double)length : 0.0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) v[DOCKAUV_STAT_COND0 + k] = (done && ((cond >> k) & 1u)) ? 1.0 : 0.0;
+            v[DOCKAUV_STAT_SUM_FINAL_DELTA_D] = done ? delta_d : 0.0;
+            v[DOCKAUV_STAT_NAN_ENVS] = (done && nan) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < DOCKAUV_STAT_ENV_STEPS; k++) {
+                double x = v[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == 0 && x != 0.0) atomicAdd(&g[k], x);
+            }
+        }
+        if (lane == 0 && n_steps > 0) atomicAdd(&g[DOCKAUV_STAT_ENV_STEPS], (double)n_steps);
     }
 };
 

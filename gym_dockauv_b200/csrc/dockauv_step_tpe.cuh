@@ -187,7 +187,7 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
 // SB3-VecEnv style auto-reset.  Returns the done flag.
 template <typename T>
 __device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T r_oa, bool collision,
-                                            BlockStats &bs) {
+                                            WarpStats &bs) {
     const int64_t N = p.n_envs;
     T *r = cy.rarr;
     T lp_d = r[6];
@@ -208,14 +208,13 @@ __device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, Step
     if (done) {
         if (p.ep_return_out) p.ep_return_out[i] = ep_ret;
         if (p.ep_len_out) p.ep_len_out[i] = t_new;
-        bs.add(DOCKAUV_STAT_EPISODES, 1.0);
-        bs.add(DOCKAUV_STAT_SUM_RETURN, (double)ep_ret);
-        bs.add(DOCKAUV_STAT_SUM_LENGTH, (double)t_new);
-        for (int k = 0; k < 5; k++)
-            if ((cond >> k) & 1u) bs.add(DOCKAUV_STAT_COND0 + k, 1.0);
-        bs.add(DOCKAUV_STAT_SUM_FINAL_DELTA_D, (double)cy.delta_d);
+        bs.done = true;
+        bs.cond = cond;
+        bs.length = t_new;
+        bs.ep_return = (double)ep_ret;
+        bs.delta_d = (double)cy.delta_d;
+        bs.nan = reward != reward;      // episodes that ended on a NaN reward
     }
-    if (reward != reward) bs.add(DOCKAUV_STAT_NAN_ENVS, 1.0);
     if (done && p.auto_reset) {
         reset_env<T>(p, i);
     } else {
@@ -243,9 +242,8 @@ __device__ __forceinline__ void write_obs_row(const KParams<T> &p, int64_t i, co
 
 template <typename T, int VEH, int NU>
 __global__ void __launch_bounds__(128) step_tpe_kernel(const __grid_constant__ KParams<T> p) {
-    __shared__ double s_stats[DOCKAUV_N_STATS];
-    BlockStats bs{s_stats};
-    bs.init();
+    WarpStats bs;
+    bool done = false;
     const int64_t N = p.n_envs;
     const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * blockDim.x;
     const int64_t i = i0 + threadIdx.x;
@@ -331,7 +329,7 @@ __global__ void __launch_bounds__(128) step_tpe_kernel(const __grid_constant__ K
         }
         T r_oa = p.sum_beta_oa / oa_dot - T(1);
 
-        bool done = step_finish<T>(p, i, cy, r_oa, collision, bs);
+        done = step_finish<T>(p, i, cy, r_oa, collision, bs);
 
         // ---- observation row
         write_obs_row<T>(p, i, obs16, 16, 0, done);
@@ -349,7 +347,7 @@ __global__ void __launch_bounds__(128) step_tpe_kernel(const __grid_constant__ K
     }
     {
         int64_t left = p.env_end - i0;
-        bs.flush(p.stats, (int)(left < (int64_t)blockDim.x ? left : (int64_t)blockDim.x));
+        bs.flush(p.stats, threadIdx.x < 32 ? (int)(left < (int64_t)blockDim.x ? left : (int64_t)blockDim.x) : 0);
     }
 }
 

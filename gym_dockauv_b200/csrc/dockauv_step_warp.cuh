@@ -38,8 +38,7 @@ struct WarpSmem {
         ray_off = off;  off += 4 * ray_stride * (int)sizeof(T);
         obs_stride = n_obs | 1;
         obs_off = off;  off += kWarpEnvs * obs_stride * (int)sizeof(float);
-        off = (off + 15) & ~15;
-        total = off + DOCKAUV_N_STATS * (int)sizeof(double);
+        total = (off + 15) & ~15;
     }
 };
 
@@ -51,13 +50,14 @@ __device__ __forceinline__ T warp_sum(T v) {
 }
 
 template <typename T, int VEH, int NU, int RPL>
+// no min-CTAs hint on purpose: __launch_bounds__(128, 3) ends at the same 168 registers but a 6 % slower schedule,
+// (128, 4) and (128, 5) spill (measured on B200, profiles/r01/NOTES.md)
 __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const WarpSmem<T> L(p.n_obs, p.n_rays);
     T *s_pose = reinterpret_cast<T *>(smem_raw + L.pose_off);
     float *s_obs = reinterpret_cast<float *>(smem_raw + L.obs_off);
-    BlockStats bs{reinterpret_cast<double *>(smem_raw + L.total - DOCKAUV_N_STATS * (int)sizeof(double))};
-    bs.init();
+    WarpStats bs;
 
     const int64_t N = p.n_envs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
             }
         }
     }
-    bs.flush(p.stats, n_here);
+    bs.flush(p.stats, warp == 0 ? n_here : 0);
 }
 
 template <typename T, int VEH, int NU, int RPL>
