@@ -150,6 +150,25 @@ static void fill_kparams(const DockauvParams &s, int64_t n_envs, KParams<T> &k) 
         sb += s.beta_oa[i];
     }
     k.sum_beta_oa = (T)sb;
+    // bounding pyramid of the ray fan (used by the warp layout's field-of-view cull); a ray with x <= 0 disables it
+    double ty = 0.0, tz = 0.0;
+    bool fan_ok = true;
+    for (int i = 0; i < s.n_rays; i++) {
+        const double x = s.rd_b[3 * i];
+        if (!(x > 1e-6)) {
+            fan_ok = false;
+            break;
+        }
+        ty = std::fmax(ty, std::fabs(s.rd_b[3 * i + 1]) / x);
+        tz = std::fmax(tz, std::fabs(s.rd_b[3 * i + 2]) / x);
+    }
+    if (!fan_ok) ty = tz = 1e30;
+    ty *= 1.0 + 1e-9;
+    tz *= 1.0 + 1e-9;
+    k.fov_ty = (T)ty;
+    k.fov_tz = (T)tz;
+    k.fov_ny = (T)std::sqrt(1.0 + ty * ty);
+    k.fov_nz = (T)std::sqrt(1.0 + tz * tz);
 }
 
 extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device, DockauvHandle **out) {

@@ -36,6 +36,9 @@ struct KParams {
     float arf_f32[DOCKAUV_MAX_U];
     T cur_mu, cur_sigma;
     T radar_max_dist, sum_beta_oa;
+    // ray pyramid in the body frame: every ray direction satisfies x > 0, |y| <= fov_ty x, |z| <= fov_tz x;
+    // fov_ny = sqrt(1 + ty^2), fov_nz = sqrt(1 + tz^2) (norms of the side-plane normals)
+    T fov_ty, fov_tz, fov_ny, fov_nz;
     // persistent state (SoA, env fastest)
     T *state, *u_prev, *goal, *heading_goal, *current, *capsules, *spheres, *ep_return;
     int32_t *t_steps, *episode;

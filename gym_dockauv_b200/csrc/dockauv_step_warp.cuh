@@ -21,7 +21,8 @@
 namespace dockauv {
 
 constexpr int kWarpEnvs = 128;       // envs (= threads) per CTA
-constexpr int kPreStride = 13;       // shared words per (env, obstacle) record; odd -> at most 2-way write conflicts
+constexpr int kPoseStride = 14;      // shared words per env: pos[3] R[9] poison pad
+constexpr int kPreStride = 14;       // shared words per (env, obstacle) record, 16-byte aligned for 128-bit reads
                                      // capsule: ba[3] oa[3] baba baoa c c2a c2b ; sphere: oc[3] c
 
 template <typename T>
@@ -29,12 +30,12 @@ struct WarpSmem {
     // layout of the dynamic shared memory block (offsets in bytes, computed on host and device alike)
     int pose_off, obs_off, pre_off, ray_off, total;
     int obs_stride;     // floats per staged observation row (odd -> conflict-free column writes)
-    int ray_stride;     // T words per warp of ray-distance scratch
+    int ray_stride;     // T words per warp of ray-distance scratch (+1 zero slot for the pooling padding)
     __host__ __device__ WarpSmem(int n_obs, int n_rays) {
         int off = 0;
-        pose_off = off; off += kWarpEnvs * 12 * (int)sizeof(T);
+        pose_off = off; off += kWarpEnvs * kPoseStride * (int)sizeof(T);
         pre_off = off;  off += 4 * 32 * kPreStride * (int)sizeof(T);
-        ray_stride = (n_rays + 1) & ~1;
+        ray_stride = (n_rays + 2) & ~1;
         ray_off = off;  off += 4 * ray_stride * (int)sizeof(T);
         obs_stride = n_obs | 1;
         obs_off = off;  off += kWarpEnvs * obs_stride * (int)sizeof(float);
@@ -49,11 +50,24 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
-template <typename T, int VEH, int NU, int RPL>
+// two shared words with one 128-bit (double) / 64-bit (float) load
+template <typename T>
+struct Pair;
+template <>
+struct Pair<double> {
+    using type = double2;
+};
+template <>
+struct Pair<float> {
+    using type = float2;
+};
+
 // no min-CTAs hint on purpose: __launch_bounds__(128, 3) ends at the same 168 registers but a 6 % slower schedule,
 // (128, 4) and (128, 5) spill (measured on B200, profiles/r01/NOTES.md)
+template <typename T, int VEH, int NU, int RPL>
 __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using P2 = typename Pair<T>::type;
     const WarpSmem<T> L(p.n_obs, p.n_rays);
     T *s_pose = reinterpret_cast<T *>(smem_raw + L.pose_off);
     float *s_obs = reinterpret_cast<float *>(smem_raw + L.obs_off);
@@ -75,10 +89,21 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
         T spsi, cpsi, att[3];
         float obs16[16];
         step_dynamics<T, VEH, NU>(p, i, cy, spsi, cpsi, obs16, att);
+        T *ps = s_pose + tid * kPoseStride;
+        T acc = T(0);
 #pragma unroll
-        for (int c = 0; c < 3; c++) s_pose[tid * 12 + c] = cy.pos[c];
+        for (int c = 0; c < 3; c++) {
+            ps[c] = cy.pos[c];
+            acc += cy.pos[c];
+        }
 #pragma unroll
-        for (int c = 0; c < 9; c++) s_pose[tid * 12 + 3 + c] = cy.R[c];
+        for (int c = 0; c < 9; c++) {
+            ps[3 + c] = cy.R[c];
+            acc += cy.R[c];
+        }
+        // 0 for a finite pose, NaN otherwise: added to every ray distance so that a blown-up state poisons the
+        // radar outputs exactly like the reference's NaN propagation does
+        ps[12] = acc * T(0);
 #pragma unroll
         for (int c = 0; c < 16; c++) s_obs[tid * L.obs_stride + c] = obs16[c];
     }
@@ -104,9 +129,10 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
             for (int c = 0; c < 3; c++) rb[j][c] = ok ? p.ray_tab[c * n_r + ir] : T(0);
             bw[j] = ok ? p.ray_tab[3 * n_r + ir] : T(0);
         }
-        // pooling fast path (2x2 blocks, at most one pooled cell per lane): source slots of this lane's cell
+        // pooling fast path (2x2 blocks, at most one pooled cell per lane): the four source slots of this lane's
+        // cell; cells beyond the ray grid read the zero slot s_ray[n_r] (block_reduce pads with cval = 0)
         const bool fast_pool = (p.block == 2) && (p.n_rr <= 32);
-        int pidx[4] = {-1, -1, -1, -1};
+        int pidx[4] = {n_r, n_r, n_r, n_r};
         if (fast_pool && lane < p.n_rr) {
             const int pr = lane / p.n_hr, pcol = lane - pr * p.n_hr;
 #pragma unroll
@@ -115,6 +141,7 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                 if (rv < p.n_vert && rh < p.n_horiz) pidx[q] = rv * p.n_horiz + rh;
             }
         }
+        if (lane == 0) s_ray[n_r] = T(0);
         // obstacle slot of this lane in pass 1
         const int slots = n_obst <= 8 ? 8 : 16;
         const int epp = 32 / slots;                        // envs per sub-batch
@@ -123,6 +150,7 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
         const bool slot_is_cap = my_slot < n_caps, slot_used = my_slot < n_obst;
         const T *obst_row = slot_is_cap ? p.capsules + (int64_t)(my_slot * 7) * N
                                         : p.spheres + (int64_t)((my_slot - n_caps) * 4) * N;
+        const T fov_ty = p.fov_ty, fov_tz = p.fov_tz, fov_ny = p.fov_ny, fov_nz = p.fov_nz;
 
         for (int eb = 0; eb < n_warp; eb += epp) {
             // ---- pass 1: one (env, obstacle) pair per lane
@@ -130,12 +158,14 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
             {
                 const int e = eb + my_sub;
                 if (slot_used && e < n_warp) {
-                    const T *pose = s_pose + (e_warp + e) * 12;
+                    const T *pose = s_pose + (e_warp + e) * kPoseStride;
                     const T pos[3] = {pose[0], pose[1], pose[2]};
                     const T *g = obst_row + (i0 + e_warp + e);
                     T *w = s_pre + lane * kPreStride;
+                    T rad, dist;
+                    T q0[3], q1[3];     // obstacle end points relative to the vehicle, NED
                     if (slot_is_cap) {
-                        T bot[3], top[3], rad;
+                        T bot[3], top[3];
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
                             bot[c] = g[(int64_t)c * N];
@@ -147,11 +177,25 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                         w[0] = q.ba[0]; w[1] = q.ba[1]; w[2] = q.ba[2];
                         w[3] = q.oa[0]; w[4] = q.oa[1]; w[5] = q.oa[2];
                         w[6] = q.baba; w[7] = q.baoa; w[8] = q.c; w[9] = q.c2a; w[10] = q.c2b;
-                        T dist = dist_segment_point<T>(pos, bot, top);
-                        hit_body = dist <= rad + R_safe;                       // shape.py:195-210
-                        in_range = !(dist - rad > cull);
+                        // dist_line_point (shape.py:393-417): clamped parallel part and perpendicular part of pos
+                        // relative to the axis, with one reciprocal instead of three divisions and hypot
+                        const T inv_n = T(1) / Mth<T>::sqrt_(q.baba);
+                        const T sp = -q.baoa * inv_n;                                   // (bot - pos) . d
+                        const T tp = (q.oc2[0] * q.ba[0] + q.oc2[1] * q.ba[1] + q.oc2[2] * q.ba[2]) * inv_n;  // (pos - top) . d
+                        T hh = sp;
+                        if (tp > hh || tp != tp) hh = tp;
+                        if (T(0) > hh) hh = T(0);
+                        T cr[3];
+                        cross3(q.oa, q.ba, cr);
+                        const T perp2 = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * (inv_n * inv_n);
+                        dist = Mth<T>::sqrt_(hh * hh + perp2);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            q0[c] = -q.oa[c];
+                            q1[c] = -q.oc2[c];
+                        }
                     } else {
-                        T oc[3], rad, d2 = T(0);
+                        T oc[3], d2 = T(0);
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
                             oc[c] = pos[c] - g[(int64_t)c * N];
@@ -159,10 +203,33 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                         }
                         rad = g[(int64_t)3 * N];
                         w[0] = oc[0]; w[1] = oc[1]; w[2] = oc[2]; w[3] = d2 - rad * rad;
-                        T dist = Mth<T>::sqrt_(d2);
-                        hit_body = dist <= R_safe + rad;                       // shape.py:182-192
-                        in_range = !(dist - rad > cull);
+                        dist = Mth<T>::sqrt_(d2);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) q0[c] = q1[c] = -oc[c];
                     }
+                    hit_body = dist <= rad + R_safe;              // shape.py:182-210 (safety radius, auvsim.py:43)
+                    // radar culls (exact: a culled obstacle can only yield "no positive distance" or a distance
+                    // beyond max_dist, both of which end as max_dist, sensor.py:117):
+                    //  - range: nearest surface point farther than max_dist;
+                    //  - field of view: the obstacle lies entirely outside one of the five planes of the ray pyramid
+                    //    {x >= 0, |y| <= ty x, |z| <= tz x} (body frame), in which every ray direction lies.
+                    bool outside = dist - rad > cull;
+                    {
+                        T a0[3], a1[3];    // body-frame coordinates R^T q
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            a0[c] = pose[3 + c] * q0[0] + pose[6 + c] * q0[1] + pose[9 + c] * q0[2];
+                            a1[c] = pose[3 + c] * q1[0] + pose[6 + c] * q1[1] + pose[9 + c] * q1[2];
+                        }
+                        const T rm = rad * T(1.000001) + T(1e-9);
+                        const T ry = rm * fov_ny, rz = rm * fov_nz;
+                        outside |= (a0[0] < -rm) && (a1[0] < -rm);
+                        outside |= (a0[1] - fov_ty * a0[0] > ry) && (a1[1] - fov_ty * a1[0] > ry);
+                        outside |= (-a0[1] - fov_ty * a0[0] > ry) && (-a1[1] - fov_ty * a1[0] > ry);
+                        outside |= (a0[2] - fov_tz * a0[0] > rz) && (a1[2] - fov_tz * a1[0] > rz);
+                        outside |= (-a0[2] - fov_tz * a0[0] > rz) && (-a1[2] - fov_tz * a1[0] > rz);
+                    }
+                    in_range = !outside;
                 }
             }
             const unsigned colb = __ballot_sync(0xffffffffu, hit_body);
@@ -177,84 +244,86 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
             for (int s = 0; s < epp && eb + s < n_warp; s++) {
                 const int e = eb + s;
                 const int64_t ie = i0 + e_warp + e;
-                const T *pose = s_pose + (e_warp + e) * 12;
+                const T *pose = s_pose + (e_warp + e) * kPoseStride;
                 const unsigned near_mask = (nearb >> (slots * s)) & slot_mask;
-                T R[9];
+                T best[RPL];
 #pragma unroll
-                for (int c = 0; c < 9; c++) R[c] = pose[3 + c];
-                T rd[RPL][3], best[RPL], first[RPL];
+                for (int j = 0; j < RPL; j++) best[j] = Mth<T>::inf();
+                if (near_mask) {
+                    T R[9];
 #pragma unroll
-                for (int j = 0; j < RPL; j++) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++)
-                        rd[j][c] = R[3 * c] * rb[j][0] + R[3 * c + 1] * rb[j][1] + R[3 * c + 2] * rb[j][2];
-                    best[j] = Mth<T>::inf();
-                    first[j] = -Mth<T>::inf();
-                }
-                const T *pre_env = s_pre + (s * slots) * kPreStride;
-                unsigned cap_mask = near_mask & ((1u << n_caps) - 1u);
-                unsigned sph_mask = (near_mask >> n_caps) & ((1u << n_sph) - 1u);
-                while (cap_mask) {
-                    const int k = __ffs(cap_mask) - 1;
-                    cap_mask &= cap_mask - 1;
-                    const T *w = pre_env + k * kPreStride;
-                    CapPre<T> q;
-                    q.ba[0] = w[0]; q.ba[1] = w[1]; q.ba[2] = w[2];
-                    q.oa[0] = w[3]; q.oa[1] = w[4]; q.oa[2] = w[5];
-                    q.baba = w[6]; q.baoa = w[7]; q.c = w[8]; q.c2a = w[9]; q.c2b = w[10];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) q.oc2[c] = q.oa[c] - q.ba[c];
-                    q.r = T(0);
+                    for (int c = 0; c < 9; c++) R[c] = pose[3 + c];
+                    T rd[RPL][3];
 #pragma unroll
                     for (int j = 0; j < RPL; j++) {
-                        T v = ray_capsule<T>(q, rd[j]);
-                        if (k == 0) first[j] = v;
-                        if (v > T(0) && v < best[j]) best[j] = v;
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+                            rd[j][c] = R[3 * c] * rb[j][0] + R[3 * c + 1] * rb[j][1] + R[3 * c + 2] * rb[j][2];
                     }
-                }
-                if (n_sph > 0) {
-                    T sbest[RPL], sfirst[RPL];
+                    const T *pre_env = s_pre + (s * slots) * kPreStride;
+                    unsigned cap_mask = near_mask & ((1u << n_caps) - 1u);
+                    unsigned sph_mask = (near_mask >> n_caps) & ((1u << n_sph) - 1u);
+                    while (cap_mask) {
+                        const int k = __ffs(cap_mask) - 1;
+                        cap_mask &= cap_mask - 1;
+                        const P2 *w2 = reinterpret_cast<const P2 *>(pre_env + k * kPreStride);
+                        const P2 v0 = w2[0], v1 = w2[1], v2 = w2[2], v3 = w2[3], v4 = w2[4], v5 = w2[5];
+                        const T ba[3] = {v0.x, v0.y, v1.x}, oa[3] = {v1.y, v2.x, v2.y};
+                        const T baba = v3.x, baoa = v3.y, cc = v4.x, c2a = v4.y, c2b = v5.x;
 #pragma unroll
-                    for (int j = 0; j < RPL; j++) {
-                        sbest[j] = Mth<T>::inf();
-                        sfirst[j] = -Mth<T>::inf();
+                        for (int j = 0; j < RPL; j++) {
+                            // shape.py:341-390 for one ray: cylinder root, body hit if 0 < y < baba, else end cap
+                            const T bard = rd[j][0] * ba[0] + rd[j][1] * ba[1] + rd[j][2] * ba[2];
+                            const T rdoa = rd[j][0] * oa[0] + rd[j][1] * oa[1] + rd[j][2] * oa[2];
+                            const T a = baba - bard * bard;
+                            const T b = baba * rdoa - baoa * bard;
+                            const T h = b * b - a * cc;
+                            if (h > T(0)) {
+                                const T t = (-b - Mth<T>::sqrt_(h)) / a;
+                                const T y = baoa + t * bard;
+                                T v = t;
+                                if (!(y > T(0) && y < baba)) {
+                                    const bool far_end = y >= T(0);
+                                    const T b2 = far_end ? rdoa - bard : rdoa;     // rd . (pos - cap end)
+                                    const T h2 = b2 * b2 - (far_end ? c2b : c2a);
+                                    v = (h2 > T(0)) ? (-b2 - Mth<T>::sqrt_(h2)) : T(-1);
+                                }
+                                if (v > T(0) && v < best[j]) best[j] = v;
+                            }
+                        }
                     }
                     while (sph_mask) {
                         const int k = __ffs(sph_mask) - 1;
                         sph_mask &= sph_mask - 1;
-                        const T *w = pre_env + (n_caps + k) * kPreStride;
-                        T oc[3] = {w[0], w[1], w[2]};
-                        T c = w[3];
+                        const P2 *w2 = reinterpret_cast<const P2 *>(pre_env + (n_caps + k) * kPreStride);
+                        const P2 v0 = w2[0], v1 = w2[1];
 #pragma unroll
                         for (int j = 0; j < RPL; j++) {
-                            T v = ray_sphere<T>(oc, c, rd[j]);
-                            if (k == 0) sfirst[j] = v;
-                            if (v > T(0) && v < sbest[j]) sbest[j] = v;
+                            // shape.py:252-263: nearest root of the ray / sphere quadratic
+                            const T b = v0.x * rd[j][0] + v0.y * rd[j][1] + v1.x * rd[j][2];
+                            const T h = b * b - v1.y;
+                            if (h >= T(0)) {
+                                const T v = -b - Mth<T>::sqrt_(h);
+                                if (v > T(0) && v < best[j]) best[j] = v;
+                            }
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < RPL; j++) {
-                        T v = (sbest[j] < Mth<T>::inf()) ? sbest[j] : sfirst[j];   // shape.py:264
-                        if (n_caps == 0) first[j] = v;
-                        if (v > T(0) && v < best[j]) best[j] = v;
-                    }
                 }
-                // ---- clamp (sensor.py:117), obstacle-avoidance partial sum (docking3d.py:792), stash for pooling
+                // ---- clamp (sensor.py:117), obstacle-avoidance partial sum (docking3d.py:767-792), stash for pooling
+                const T poison = pose[12];
                 T oa_part = T(0);
 #pragma unroll
                 for (int j = 0; j < RPL; j++) {
                     const int ir = lane + 32 * j;
                     if (ir < n_r) {
-                        T d = dmax;
-                        if (n_obst > 0) {
-                            d = (best[j] < Mth<T>::inf()) ? best[j] : first[j];      // docking3d.py:438-439
-                            if (d < T(0) || d > dmax) d = dmax;
-                        }
+                        // min positive distance over obstacles (docking3d.py:438-439), max_dist if none or farther
+                        T d = (best[j] > dmax ? dmax : best[j]) + poison;
                         s_ray[ir] = d;
                         if (p.dbg_ray_dist) p.dbg_ray_dist[(int64_t)ir * N + ie] = d;
-                        T c = clipv(T(1) - d * inv_dmax, T(0), T(1));
-                        T qq = (T(1) - c) * (T(1) - c);
-                        T mx = (qq != qq) ? qq : (qq > T(0.001) ? qq : T(0.001));
+                        // (gamma_c (1 - c))^2 with c = clip(1 - d/d_max, 0, 1): 1 - c = d/d_max for d in [0, d_max]
+                        const T x = d * inv_dmax;
+                        const T qq = x * x;
+                        const T mx = !(qq <= T(0.001)) ? qq : T(0.001);     // np.maximum, NaN propagates
                         oa_part += mx * bw[j];
                     }
                 }
@@ -265,17 +334,14 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                 float *orow = s_obs + (e_warp + e) * L.obs_stride + 16;
                 if (fast_pool) {
                     if (lane < p.n_rr) {
-                        T mx = T(0);
-                        bool nan = false;
+                        T mx = s_ray[pidx[0]];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            if (pidx[q] >= 0) {
-                                T v = s_ray[pidx[q]];
-                                nan |= (v != v);
-                                mx = v > mx ? v : mx;
-                            }
+                        for (int q = 1; q < 4; q++) {
+                            const T v = s_ray[pidx[q]];
+                            mx = !(v <= mx) ? v : mx;            // np.max, NaN propagates
                         }
-                        T o = nan ? Mth<T>::nan() : clipv(mx * inv_dmax, T(0), T(1));
+                        T o = mx * inv_dmax;                     // clip(d / max_dist, 0, 1), docking3d.py:487
+                        o = o > T(1) ? T(1) : o;
                         orow[lane] = (float)o;
                         if (p.dbg_obs) p.dbg_obs[(int64_t)(16 + lane) * N + ie] = o;
                     }
@@ -283,17 +349,16 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                     for (int pc = lane; pc < p.n_rr; pc += 32) {
                         const int pr = pc / p.n_hr, pcol = pc - pr * p.n_hr;
                         T mx = T(0);
-                        bool nan = false;
                         for (int dv = 0; dv < p.block; dv++)
                             for (int dh = 0; dh < p.block; dh++) {
                                 const int rv = pr * p.block + dv, rh = pcol * p.block + dh;
                                 if (rv < p.n_vert && rh < p.n_horiz) {
-                                    T v = s_ray[rv * p.n_horiz + rh];
-                                    nan |= (v != v);
-                                    mx = v > mx ? v : mx;
+                                    const T v = s_ray[rv * p.n_horiz + rh];
+                                    mx = !(v <= mx) ? v : mx;
                                 }
                             }
-                        T o = nan ? Mth<T>::nan() : clipv(mx * inv_dmax, T(0), T(1));
+                        T o = mx * inv_dmax;
+                        o = o > T(1) ? T(1) : o;
                         orow[pc] = (float)o;
                         if (p.dbg_obs) p.dbg_obs[(int64_t)(16 + pc) * N + ie] = o;
                     }
@@ -315,14 +380,15 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
         const int n_obs = p.n_obs;
         const bool ar = p.auto_reset != 0;
         const unsigned done_mask = __ballot_sync(0xffffffffu, done);
+        float *gobs = p.obs + (i0 + e_warp) * n_obs;
+        float *gterm = p.terminal_obs ? p.terminal_obs + (i0 + e_warp) * n_obs : nullptr;
         for (int e = 0; e < n_warp; e++) {
             const bool dn = (done_mask >> e) & 1u;
             const float *row = s_obs + (e_warp + e) * L.obs_stride;
-            float *gobs = p.obs + (i0 + e_warp + e) * n_obs;
             for (int c = lane; c < n_obs; c += 32) {
                 const float v = row[c];
-                if (dn && p.terminal_obs) p.terminal_obs[(i0 + e_warp + e) * n_obs + c] = v;
-                gobs[c] = (dn && ar) ? 0.0f : v;   // reset() hands back the all-zero observation (docking3d.py:269,322)
+                if (dn && gterm) gterm[e * n_obs + c] = v;
+                gobs[e * n_obs + c] = (dn && ar) ? 0.0f : v;   // reset() returns the all-zero observation (docking3d.py:269,322)
             }
         }
     }
