@@ -28,17 +28,14 @@ constexpr int kPreStride = 14;       // shared words per (env, obstacle) record,
 template <typename T>
 struct WarpSmem {
     // layout of the dynamic shared memory block (offsets in bytes, computed on host and device alike)
-    int pose_off, obs_off, pre_off, ray_off, total;
-    int obs_stride;     // floats per staged observation row (odd -> conflict-free column writes)
+    int pose_off, pre_off, ray_off, total;
     int ray_stride;     // T words per warp of ray-distance scratch (+1 zero slot for the pooling padding)
-    __host__ __device__ WarpSmem(int n_obs, int n_rays) {
+    __host__ __device__ WarpSmem(int n_rays) {
         int off = 0;
         pose_off = off; off += kWarpEnvs * kPoseStride * (int)sizeof(T);
         pre_off = off;  off += 4 * 32 * kPreStride * (int)sizeof(T);
         ray_stride = (n_rays + 2) & ~1;
         ray_off = off;  off += 4 * ray_stride * (int)sizeof(T);
-        obs_stride = n_obs | 1;
-        obs_off = off;  off += kWarpEnvs * obs_stride * (int)sizeof(float);
         total = (off + 15) & ~15;
     }
 };
@@ -68,9 +65,8 @@ template <typename T, int VEH, int NU, int RPL>
 __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using P2 = typename Pair<T>::type;
-    const WarpSmem<T> L(p.n_obs, p.n_rays);
+    const WarpSmem<T> L(p.n_rays);
     T *s_pose = reinterpret_cast<T *>(smem_raw + L.pose_off);
-    float *s_obs = reinterpret_cast<float *>(smem_raw + L.obs_off);
     WarpStats bs;
 
     const int64_t N = p.n_envs;
@@ -90,22 +86,24 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
         float obs16[16];
         step_dynamics<T, VEH, NU>(p, i, cy, spsi, cpsi, obs16, att);
         T *ps = s_pose + tid * kPoseStride;
-        T acc = T(0);
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            ps[c] = cy.pos[c];
-            acc += cy.pos[c];
-        }
+        for (int c = 0; c < 3; c++) ps[c] = cy.pos[c];
 #pragma unroll
-        for (int c = 0; c < 9; c++) {
-            ps[3 + c] = cy.R[c];
-            acc += cy.R[c];
-        }
+        for (int c = 0; c < 9; c++) ps[3 + c] = cy.R[c];
         // 0 for a finite pose, NaN otherwise: added to every ray distance so that a blown-up state poisons the
         // radar outputs exactly like the reference's NaN propagation does
-        ps[12] = acc * T(0);
+        ps[12] = (((cy.pos[0] + cy.pos[1]) + (cy.pos[2] + att[0])) + (att[1] + att[2])) * T(0);
+        // obs[0:16] goes straight to its HBM row (four 16-byte stores); phase C zeroes the row if the env is reset
+        float4 *orow4 = reinterpret_cast<float4 *>(p.obs + i * p.n_obs);
+        if ((p.n_obs & 3) == 0) {
 #pragma unroll
-        for (int c = 0; c < 16; c++) s_obs[tid * L.obs_stride + c] = obs16[c];
+            for (int c = 0; c < 4; c++)
+                orow4[c] = make_float4(obs16[4 * c], obs16[4 * c + 1], obs16[4 * c + 2], obs16[4 * c + 3]);
+        } else {
+            float *orow = p.obs + i * p.n_obs;
+#pragma unroll
+            for (int c = 0; c < 16; c++) orow[c] = obs16[c];
+        }
     }
     __syncwarp();
 
@@ -152,7 +150,28 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                                         : p.spheres + (int64_t)((my_slot - n_caps) * 4) * N;
         const T fov_ty = p.fov_ty, fov_tz = p.fov_tz, fov_ny = p.fov_ny, fov_nz = p.fov_nz;
 
+        // raw obstacle of this lane's (env, slot) pair: loaded one sub-batch ahead so that the HBM latency of the
+        // next pre-pass is covered by the ray loop of the current one
+        auto load_obstacle = [&](int eb_, T ob[7]) {
+            const int e_ = eb_ + my_sub;
+            if (slot_used && e_ < n_warp) {
+                const T *g = obst_row + (i0 + e_warp + e_);
+                const int n_words = slot_is_cap ? 7 : 4;
+#pragma unroll
+                for (int c = 0; c < 7; c++)
+                    if (c < n_words) ob[c] = g[(int64_t)c * N];
+            }
+        };
+        T ob_next[7];
+#pragma unroll
+        for (int c = 0; c < 7; c++) ob_next[c] = T(0);
+        load_obstacle(0, ob_next);
+
         for (int eb = 0; eb < n_warp; eb += epp) {
+            T ob[7];
+#pragma unroll
+            for (int c = 0; c < 7; c++) ob[c] = ob_next[c];
+            if (eb + epp < n_warp) load_obstacle(eb + epp, ob_next);
             // ---- pass 1: one (env, obstacle) pair per lane
             bool hit_body = false, in_range = false;
             {
@@ -160,18 +179,12 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                 if (slot_used && e < n_warp) {
                     const T *pose = s_pose + (e_warp + e) * kPoseStride;
                     const T pos[3] = {pose[0], pose[1], pose[2]};
-                    const T *g = obst_row + (i0 + e_warp + e);
                     T *w = s_pre + lane * kPreStride;
                     T rad, dist;
                     T q0[3], q1[3];     // obstacle end points relative to the vehicle, NED
                     if (slot_is_cap) {
-                        T bot[3], top[3];
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            bot[c] = g[(int64_t)c * N];
-                            top[c] = g[(int64_t)(3 + c) * N];
-                        }
-                        rad = g[(int64_t)6 * N];
+                        const T bot[3] = {ob[0], ob[1], ob[2]}, top[3] = {ob[3], ob[4], ob[5]};
+                        rad = ob[6];
                         CapPre<T> q;
                         capsule_pre<T>(pos, bot, top, rad, q);
                         w[0] = q.ba[0]; w[1] = q.ba[1]; w[2] = q.ba[2];
@@ -198,10 +211,10 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                         T oc[3], d2 = T(0);
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
-                            oc[c] = pos[c] - g[(int64_t)c * N];
+                            oc[c] = pos[c] - ob[c];
                             d2 += oc[c] * oc[c];
                         }
-                        rad = g[(int64_t)3 * N];
+                        rad = ob[3];
                         w[0] = oc[0]; w[1] = oc[1]; w[2] = oc[2]; w[3] = d2 - rad * rad;
                         dist = Mth<T>::sqrt_(d2);
 #pragma unroll
@@ -309,8 +322,15 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                         }
                     }
                 }
-                // ---- clamp (sensor.py:117), obstacle-avoidance partial sum (docking3d.py:767-792), stash for pooling
                 const T poison = pose[12];
+                if (near_mask == 0u && poison == T(0) && p.dbg_ray_dist == nullptr && p.dbg_obs == nullptr) {
+                    // nothing within range and view: every ray reads max_dist (sensor.py:113-117), the pooled
+                    // observation is all ones and the obstacle-avoidance sum is sum(beta) (r_oa = 0)
+                    float *orow1 = p.obs + ie * p.n_obs + 16;
+                    for (int pc = lane; pc < p.n_rr; pc += 32) orow1[pc] = 1.0f;
+                    continue;            // my_oa_dot of the owner lane keeps its neutral value sum(beta)
+                }
+                // ---- clamp (sensor.py:117), obstacle-avoidance partial sum (docking3d.py:767-792), stash for pooling
                 T oa_part = T(0);
 #pragma unroll
                 for (int j = 0; j < RPL; j++) {
@@ -331,7 +351,7 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                 if (lane == e) my_oa_dot = oa_dot;
                 __syncwarp();
                 // ---- 2x2 max-pool with zero padding (sensor.py:131-137) -> obs[16:]
-                float *orow = s_obs + (e_warp + e) * L.obs_stride + 16;
+                float *orow = p.obs + ie * p.n_obs + 16;
                 if (fast_pool) {
                     if (lane < p.n_rr) {
                         T mx = s_ray[pidx[0]];
@@ -374,23 +394,17 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
         const T r_oa = p.sum_beta_oa / my_oa_dot - T(1);      // docking3d.py:792
         done = step_finish<T>(p, i, cy, r_oa, my_col, bs);
     }
-    __syncwarp();
-    // ---- each warp streams the observation rows of its own envs: one coalesced store per row segment
-    {
-        const int n_obs = p.n_obs;
-        const bool ar = p.auto_reset != 0;
-        const unsigned done_mask = __ballot_sync(0xffffffffu, done);
-        float *gobs = p.obs + (i0 + e_warp) * n_obs;
-        float *gterm = p.terminal_obs ? p.terminal_obs + (i0 + e_warp) * n_obs : nullptr;
-        for (int e = 0; e < n_warp; e++) {
-            const bool dn = (done_mask >> e) & 1u;
-            const float *row = s_obs + (e_warp + e) * L.obs_stride;
-            for (int c = lane; c < n_obs; c += 32) {
-                const float v = row[c];
-                if (dn && gterm) gterm[e * n_obs + c] = v;
-                gobs[e * n_obs + c] = (dn && ar) ? 0.0f : v;   // reset() returns the all-zero observation (docking3d.py:269,322)
-            }
+    __syncwarp();     // orders the pooled-cell stores of the other lanes before the row fix-up below
+    // ---- rows of envs whose episode ended: keep the last observation as terminal_observation, hand back the
+    //      all-zero reset observation (docking3d.py:269,322).  ~1 % of the envs per step.
+    if (done) {
+        float *row = p.obs + i * p.n_obs;
+        if (p.terminal_obs) {
+            float *trow = p.terminal_obs + i * p.n_obs;
+            for (int c = 0; c < p.n_obs; c++) trow[c] = row[c];
         }
+        if (p.auto_reset)
+            for (int c = 0; c < p.n_obs; c++) row[c] = 0.0f;
     }
     bs.flush(p.stats, warp == 0 ? n_here : 0);
 }
@@ -398,7 +412,7 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
 template <typename T, int VEH, int NU, int RPL>
 static cudaError_t launch_step_warp_rpl(const KParams<T> &k, cudaStream_t st) {
     const int64_t n = k.env_end - k.env_begin;
-    const WarpSmem<T> L(k.n_obs, k.n_rays);
+    const WarpSmem<T> L(k.n_rays);
     auto kern = step_warp_kernel<T, VEH, NU, RPL>;
     if (L.total > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
