@@ -21,7 +21,7 @@ SYMBOLS = {
     "dockauv_set_seed": (_i, [_vp, C.c_uint64]),
     "dockauv_reset": (_i, [_vp, _vp, _vp]),
     "dockauv_step": (_i, [_vp, _vp, _i, _vp, C.POINTER(DockauvStepOut), C.POINTER(DockauvDebugOut), _i, _vp]),
-    "dockauv_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i]),
+    "dockauv_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(DockauvStepOut)]),
     "dockauv_stats_ptr": (_i, [_vp, C.POINTER(_vp)]),
     "dockauv_get_stats": (_i, [_vp, C.POINTER(C.c_double), _vp]),
     "dockauv_clear_stats": (_i, [_vp, _vp]),

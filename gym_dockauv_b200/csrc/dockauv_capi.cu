@@ -414,7 +414,8 @@ static int ensure_host_pipeline(DockauvHandle *h, size_t action_bytes) {
 }
 
 extern "C" int dockauv_step_host(DockauvHandle *h, const void *actions_host, int action_dtype, float *obs_host,
-                                 void *reward_host, uint8_t *done_host, uint8_t *cond_bits_host, int auto_reset) {
+                                 void *reward_host, uint8_t *done_host, uint8_t *cond_bits_host, int auto_reset,
+                                 const DockauvStepOut *aux) {
     if (!h || !actions_host || !obs_host || !reward_host || !done_host) return fail(DOCKAUV_EINVAL, "null argument");
     if (!h->bound) return fail(DOCKAUV_ESTATE, "dockauv_bind must be called before dockauv_step_host");
     if (action_dtype != DOCKAUV_ACT_F32 && action_dtype != DOCKAUV_ACT_F64) return fail(DOCKAUV_EINVAL, "bad action dtype");
@@ -434,6 +435,11 @@ extern "C" int dockauv_step_host(DockauvHandle *h, const void *actions_host, int
     out.reward = h->st_reward;
     out.done = h->st_done;
     out.cond_bits = h->st_cond;
+    if (aux) {
+        out.terminal_obs = aux->terminal_obs;
+        out.ep_return_out = aux->ep_return_out;
+        out.ep_len_out = aux->ep_len_out;
+    }
     int c = 0;
     for (int64_t b = 0; b < N; b += chunk, c++) {
         const int64_t e = b + chunk < N ? b + chunk : N;

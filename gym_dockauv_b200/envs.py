@@ -221,7 +221,7 @@ class BaseDocking3d:
         _capi.check(self._lib.dockauv_step_host(self._handle, C.c_void_p(a.ctypes.data), adt,
                                                 C.c_void_p(hb["obs"].data_ptr()), C.c_void_p(hb["reward"].data_ptr()),
                                                 C.c_void_p(hb["done"].data_ptr()), C.c_void_p(hb["cond"].data_ptr()),
-                                                int(self.auto_reset)))
+                                                int(self.auto_reset), C.byref(self._out)))
         self.t_total_steps += 1
         return hb["obs"].numpy(), hb["reward"].numpy(), hb["done"].numpy().view(np.bool_), {"cond_bits": hb["cond"].numpy()}
 

@@ -212,9 +212,12 @@ DOCKAUV_API int dockauv_step(DockauvHandle *h, const void *actions_dev, int acti
 
 /* Same step with HOST buffers (pinned memory recommended): actions are copied in, obs/reward/done (and
  * cond_bits if non-NULL) are copied out, pipelined in chunks over the handle's internal streams; returns
- * after the results are in host memory.  reward_host is double[N] or float[N] per the handle precision. */
+ * after the results are in host memory.  reward_host is double[N] or float[N] per the handle precision.
+ * aux_dev_or_null: optional DEVICE buffers for the per-episode extras (only terminal_obs, ep_return_out and
+ * ep_len_out are read from it); they stay on the device, the caller fetches the few finished rows it needs. */
 DOCKAUV_API int dockauv_step_host(DockauvHandle *h, const void *actions_host, int action_dtype, float *obs_host,
-                      void *reward_host, uint8_t *done_host, uint8_t *cond_bits_host, int auto_reset);
+                      void *reward_host, uint8_t *done_host, uint8_t *cond_bits_host, int auto_reset,
+                      const DockauvStepOut *aux_dev_or_null);
 
 /* Episode statistics accumulated on the device since the last clear (DOCKAUV_STAT_*).  stats_dev points at
  * double[DOCKAUV_N_STATS] on the device: it is the send buffer of the per-rollout NCCL all-reduce. */

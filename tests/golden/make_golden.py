@@ -346,6 +346,21 @@ def record_unit_vectors():
     v.state[3:6] = [0.2, -0.3, 1.0]
     v.step(np.array([0.5, -0.25, 1.0, 0.1, -0.7, 0.3]), np.array([0.3, -0.1, 0.05, 0, 0, 0]))
     out["G2_state"] = v.state.copy()
+    # BlueROV2 control_mode="direct" (8 thrusters, BlueROV2.py:53-72): the env never selects it (docking3d.py:78), so
+    # it is pinned at the AUVSim level: 60 steps of vehicle.step() with random 8-dim actions and a constant current
+    v = BlueROV2(control_mode="direct")
+    v.step_size = 0.1
+    acts = rng.uniform(-0.25, 0.25, (60, 8))   # full-scale random thrust blows the explicit RK4 up at h = 0.1
+    nu_c = np.array([0.2, -0.1, 0.05, 0, 0, 0])
+    v.state = np.zeros(12)
+    v.state[3:6] = [0.1, -0.05, 0.7]
+    traj, us = [], []
+    for a in acts:
+        v.step(a, nu_c)
+        traj.append(v.state.copy())
+        us.append(v.u.copy())
+    out["direct_actions"], out["direct_states"], out["direct_u"] = acts, np.array(traj), np.array(us)
+    out["direct_nu_c"] = nu_c
     # radar tables
     for tag, kw in (("stock", BASE_CONFIG["radar"]), ("r64", {**BASE_CONFIG["radar"], **RADAR64})):
         r = Radar(eta=np.zeros(6), **kw)

@@ -165,15 +165,80 @@ def test_lauv_current_rollout_vs_oracle():
 
 
 def test_fp32_variant():
-    """FP32 kernels: stated looser bound.  Over 50 steps from identical initial conditions the FP32 state stays
-    within 2e-4 (relative, floor 1.0) of the FP64 oracle and single-step rewards within 1e-3; flags may differ only
-    for envs sitting on a threshold, so at most 0.5 % of (env, step) pairs may disagree."""
+    """FP32 kernels (precision="f32"): the stated looser bound.  2048 envs of the C4 workload, 60 steps from identical
+    initial conditions against the FP64 oracle, comparing every env until its first episode end on either side:
+    state within 2e-5, reward within 5e-5, observation within 5e-4 (relative, floor 1.0; measured 3.6e-6 / 1.7e-5 /
+    3e-4, profiles/tools/fp32_check.py), done flags may differ for at most 0.1 % of the envs (threshold crossings)."""
+    import torch
+    from gym_dockauv_b200 import envs
     from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
+    from oracle import oracle as orc
     cfg = dict(BASE_CONFIG)
     cfg["radar"] = dict(RADAR_64)
-    r = _oracle_rollout(cfg, "ObstaclesDocking3d", 512, 50, seed=9, n_synth=3, dtype=np.float32, layout="warp_rays",
-                        precision="f32")
-    assert r["done_mismatch"] <= 0.005 * 512 * 50, r
+    n = 2048
+    env = envs.ObstaclesDocking3d(cfg, num_envs=n, seed=9, n_synthetic_spheres=3, precision="f32")
+    env.reset()
+    bo = orc.BatchOracle(cfg, "ObstaclesDocking3d", n, seed=9, n_extra_spheres=3)
+    assert env.state.dtype == torch.float32 and env.reward.dtype == torch.float32
+    rng = np.random.default_rng(9)
+    alive = np.ones(n, bool)
+    mismatches, worst = 0, dict(state=0.0, reward=0.0, obs=0.0)
+    for t in range(60):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        obs, rew, done, _ = env.step(torch.as_tensor(a, device=env.device))
+        robs, rrew, rdone, _ = bo.step(a)
+        d, rd = done.cpu().numpy().astype(bool), rdone.astype(bool)
+        mismatches += int(((d != rd) & alive).sum())
+        m = alive & ~d & ~rd
+        worst["state"] = max(worst["state"], rel_err(env.state.t().cpu().numpy().astype(np.float64)[m], bo.field("state")[m]))
+        worst["reward"] = max(worst["reward"], rel_err(rew.cpu().numpy().astype(np.float64)[alive], rrew[alive]))
+        worst["obs"] = max(worst["obs"], rel_err(obs.cpu().numpy()[m], robs[m]))
+        alive &= ~(d | rd)
+    assert alive.sum() > n // 3
+    assert worst["state"] < 2e-5 and worst["reward"] < 5e-5 and worst["obs"] < 5e-4, worst
+    assert mismatches <= n // 1000, mismatches
+    env.close()
+
+
+def test_bluerov2_direct_mode_vs_reference():
+    """control_mode="direct" (n_u = 8, dense 6 x 8 thrust map): 60 AUVSim steps recorded from the reference with a
+    constant current; the CUDA env is driven with an injected constant current of the same body-frame value by
+    freezing the attitude dependence: compared on state and command with the current switched off instead."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.config import BASE_CONFIG
+    from oracle import oracle as orc
+    import ctypes as C
+    uv = np.load(__import__("os").path.join(__import__("tests.golden_utils", fromlist=["GOLDEN_DIR"]).GOLDEN_DIR,
+                                            "unit_vectors.npz"))
+    # reference trace has a constant body-frame current, which the env API cannot express (the env rotates a NED
+    # current); so: oracle (pinned to that trace by tests/test_oracle_golden.py) vs CUDA on a no-current rollout
+    cfg = dict(BASE_CONFIG)
+    P = orc.make_params(cfg, vehicle_key="BlueROV2_direct")
+    L = orc.lib()
+    L.orc_auv_step.argtypes = [C.POINTER(orc.OrcParams), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p,
+                               C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    env = envs.SimpleDocking3d(cfg, num_envs=4, control_mode="direct", auto_reset=False)
+    assert env.n_actions == 8
+    st0 = np.zeros((4, 12))
+    st0[:, 3:6] = [0.1, -0.05, 0.7]
+    st0[:, 0] = [1.0, 2.0, 3.0, 4.0]
+    env.set_state(state=st0, goal=np.zeros((4, 3)), heading_goal=np.zeros(4), current=np.zeros((4, 5)),
+                  u_prev=np.zeros((4, 8)), t_steps=np.zeros(4), ep_return=np.zeros(4))
+    ref_state = st0.copy()
+    ref_u = np.zeros((4, 8))
+    sd = np.zeros(12)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+    for t, a in enumerate(uv["direct_actions"][:40]):
+        acts = np.tile(a, (4, 1)) * np.array([[1.0], [0.5], [-0.7], [0.2]])
+        env.step(torch.as_tensor(acts, device=env.device))
+        for e in range(4):
+            s_e, u_e, a_e = ref_state[e].copy(), ref_u[e].copy(), np.ascontiguousarray(acts[e])
+            L.orc_auv_step(C.byref(P), dp(s_e), dp(u_e), a_e.ctypes.data_as(C.c_void_p), 0, dp(np.zeros(6)), dp(sd))
+            ref_state[e], ref_u[e] = s_e, u_e
+        assert rel_err(env.state.t().cpu().numpy(), ref_state) < TOL, t
+        assert rel_err(env.u_prev.t().cpu().numpy(), ref_u) < TOL, t
+    env.close()
 
 
 def test_step_host_matches_device_step():

@@ -210,6 +210,22 @@ def test_auvsim_golden_G1_G2():
     assert rel_err(state, uv["G2_state"], floor=1e-2) < 1e-13
 
 
+def test_bluerov2_direct_mode():
+    """BlueROV2 control_mode="direct" (6 x 8 thrust map, BlueROV2.py:53-72) at the AUVSim level."""
+    uv = unit_vectors()
+    L = orc.lib()
+    P = orc.make_params(_base_config(), vehicle_key="BlueROV2_direct")
+    assert P.n_u == 8
+    L.orc_auv_step.argtypes = [C.POINTER(orc.OrcParams), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p,
+                               C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    state, u, sd = np.zeros(12), np.zeros(8), np.zeros(12)
+    state[3:6] = [0.1, -0.05, 0.7]
+    for t, a in enumerate(uv["direct_actions"]):
+        a = np.ascontiguousarray(a)
+        L.orc_auv_step(C.byref(P), _dp(state), _dp(u), a.ctypes.data_as(C.c_void_p), 0, _dp(uv["direct_nu_c"]), _dp(sd))
+        assert rel_err(state, uv["direct_states"][t]) < 1e-11 and rel_err(u, uv["direct_u"][t]) < 1e-13, t
+
+
 @pytest.mark.parametrize("tag", ["stock", "r64"])
 def test_radar_table_pool_and_oa(tag):
     """sensor.py:43-71 ray table, :131-137 block_reduce (2x2 max, zero padded -- the one third-party op on the
