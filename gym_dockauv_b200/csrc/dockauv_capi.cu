@@ -134,6 +134,9 @@ static void fill_kparams(const DockauvParams &s, int64_t n_envs, KParams<T> &k) 
     k.dist_goal_reached_tol = (T)s.dist_goal_reached_tol;
     k.u_max = (T)s.u_max; k.v_max = (T)s.v_max; k.w_max = (T)s.w_max;
     k.p_max = (T)s.p_max; k.q_max = (T)s.q_max; k.r_max = (T)s.r_max;
+    k.inv_u_max = (T)(1.0 / s.u_max); k.inv_v_max = (T)(1.0 / s.v_max); k.inv_w_max = (T)(1.0 / s.w_max);
+    k.inv_p_max = (T)(1.0 / s.p_max); k.inv_q_max = (T)(1.0 / s.q_max); k.inv_r_max = (T)(1.0 / s.r_max);
+    k.inv_max_attitude = (T)(1.0 / s.max_attitude);
     k.log_den_obs = (T)std::log(s.dist_goal_reached_tol / s.max_dist_from_goal);
     k.log_den_rew = (T)std::log(std::fmax(s.dist_goal_reached_tol, 0.001) / s.max_dist_from_goal);
     k.w_d = (T)s.w_d; k.w_delta_psi = (T)s.w_delta_psi; k.w_delta_theta = (T)s.w_delta_theta;
@@ -293,9 +296,9 @@ static bool scenario_has_current(int scn) {
 
 static int resolve_layout(const DockauvHandle *h) {
     int layout = h->params.layout;
-    if (layout == DOCKAUV_LAYOUT_AUTO)
-        layout = (h->params.n_capsules + h->params.n_spheres) > 0 ? DOCKAUV_LAYOUT_WARP_RAYS
-                                                                  : DOCKAUV_LAYOUT_THREAD_PER_ENV;
+    // the warp layout wins in every measured scenario, obstacle-free ones included (its ray pass degenerates to a
+    // per-env skip, 0.56 ms vs 0.82 ms per 1M envs for SimpleDocking3d); thread-per-env stays as the cross-check
+    if (layout == DOCKAUV_LAYOUT_AUTO) layout = DOCKAUV_LAYOUT_WARP_RAYS;
     return layout;
 }
 

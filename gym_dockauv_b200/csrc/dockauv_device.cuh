@@ -31,6 +31,7 @@ struct Mth<double> {
     static constexpr double pi = 3.141592653589793;
     static constexpr double two_pi = 6.283185307179586;
     static constexpr double half_pi = 1.5707963267948966;
+    static constexpr double inv_pi = 0.3183098861837907, inv_half_pi = 0.6366197723675814;
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
     static __device__ __forceinline__ double nan() { return CUDART_NAN; }
     static __device__ __forceinline__ void sincos_(double x, double *s, double *c) {
@@ -53,6 +54,7 @@ struct Mth<float> {
     static constexpr float pi = 3.14159265358979f;
     static constexpr float two_pi = 6.28318530717959f;
     static constexpr float half_pi = 1.57079632679490f;
+    static constexpr float inv_pi = 0.318309886183791f, inv_half_pi = 0.636619772367581f;
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
     static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
     static __device__ __forceinline__ void sincos_(float x, float *s, float *c) { sincosf(x, s, c); }

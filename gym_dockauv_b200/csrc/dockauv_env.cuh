@@ -130,6 +130,8 @@ struct StepCarry {
     T rarr[13];        // reward_arr (only [0..5], [7] filled here)
     uint32_t cond;     // bits 0..3
     T delta_d;
+    int32_t t_steps;   // episode step counter before this step
+    T ep_return;       // cumulative reward before this step
 };
 
 // action -> low-passed command (auvsim.py:67-87, lowpassfilter.py:29-42) and the action penalty

@@ -27,7 +27,10 @@ struct KParams {
     T lp_alpha, h, safety_radius;
     // env
     T max_dist_from_goal, max_attitude, dist_goal_reached_tol;
-    T inv_u_max, u_max, v_max, w_max, p_max, q_max, r_max;
+    T u_max, v_max, w_max, p_max, q_max, r_max;
+    // reciprocals of the observation / reward normalisers (docking3d.py:467-483, 520-558): one multiply instead of a
+    // ~25-instruction IEEE division each; the quotient may differ from numpy's by one ulp (1.1e-16 relative)
+    T inv_u_max, inv_v_max, inv_w_max, inv_p_max, inv_q_max, inv_r_max, inv_max_attitude;
     T log_den_obs;    // log(dist_goal_reached_tol / max_dist_from_goal), docking3d.py:465-466
     T log_den_rew;    // log(max(tol, 1e-3) / max_dist), docking3d.py:723
     T w_d, w_delta_psi, w_delta_theta, w_phi, w_theta, w_Thetadot, w_oa;

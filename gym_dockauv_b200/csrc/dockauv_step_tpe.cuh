@@ -18,6 +18,13 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
 #pragma unroll
     for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
+    // everything else this step reads is requested up front so that one HBM round trip covers all of it
+    T goal[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) goal[c] = p.goal[(int64_t)c * N + i];
+    const int32_t t_steps = p.t_steps[i];
+    cy.t_steps = t_steps;
+    cy.ep_return = p.ep_return[i];
 
     // ---- ocean current: Current.sim (current.py:78-96) then nu_c from the PRE-step attitude (docking3d.py:348-349)
     T nu_c[3] = {T(0), T(0), T(0)};
@@ -101,7 +108,7 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     // ---- navigation errors (docking3d.py:404-413)
     T diff[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) diff[c] = p.goal[(int64_t)c * N + i] - pos[c];
+    for (int c = 0; c < 3; c++) diff[c] = goal[c] - pos[c];
     T dxy2 = diff[0] * diff[0] + diff[1] * diff[1];
     T delta_d = Mth<T>::sqrt_(dxy2 + diff[2] * diff[2]);
     T delta_theta = y[1] + ssa<T>(Mth<T>::atan2_(diff[2], Mth<T>::sqrt_(dxy2)));
@@ -113,18 +120,18 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     T o[16];
     T lg = Mth<T>::log_(delta_d / p.max_dist_from_goal);
     o[0] = clipv(T(1) - lg / p.log_den_obs, T(0), T(1));
-    o[1] = clipv(delta_theta / Mth<T>::half_pi, T(-1), T(1));
-    o[2] = clipv(delta_psi / Mth<T>::pi, T(-1), T(1));
-    o[3] = clipv(nu[0] / p.u_max, T(-1), T(1));
-    o[4] = clipv(nu[1] / p.v_max, T(-1), T(1));
-    o[5] = clipv(nu[2] / p.w_max, T(-1), T(1));
-    o[6] = clipv(y[0] / p.max_attitude, T(-1), T(1));
-    o[7] = clipv(y[1] / p.max_attitude, T(-1), T(1));
+    o[1] = clipv(delta_theta * Mth<T>::inv_half_pi, T(-1), T(1));
+    o[2] = clipv(delta_psi * Mth<T>::inv_pi, T(-1), T(1));
+    o[3] = clipv(nu[0] * p.inv_u_max, T(-1), T(1));
+    o[4] = clipv(nu[1] * p.inv_v_max, T(-1), T(1));
+    o[5] = clipv(nu[2] * p.inv_w_max, T(-1), T(1));
+    o[6] = clipv(y[0] * p.inv_max_attitude, T(-1), T(1));
+    o[7] = clipv(y[1] * p.inv_max_attitude, T(-1), T(1));
     o[8] = clipv(spsi, T(-1), T(1));
     o[9] = clipv(cpsi, T(-1), T(1));
-    o[10] = clipv(nu[3] / p.p_max, T(-1), T(1));
-    o[11] = clipv(nu[4] / p.q_max, T(-1), T(1));
-    o[12] = clipv(nu[5] / p.r_max, T(-1), T(1));
+    o[10] = clipv(nu[3] * p.inv_p_max, T(-1), T(1));
+    o[11] = clipv(nu[4] * p.inv_q_max, T(-1), T(1));
+    o[12] = clipv(nu[5] * p.inv_r_max, T(-1), T(1));
     o[13] = clipv(nu_c[0] / T(2), T(-1), T(1));
     o[14] = clipv(nu_c[1] / T(2), T(-1), T(1));
     o[15] = clipv(nu_c[2] / T(2), T(-1), T(1));
@@ -132,7 +139,6 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     for (int c = 0; c < 16; c++) obs16[c] = (float)o[c];
 
     // ---- is_done conditions 0..3 (docking3d.py:606-615; t_steps is the value before the increment)
-    int32_t t_steps = p.t_steps[i];
     uint32_t cond = 0;
     cond |= (delta_d < p.dist_goal_reached_tol) ? 1u : 0u;
     cond |= (delta_d > p.max_dist_from_goal) ? 2u : 0u;
@@ -150,7 +156,7 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     }
     r[0] = -p.w_d * lp_d;
     if (p.reward_set == 1) {
-        T a = delta_theta / Mth<T>::half_pi, b = delta_psi / Mth<T>::pi;
+        T a = delta_theta * Mth<T>::inv_half_pi, b = delta_psi * Mth<T>::inv_pi;
         r[1] = -p.w_delta_theta * (a * a);
         r[2] = -p.w_delta_psi * (b * b);
     } else {
@@ -158,10 +164,10 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
         r[2] = -p.w_delta_psi * cont_goal_constraints<T>(Mth<T>::abs_(delta_psi), Mth<T>::pi, lp_d);
     }
     {
-        T a = y[0] / Mth<T>::half_pi, b = y[1] / Mth<T>::half_pi;
+        T a = y[0] * Mth<T>::inv_half_pi, b = y[1] * Mth<T>::inv_half_pi;
         r[3] = -p.w_phi * (a * a);
         r[4] = -p.w_theta * (b * b);
-        T nrm = Mth<T>::sqrt_(ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]) / p.p_max;
+        T nrm = Mth<T>::sqrt_(ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]) * p.inv_p_max;
         r[5] = -p.w_Thetadot * (nrm * nrm);
     }
     r[6] = lp_d;   // parked here for reward_set 2 (overwritten by the obstacle-avoidance term)
@@ -201,8 +207,8 @@ __device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, Step
     p.reward[i] = reward;
     p.done[i] = done ? 1 : 0;
     if (p.cond_bits) p.cond_bits[i] = (uint8_t)cond;
-    T ep_ret = p.ep_return[i] + reward;
-    int32_t t_new = p.t_steps[i] + 1;
+    T ep_ret = cy.ep_return + reward;
+    int32_t t_new = cy.t_steps + 1;
     if (p.dbg_reward_arr)
         for (int k = 0; k < 13; k++) p.dbg_reward_arr[(int64_t)k * N + i] = r[k];
     if (done) {

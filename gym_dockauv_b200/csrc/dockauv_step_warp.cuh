@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
     // ------------------------------------------------------------------ phase B
     T my_oa_dot = p.sum_beta_oa;     // owner-lane copies of the per-env radar results (neutral values: r_oa = 0)
     bool my_col = false;
+    bool my_view_empty = true;       // nothing within range and view: the owner lane writes the all-ones ray cells
+    const bool no_dbg = p.dbg_ray_dist == nullptr && p.dbg_obs == nullptr;
     {
         T *s_pre = reinterpret_cast<T *>(smem_raw + L.pre_off) + warp * 32 * kPreStride;
         T *s_ray = reinterpret_cast<T *>(smem_raw + L.ray_off) + warp * L.ray_stride;
@@ -249,7 +251,10 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
             const unsigned nearb = __ballot_sync(0xffffffffu, in_range);
             {   // the owner lane of each env of this sub-batch keeps its collision flag for phase C
                 const int s = lane - eb;
-                if (s >= 0 && s < epp) my_col = ((colb >> (slots * s)) & slot_mask) != 0u;
+                if (s >= 0 && s < epp) {
+                    my_col = ((colb >> (slots * s)) & slot_mask) != 0u;
+                    my_view_empty = ((nearb >> (slots * s)) & slot_mask) == 0u;
+                }
             }
             __syncwarp();
 
@@ -323,12 +328,11 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                     }
                 }
                 const T poison = pose[12];
-                if (near_mask == 0u && poison == T(0) && p.dbg_ray_dist == nullptr && p.dbg_obs == nullptr) {
+                if (near_mask == 0u && poison == T(0) && no_dbg) {
                     // nothing within range and view: every ray reads max_dist (sensor.py:113-117), the pooled
-                    // observation is all ones and the obstacle-avoidance sum is sum(beta) (r_oa = 0)
-                    float *orow1 = p.obs + ie * p.n_obs + 16;
-                    for (int pc = lane; pc < p.n_rr; pc += 32) orow1[pc] = 1.0f;
-                    continue;            // my_oa_dot of the owner lane keeps its neutral value sum(beta)
+                    // observation is all ones (written by the owner lane in phase C) and the obstacle-avoidance
+                    // sum keeps its neutral value sum(beta) (r_oa = 0)
+                    continue;
                 }
                 // ---- clamp (sensor.py:117), obstacle-avoidance partial sum (docking3d.py:767-792), stash for pooling
                 T oa_part = T(0);
@@ -391,6 +395,15 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
     // ------------------------------------------------------------------ phase C
     bool done = false;
     if (active) {
+        if (my_view_empty && no_dbg && s_pose[tid * kPoseStride + 12] == T(0)) {
+            float *cells = p.obs + i * p.n_obs + 16;
+            if ((p.n_obs & 3) == 0 && (p.n_rr & 3) == 0) {
+                float4 *c4 = reinterpret_cast<float4 *>(cells);
+                for (int c = 0; c < (p.n_rr >> 2); c++) c4[c] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            } else {
+                for (int c = 0; c < p.n_rr; c++) cells[c] = 1.0f;
+            }
+        }
         const T r_oa = p.sum_beta_oa / my_oa_dot - T(1);      // docking3d.py:792
         done = step_finish<T>(p, i, cy, r_oa, my_col, bs);
     }
