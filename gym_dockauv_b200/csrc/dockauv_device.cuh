@@ -129,6 +129,15 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t env_id,
     return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// both uniforms of Philox block `blk` of the stream (seed, env id, episode): u[0] = draw 2*blk, u[1] = draw 2*blk+1
+__device__ __forceinline__ void philox_uniform_pair(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t blk,
+                                                    double u[2]) {
+    uint32_t c[4] = {(uint32_t)env_id, (uint32_t)(env_id >> 32), episode, blk};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    u[0] = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6)) * (1.0 / 9007199254740992.0);
+    u[1] = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) * (1.0 / 9007199254740992.0);
+}
+
 // standard normal from the per-step stream (Box-Muller); counter word 3 = 0x80000000 | t_steps keeps it apart
 // from the reset stream of the same episode.
 __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t t_steps) {

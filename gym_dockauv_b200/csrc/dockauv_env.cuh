@@ -18,7 +18,13 @@ static __device__ __noinline__ void reset_env(const KParams<T> &p, int64_t i) {
     const uint32_t ep = (uint32_t)p.episode[i];
     p.episode[i] = (int32_t)(ep + 1);
     const double PI = 3.141592653589793;
-    auto U = [&](uint32_t idx) { return philox_uniform(p.seed, gid, ep, idx); };
+    // all draws of this reset up front, one Philox block per two uniforms (slots 0..12 always, 13.. for the
+    // synthetic spheres); a reset runs with one or two active lanes per warp, so its instruction count matters
+    double uu[14 + 3 * DOCKAUV_MAX_SPHERES];
+    const int n_draws = 13 + 3 * min(p.n_synth_sph, p.n_sph);
+#pragma unroll 1
+    for (int b = 0; 2 * b < n_draws; b++) philox_uniform_pair(p.seed, gid, ep, (uint32_t)b, uu + 2 * b);
+    auto U = [&](uint32_t idx) { return uu[idx]; };
 
     double goal[3] = {0.0, 0.0, 0.0};
     double heading = (U(0) - 0.5) * PI;                                   // :814
