@@ -27,6 +27,9 @@ import numpy as np  # noqa: E402
 BYTES_PER_ENV_STEP = 898      # algorithmic HBM bytes per env-step for C4 (FP64 SoA, f32 obs/actions)
 FLOPS_PER_ENV_STEP = 17700    # algorithmic flops per env-step for C4
 HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE step_warp_kernel launch over 1,048,576 envs (FP64) from the
+# committed `ncu --set full` capture profiles/r01/v6_step_warp_ncu_raw.csv: 614.8 MB + 337.2 MB
+NCU_TRAFFIC_BYTES_1M_F64 = 951.9e6
 SCENARIO = "ObstaclesDocking3d"
 N_SYNTH_SPHERES = 3
 
@@ -59,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -266,7 +269,10 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                         "frac": achieved_gbs / hbm_peak,
+                         "traffic": NCU_TRAFFIC_BYTES_1M_F64 if (N == 1 << 20 and args.precision == "f64") else None,
+                         "traffic_source": "profiles/r01/v6_step_warp_ncu_raw.csv (bytes per launch)",
+                         "peak_source": hbm_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kern_ms,
                          "note": "the path is FP64-pipe-bound (19.7 flop/B vs machine balance ~5.7), see 'pipe'"},
             "pipe": {"bound": "fp64" if args.precision == "f64" else "fp32", "achieved": achieved_tf,
