@@ -57,6 +57,7 @@ struct DockauvHandle {
     KParams<double> kd;
     KParams<float> kf;
     void *ray_tab = nullptr;
+    void *handoff = nullptr;       // split layout only
     double *stats = nullptr;
     int64_t launches = 0;
     bool timing = false;
@@ -237,6 +238,25 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         h->kd.stats = h->stats;
         h->kf.stats = h->stats;
     }
+    if (p->layout == DOCKAUV_LAYOUT_SPLIT ||
+        (p->layout == DOCKAUV_LAYOUT_AUTO && (p->n_capsules + p->n_spheres) > 0)) {
+        const size_t esz = p->precision == DOCKAUV_F64 ? 8 : 4;
+        const size_t words = (size_t)22 * (size_t)n_envs * esz;
+        cudaError_t e5 = cudaMalloc(&h->handoff, words + sizeof(uint32_t) * (size_t)n_envs);
+        if (e5 != cudaSuccess) {
+            cudaFree(h->ray_tab);
+            cudaFree(h->stats);
+            delete h;
+            return fail(DOCKAUV_ECUDA, "device allocation of the hand-off buffer failed: %s", cudaGetErrorString(e5));
+        }
+        h->kd.handoff = (double *)h->handoff;
+        h->kf.handoff = (float *)h->handoff;
+        h->kd.handoff_cond = h->kf.handoff_cond = (uint32_t *)((char *)h->handoff + words);
+        // one launch pair over the whole batch by default: smaller chunks would keep the hand-off in L2 but lose more
+        // to partial waves than they gain (0.89 ms at 1M envs per pair, 0.94 at 512K, 1.04 at 256K)
+        const int64_t chunk = p->split_chunk_envs > 0 ? p->split_chunk_envs : n_envs;
+        h->kd.split_chunk = h->kf.split_chunk = chunk;
+    }
     *out = h;
     return DOCKAUV_OK;
 }
@@ -246,6 +266,7 @@ extern "C" int dockauv_destroy(DockauvHandle *h) {
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     if (h->ray_tab) cudaFree(h->ray_tab);
+    if (h->handoff) cudaFree(h->handoff);
     if (h->stats) cudaFree(h->stats);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -296,9 +317,11 @@ static bool scenario_has_current(int scn) {
 
 static int resolve_layout(const DockauvHandle *h) {
     int layout = h->params.layout;
-    // the warp layout wins in every measured scenario, obstacle-free ones included (its ray pass degenerates to a
-    // per-env skip, 0.56 ms vs 0.82 ms per 1M envs for SimpleDocking3d); thread-per-env stays as the cross-check
-    if (layout == DOCKAUV_LAYOUT_AUTO) layout = DOCKAUV_LAYOUT_WARP_RAYS;
+    // measured on B200 (profiles/r01/NOTES.md): with obstacles the two-launch split layout is ~12 % faster than the
+    // fused kernel (0.89 vs 1.00 ms per 1M envs on C4), without obstacles the fused kernel wins marginally;
+    // thread-per-env stays as the independently written cross-check
+    if (layout == DOCKAUV_LAYOUT_AUTO)
+        layout = (h->params.n_capsules + h->params.n_spheres) > 0 ? DOCKAUV_LAYOUT_SPLIT : DOCKAUV_LAYOUT_WARP_RAYS;
     return layout;
 }
 
@@ -349,7 +372,12 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
         e = launch_step<float>(k, h->params.vehicle, layout, st);
     }
     if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
-    h->launches += 1;
+    if (layout == DOCKAUV_LAYOUT_SPLIT) {
+        const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
+        h->launches += 2 * ((end - begin + chunk - 1) / chunk);
+    } else {
+        h->launches += 1;
+    }
     return DOCKAUV_OK;
 }
 

@@ -10,6 +10,7 @@ static cudaError_t launch_variant(const KParams<T> &k, int layout, cudaStream_t 
     const int64_t n = k.env_end - k.env_begin;
     if (n <= 0) return cudaSuccess;
     if (layout == DOCKAUV_LAYOUT_WARP_RAYS) return launch_step_warp<T, VEH, NU>(k, st);
+    if (layout == DOCKAUV_LAYOUT_SPLIT) return launch_step_split<T, VEH, NU>(k, k.split_chunk, st);
     const int threads = 128;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
     step_tpe_kernel<T, VEH, NU><<<blocks, threads, 0, st>>>(k);

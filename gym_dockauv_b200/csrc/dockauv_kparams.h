@@ -55,6 +55,10 @@ struct KParams {
     int32_t *ep_len_out;
     // debug outputs
     T *dbg_ray_dist, *dbg_reward_arr, *dbg_euler_dot, *dbg_nu_c, *dbg_nav, *dbg_obs;
+    // hand-off between the two launches of the split layout (library-owned): T[22][n_envs] + u32[n_envs]
+    T *handoff;
+    uint32_t *handoff_cond;
+    int64_t split_chunk;
     // stats accumulator (double[DOCKAUV_N_STATS])
     double *stats;
     // ray table in global memory (lane-indexed reads in the warp layout): rd_b[3][n_rays], beta_oa[n_rays]

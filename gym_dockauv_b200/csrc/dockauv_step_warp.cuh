@@ -61,8 +61,24 @@ struct Pair<float> {
 
 // no min-CTAs hint on purpose: __launch_bounds__(128, 3) ends at the same 168 registers but a 6 % slower schedule,
 // (128, 4) and (128, 5) spill (measured on B200, profiles/r01/NOTES.md)
-template <typename T, int VEH, int NU, int RPL>
-__global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_constant__ KParams<T> p) {
+// MODE 0: fused step (phases A, B, C in one launch).
+// MODE 1 / 2: the same step as two launches (layout DOCKAUV_LAYOUT_SPLIT): MODE 1 runs phase A and parks the post-step
+// pose and the radar-independent reward terms in a hand-off buffer (kHandoffWords words + one flag word per env, SoA);
+// MODE 2 picks them up and runs phases B and C.  Each launch then gets its own register allocation (phase A needs
+// 168 registers, phases B/C far fewer -> more resident warps for the latency-bound ray pass) and the ray loop no
+// longer shares the instruction cache with the 70 KB of straight-line integrator code.
+constexpr int kHandoffWords = 22;    // pos[3] R[9] poison | reward terms r[0..7] | delta_d
+
+#ifndef DOCKAUV_MINB_A
+#define DOCKAUV_MINB_A 4
+#endif
+#ifndef DOCKAUV_MINB_B
+#define DOCKAUV_MINB_B 4
+#endif
+// min-CTAs hints (0 = none): the fused kernel is fastest without one; measured for the split pair in profiles/r01/NOTES.md
+template <typename T, int VEH, int NU, int RPL, int MODE>
+__global__ void __launch_bounds__(kWarpEnvs, MODE == 1 ? DOCKAUV_MINB_A : (MODE == 2 ? DOCKAUV_MINB_B : 0))
+step_warp_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using P2 = typename Pair<T>::type;
     const WarpSmem<T> L(p.n_rays);
@@ -81,18 +97,32 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
 
     // ------------------------------------------------------------------ phase A
     StepCarry<T> cy;
-    if (active) {
+    if (MODE != 2 && active) {
         T spsi, cpsi, att[3];
         float obs16[16];
         step_dynamics<T, VEH, NU>(p, i, cy, spsi, cpsi, obs16, att);
-        T *ps = s_pose + tid * kPoseStride;
-#pragma unroll
-        for (int c = 0; c < 3; c++) ps[c] = cy.pos[c];
-#pragma unroll
-        for (int c = 0; c < 9; c++) ps[3 + c] = cy.R[c];
         // 0 for a finite pose, NaN otherwise: added to every ray distance so that a blown-up state poisons the
         // radar outputs exactly like the reference's NaN propagation does
-        ps[12] = (((cy.pos[0] + cy.pos[1]) + (cy.pos[2] + att[0])) + (att[1] + att[2])) * T(0);
+        const T poison = (((cy.pos[0] + cy.pos[1]) + (cy.pos[2] + att[0])) + (att[1] + att[2])) * T(0);
+        if (MODE == 0) {
+            T *ps = s_pose + tid * kPoseStride;
+#pragma unroll
+            for (int c = 0; c < 3; c++) ps[c] = cy.pos[c];
+#pragma unroll
+            for (int c = 0; c < 9; c++) ps[3 + c] = cy.R[c];
+            ps[12] = poison;
+        } else {
+            T *hf = p.handoff + i;
+#pragma unroll
+            for (int c = 0; c < 3; c++) hf[(int64_t)c * N] = cy.pos[c];
+#pragma unroll
+            for (int c = 0; c < 9; c++) hf[(int64_t)(3 + c) * N] = cy.R[c];
+            hf[(int64_t)12 * N] = poison;
+#pragma unroll
+            for (int c = 0; c < 8; c++) hf[(int64_t)(13 + c) * N] = cy.rarr[c];
+            hf[(int64_t)21 * N] = cy.delta_d;
+            p.handoff_cond[i] = cy.cond;
+        }
         // obs[0:16] goes straight to its HBM row (four 16-byte stores); phase C zeroes the row if the env is reset
         float4 *orow4 = reinterpret_cast<float4 *>(p.obs + i * p.n_obs);
         if ((p.n_obs & 3) == 0) {
@@ -104,6 +134,19 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
 #pragma unroll
             for (int c = 0; c < 16; c++) orow[c] = obs16[c];
         }
+    }
+    if (MODE == 1) return;
+    if (MODE == 2 && active) {
+        const T *hf = p.handoff + i;
+        T *ps = s_pose + tid * kPoseStride;
+#pragma unroll
+        for (int c = 0; c < 13; c++) ps[c] = hf[(int64_t)c * N];
+#pragma unroll
+        for (int c = 0; c < 8; c++) cy.rarr[c] = hf[(int64_t)(13 + c) * N];
+        cy.delta_d = hf[(int64_t)21 * N];
+        cy.cond = p.handoff_cond[i];
+        cy.t_steps = p.t_steps[i];
+        cy.ep_return = p.ep_return[i];
     }
     __syncwarp();
 
@@ -422,25 +465,46 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
     bs.flush(p.stats, warp == 0 ? n_here : 0);
 }
 
-template <typename T, int VEH, int NU, int RPL>
+template <typename T, int VEH, int NU, int RPL, int MODE>
 static cudaError_t launch_step_warp_rpl(const KParams<T> &k, cudaStream_t st) {
     const int64_t n = k.env_end - k.env_begin;
     const WarpSmem<T> L(k.n_rays);
-    auto kern = step_warp_kernel<T, VEH, NU, RPL>;
-    if (L.total > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    const int smem = MODE == 1 ? 0 : L.total;
+    auto kern = step_warp_kernel<T, VEH, NU, RPL, MODE>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
     }
     const unsigned blocks = (unsigned)((n + kWarpEnvs - 1) / kWarpEnvs);
-    kern<<<blocks, kWarpEnvs, L.total, st>>>(k);
+    kern<<<blocks, kWarpEnvs, smem, st>>>(k);
     return cudaGetLastError();
 }
 
+// rays per lane: 2 covers the stock 63-ray and the 64-ray radar; 8 covers everything up to DOCKAUV_MAX_RAYS
 template <typename T, int VEH, int NU>
 static cudaError_t launch_step_warp(const KParams<T> &k, cudaStream_t st) {
-    // rays per lane: 2 covers the stock 63-ray and the 64-ray radar; 8 covers everything up to DOCKAUV_MAX_RAYS
-    if (k.n_rays <= 64) return launch_step_warp_rpl<T, VEH, NU, 2>(k, st);
-    return launch_step_warp_rpl<T, VEH, NU, 8>(k, st);
+    if (k.n_rays <= 64) return launch_step_warp_rpl<T, VEH, NU, 2, 0>(k, st);
+    return launch_step_warp_rpl<T, VEH, NU, 8, 0>(k, st);
+}
+
+// layout DOCKAUV_LAYOUT_SPLIT: dynamics launch + radar launch per chunk of `chunk` envs, so that the hand-off of a
+// chunk (184 B per env) is still in L2 when the second launch reads it
+template <typename T, int VEH, int NU>
+static cudaError_t launch_step_split(const KParams<T> &k, int64_t chunk, cudaStream_t st) {
+    if (chunk <= 0) chunk = k.env_end - k.env_begin;
+    chunk = ((chunk + kWarpEnvs - 1) / kWarpEnvs) * kWarpEnvs;
+    for (int64_t b = k.env_begin; b < k.env_end; b += chunk) {
+        KParams<T> kc = k;
+        kc.env_begin = b;
+        kc.env_end = b + chunk < k.env_end ? b + chunk : k.env_end;
+        cudaError_t e = launch_step_warp_rpl<T, VEH, NU, 2, 1>(kc, st);
+        if (e != cudaSuccess) return e;
+        // the radar launch does not depend on the vehicle: one instantiation serves all of them
+        e = (k.n_rays <= 64) ? launch_step_warp_rpl<T, DOCKAUV_VEHICLE_BLUEROV2, 6, 2, 2>(kc, st)
+                             : launch_step_warp_rpl<T, DOCKAUV_VEHICLE_BLUEROV2, 6, 8, 2>(kc, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace dockauv

@@ -59,7 +59,7 @@ class BaseDocking3d:
     def __init__(self, env_config=BASE_CONFIG, num_envs=1, device="cuda:0", precision="f64", seed=0, env_id0=0,
                  layout="auto", n_spheres=0, n_synthetic_spheres=0, n_capsules=None, vehicle_xml=None,
                  control_mode="joystick", cur_mu=0.005, cur_sigma=0.0, force_current=False, auto_reset=True,
-                 debug_outputs=False):
+                 debug_outputs=False, split_chunk_envs=0):
         if self.scenario is None:
             raise TypeError("instantiate one of the scenario classes (SimpleDocking3d, ObstaclesDocking3d, ...)")
         self._lib = _capi.load()
@@ -77,7 +77,7 @@ class BaseDocking3d:
             env_config, self.scenario, precision=precision, seed=seed, env_id0=env_id0, layout=layout,
             n_capsules=n_capsules, n_spheres=n_spheres, n_synthetic_spheres=n_synthetic_spheres,
             vehicle_xml=vehicle_xml, control_mode=control_mode, cur_mu=cur_mu, cur_sigma=cur_sigma,
-            force_current=force_current)
+            force_current=force_current, split_chunk_envs=split_chunk_envs)
         self._meta = meta
         self.n_observations = meta["n_obs"]
         self.n_actions = meta["n_u"]

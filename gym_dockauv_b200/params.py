@@ -16,7 +16,7 @@ ABI_VERSION = 1
 MAX_U, MAX_CAPSULES, MAX_SPHERES, MAX_RAYS, N_REWARDS, N_STATS = 8, 8, 8, 256, 13, 16
 F64, F32 = 0, 1
 ACT_F64, ACT_F32 = 0, 1
-LAYOUTS = {"auto": 0, "thread_per_env": 1, "warp_rays": 2}
+LAYOUTS = {"auto": 0, "thread_per_env": 1, "warp_rays": 2, "split": 3}
 VEHICLE_IDS = {"BlueROV2": 0, "LAUV": 1}
 SCENARIO_IDS = {"SimpleDocking3d": 0, "SimpleCurrentDocking3d": 1, "CapsuleDocking3d": 2,
                 "CapsuleCurrentDocking3d": 3, "ObstaclesDocking3d": 4, "ObstaclesCurrentDocking3d": 5,
@@ -35,7 +35,7 @@ class DockauvParams(C.Structure):
         ("abi_version", _i), ("precision", _i), ("vehicle", _i), ("n_u", _i), ("scenario", _i),
         ("n_capsules", _i), ("n_spheres", _i), ("n_synthetic_spheres", _i), ("max_timesteps", _i),
         ("reward_set", _i), ("n_rays", _i), ("n_vert", _i), ("n_horiz", _i), ("block_reduce", _i),
-        ("action_factor_is_scalar", _i), ("layout", _i), ("force_current", _i),
+        ("action_factor_is_scalar", _i), ("layout", _i), ("force_current", _i), ("split_chunk_envs", _i),
         ("m", _d), ("r_G", _d * 3), ("I_b", _d * 9), ("MA_diag", _d * 6), ("M_inv", _d * 36),
         ("D_lin", _d * 10), ("D_quad", _d * 10), ("D_lift", _d * 10), ("G_WB", _d), ("G_r", _d * 3),
         ("B", _d * (6 * MAX_U)), ("lauv_B", _d * 4), ("u_lo", _d * MAX_U), ("u_hi", _d * MAX_U),
@@ -126,7 +126,7 @@ def radar_geometry(alpha, beta, ray_per_deg, max_dist=25, blocksize_reduce=2, fr
 
 def pack_params(env_config, scenario, precision="f64", seed=0, env_id0=0, layout="auto", n_capsules=None,
                 n_spheres=0, n_synthetic_spheres=0, vehicle_xml=None, control_mode="joystick", cur_mu=0.005,
-                cur_sigma=0.0, force_current=False):
+                cur_sigma=0.0, force_current=False, split_chunk_envs=0):
     """Returns (DockauvParams, meta) where meta carries host-side derived values (n_obs, u_bound, radar table)."""
     cfg = validate(env_config)
     vname = cfg["vehicle"]
@@ -148,6 +148,7 @@ def pack_params(env_config, scenario, precision="f64", seed=0, env_id0=0, layout
     P.reward_set = int(cfg["reward_set"])
     P.layout = LAYOUTS[layout]
     P.force_current = int(bool(force_current))
+    P.split_chunk_envs = int(split_chunk_envs)
     rb = rigid_body_matrices(v)
     P.m = v["m"]
     P.r_G[:] = rb["r_G"].tolist()

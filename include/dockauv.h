@@ -88,6 +88,7 @@ extern "C" {
 #define DOCKAUV_LAYOUT_AUTO 0
 #define DOCKAUV_LAYOUT_THREAD_PER_ENV 1   /* one thread does everything for one env */
 #define DOCKAUV_LAYOUT_WARP_RAYS 2        /* dynamics thread-per-env, radar one warp per env (lanes = rays) */
+#define DOCKAUV_LAYOUT_SPLIT 3            /* the same two phases as two launches per chunk, hand-off through L2 */
 
 /* indices into the stats vector (sums since the last clear; reduce over ranks with one all-reduce) */
 #define DOCKAUV_STAT_EPISODES 0
@@ -115,6 +116,7 @@ typedef struct DockauvParams {
     int32_t action_factor_is_scalar;   /* config "action_reward_factors" was a python scalar */
     int32_t layout;              /* DOCKAUV_LAYOUT_* */
     int32_t force_current;       /* evaluate the ocean current even if the scenario spawns none (injected currents) */
+    int32_t split_chunk_envs;    /* DOCKAUV_LAYOUT_SPLIT: envs per launch pair (0 = library default) */
     /* rigid body + hydrodynamics (statespace.py) */
     double m;
     double r_G[3];

@@ -39,7 +39,7 @@ def _env_for_case(g, layout, precision="f64", debug=True):
     return env
 
 
-@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays"])
+@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split"])
 @pytest.mark.parametrize("name", case_names())
 def test_cuda_matches_reference_trace(name, layout):
     import torch
@@ -130,7 +130,7 @@ def _oracle_rollout(config, scenario, n, steps, seed, n_synth, dtype, layout, pr
     return out
 
 
-@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays"])
+@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split"])
 def test_random_rollout_with_autoreset_vs_oracle(layout):
     """256 envs x 300 steps of the BASELINE C4 workload (64 rays, 5 capsules + 3 spheres), auto-reset on."""
     from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
