@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.environ.get("DOCKAUV_LIB_OUT") or os.path.join(LIB_DIR, "libdockauv_b200.so")   # override: tuning builds
-OBJ_DIR = os.path.join(LIB_DIR, "obj")
+OBJ_DIR = os.path.join(os.environ.get("TMPDIR", "/tmp"), "dockauv_b200_obj")   # objects never travel with the repo
 UNITS = ["dockauv_capi.cu", "dockauv_kernels_f64.cu", "dockauv_kernels_f32.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -451,16 +451,21 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
         done = step_finish<T>(p, i, cy, r_oa, my_col, bs);
     }
     __syncwarp();     // orders the pooled-cell stores of the other lanes before the row fix-up below
-    // ---- rows of envs whose episode ended: keep the last observation as terminal_observation, hand back the
-    //      all-zero reset observation (docking3d.py:269,322).  ~1 % of the envs per step.
-    if (done) {
-        float *row = p.obs + i * p.n_obs;
-        if (p.terminal_obs) {
-            float *trow = p.terminal_obs + i * p.n_obs;
-            for (int c = 0; c < p.n_obs; c++) trow[c] = row[c];
+    // ---- rows of envs whose episode ended (~1 % per step): keep the last observation as terminal_observation and
+    //      hand back the all-zero reset observation (docking3d.py:269,322); the warp moves each such row together
+    {
+        unsigned dm = __ballot_sync(0xffffffffu, done);
+        const int n_obs = p.n_obs;
+        while (dm) {
+            const int e = __ffs(dm) - 1;
+            dm &= dm - 1;
+            float *row = p.obs + (i0 + e_warp + e) * n_obs;
+            float *trow = p.terminal_obs ? p.terminal_obs + (i0 + e_warp + e) * n_obs : nullptr;
+            for (int c = lane; c < n_obs; c += 32) {
+                if (trow) trow[c] = row[c];
+                if (p.auto_reset) row[c] = 0.0f;
+            }
         }
-        if (p.auto_reset)
-            for (int c = 0; c < p.n_obs; c++) row[c] = 0.0f;
     }
     bs.flush(p.stats, warp == 0 ? n_here : 0);
 }
