@@ -101,6 +101,40 @@ __device__ __forceinline__ T ssa(T x) {
     return ssa_general<T>(x);
 }
 
+// sin / cos of (a + d) from (sin a, cos a) by angle addition.  The Runge-Kutta stage angles and the post-step
+// attitude are small shifts of the pre-step attitude (d = h * sum(a_ij k_j), |d| ~ h |Theta_dot|), so for
+// |d| <= 0.5 sin d and cos d - 1 are short Taylor polynomials (truncation < 5e-17 relative) instead of a library
+// sincos (~150 instructions with its range reduction); larger shifts and NaN / inf take the library call.
+// The result differs from sincos(a + d) by ~1 ulp, three orders of magnitude inside the 1e-9 budget.
+template <typename T>
+__device__ __forceinline__ void sincos_shift(T s0, T c0, T d, T *s, T *c) {
+    T sd, cm1;
+    if (Mth<T>::abs_(d) <= T(0.5)) {
+        const T d2 = d * d;
+        T ps = T(1.0 / 6227020800.0);
+        ps = ps * d2 + T(-1.0 / 39916800.0);
+        ps = ps * d2 + T(1.0 / 362880.0);
+        ps = ps * d2 + T(-1.0 / 5040.0);
+        ps = ps * d2 + T(1.0 / 120.0);
+        ps = ps * d2 + T(-1.0 / 6.0);
+        sd = (d * d2) * ps + d;
+        T pc = T(-1.0 / 87178291200.0);
+        pc = pc * d2 + T(1.0 / 479001600.0);
+        pc = pc * d2 + T(-1.0 / 3628800.0);
+        pc = pc * d2 + T(1.0 / 40320.0);
+        pc = pc * d2 + T(-1.0 / 720.0);
+        pc = pc * d2 + T(1.0 / 24.0);
+        pc = pc * d2 + T(-0.5);
+        cm1 = d2 * pc;
+    } else {
+        T cd;
+        Mth<T>::sincos_(d, &sd, &cd);
+        cm1 = cd - T(1);
+    }
+    *s = s0 + (s0 * cm1 + c0 * sd);
+    *c = c0 + (c0 * cm1 - s0 * sd);
+}
+
 // cold-path logarithm (epsilon guards that practically never trigger): out of line to keep the hot code small
 template <typename T>
 static __device__ __noinline__ T log_cold(T x) {
@@ -248,13 +282,12 @@ __device__ __forceinline__ void rzyx(T sphi, T cphi, T sth, T cth, T spsi, T cps
 }
 
 // One evaluation of the reduced right-hand side (auvsim.py:110-160) at y = (Theta, nu_r).
+//   tr = sin/cos of (phi, theta, psi) at y: {sphi, cphi, sth, cth, spsi, cpsi} (psi only read if WPOS)
 //   k[0:3] = T(phi, theta) nu2 (geomutils.py:72-75), k[3:9] = nu_dot;  if WPOS, pacc += wpos * R(Theta) (nu1 + nu_c).
 template <typename T, int VEH, bool WPOS>
-__device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T tau[6], const T nu_c[3], T wpos,
-                                     T pacc[3], T k[9]) {
-    T sphi, cphi, sth, cth;
-    Mth<T>::sincos_(y[0], &sphi, &cphi);
-    Mth<T>::sincos_(y[1], &sth, &cth);
+__device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T tr[6], const T tau[6], const T nu_c[3],
+                                     T wpos, T pacc[3], T k[9]) {
+    const T sphi = tr[0], cphi = tr[1], sth = tr[2], cth = tr[3];
     const T *nu = y + 3;
     T inv_cth = T(1) / cth;
     T tth = sth * inv_cth;
@@ -263,9 +296,8 @@ __device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T 
     k[1] = cphi * nu[4] - sphi * nu[5];
     k[2] = qs * inv_cth;
     if (WPOS) {
-        T spsi, cpsi, R[9];
-        Mth<T>::sincos_(y[2], &spsi, &cpsi);
-        rzyx(sphi, cphi, sth, cth, spsi, cpsi, R);
+        T R[9];
+        rzyx(sphi, cphi, sth, cth, tr[4], tr[5], R);
         T v[3] = {nu[0] + nu_c[0], nu[1] + nu_c[1], nu[2] + nu_c[2]};
 #pragma unroll
         for (int i = 0; i < 3; i++) pacc[i] += wpos * (R[3 * i] * v[0] + R[3 * i + 1] * v[1] + R[3 * i + 2] * v[2]);
@@ -273,42 +305,73 @@ __device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T 
     nu_dot<T, VEH>(p, nu, tau, sphi, cphi, sth, cth, k + 3);
 }
 
+// sin/cos of the stage attitude Theta0 + d from the pre-step values tr0 (psi skipped when the stage has no position weight)
+template <typename T, bool WPSI>
+__device__ __forceinline__ void stage_trig(const T tr0[6], const T d[3], T tr[6]) {
+    sincos_shift<T>(tr0[0], tr0[1], d[0], &tr[0], &tr[1]);
+    sincos_shift<T>(tr0[2], tr0[3], d[1], &tr[2], &tr[3]);
+    if (WPSI) sincos_shift<T>(tr0[4], tr0[5], d[2], &tr[4], &tr[5]);
+}
+
 // utils/odesolver45.py:18-26 on the reduced state; the 4th-order result is written back to pos / y.
+//   tr0: sin/cos of the pre-step attitude y[0:3]; tr1 (out): sin/cos of the post-step attitude (before ssa, which
+//   does not change them).
 template <typename T, int VEH>
-__device__ __forceinline__ void rkf45_step(const KParams<T> &p, T pos[3], T y[9], const T tau[6], const T nu_c[3]) {
+__device__ __forceinline__ void rkf45_step(const KParams<T> &p, T pos[3], T y[9], const T tr0[6], const T tau[6],
+                                           const T nu_c[3], T tr1[6]) {
     const T h = p.h;
-    T k1[9], k2[9], k3[9], k4[9], k5[9], yt[9];
+    T k1[9], k2[9], k3[9], k4[9], k5[9], yt[9], dy[9], tr[6];
     T pacc[3] = {T(0), T(0), T(0)};
-    rhs9<T, VEH, true>(p, y, tau, nu_c, h * T(25.0 / 216.0), pacc, k1);
+    rhs9<T, VEH, true>(p, y, tr0, tau, nu_c, h * T(25.0 / 216.0), pacc, k1);
     {
         const T a = h * T(0.25);
 #pragma unroll
-        for (int i = 0; i < 9; i++) yt[i] = y[i] + a * k1[i];
+        for (int i = 0; i < 9; i++) {
+            dy[i] = a * k1[i];
+            yt[i] = y[i] + dy[i];
+        }
     }
-    rhs9<T, VEH, false>(p, yt, tau, nu_c, T(0), pacc, k2);   // b2 = 0: no position contribution
+    stage_trig<T, false>(tr0, dy, tr);
+    rhs9<T, VEH, false>(p, yt, tr, tau, nu_c, T(0), pacc, k2);   // b2 = 0: no position contribution
     {
         const T a = h * T(3.0 / 32.0), b = h * T(9.0 / 32.0);
 #pragma unroll
-        for (int i = 0; i < 9; i++) yt[i] = y[i] + a * k1[i] + b * k2[i];
+        for (int i = 0; i < 9; i++) {
+            dy[i] = a * k1[i] + b * k2[i];
+            yt[i] = y[i] + dy[i];
+        }
     }
-    rhs9<T, VEH, true>(p, yt, tau, nu_c, h * T(1408.0 / 2565.0), pacc, k3);
+    stage_trig<T, true>(tr0, dy, tr);
+    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(1408.0 / 2565.0), pacc, k3);
     {
         const T a = h * T(1932.0 / 2197.0), b = h * T(-7200.0 / 2197.0), c = h * T(7296.0 / 2197.0);
 #pragma unroll
-        for (int i = 0; i < 9; i++) yt[i] = y[i] + a * k1[i] + b * k2[i] + c * k3[i];
+        for (int i = 0; i < 9; i++) {
+            dy[i] = a * k1[i] + b * k2[i] + c * k3[i];
+            yt[i] = y[i] + dy[i];
+        }
     }
-    rhs9<T, VEH, true>(p, yt, tau, nu_c, h * T(2197.0 / 4104.0), pacc, k4);
+    stage_trig<T, true>(tr0, dy, tr);
+    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(2197.0 / 4104.0), pacc, k4);
     {
         const T a = h * T(439.0 / 216.0), b = h * T(-8.0), c = h * T(3680.0 / 513.0), d = h * T(-845.0 / 4104.0);
 #pragma unroll
-        for (int i = 0; i < 9; i++) yt[i] = y[i] + a * k1[i] + b * k2[i] + c * k3[i] + d * k4[i];
+        for (int i = 0; i < 9; i++) {
+            dy[i] = a * k1[i] + b * k2[i] + c * k3[i] + d * k4[i];
+            yt[i] = y[i] + dy[i];
+        }
     }
-    rhs9<T, VEH, true>(p, yt, tau, nu_c, h * T(-1.0 / 5.0), pacc, k5);
+    stage_trig<T, true>(tr0, dy, tr);
+    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(-1.0 / 5.0), pacc, k5);
     {
         const T a = h * T(25.0 / 216.0), c = h * T(1408.0 / 2565.0), d = h * T(2197.0 / 4104.0), e = h * T(-1.0 / 5.0);
 #pragma unroll
-        for (int i = 0; i < 9; i++) y[i] = y[i] + (a * k1[i] + c * k3[i] + d * k4[i] + e * k5[i]);
+        for (int i = 0; i < 9; i++) {
+            dy[i] = a * k1[i] + c * k3[i] + d * k4[i] + e * k5[i];
+            y[i] = y[i] + dy[i];
+        }
     }
+    stage_trig<T, true>(tr0, dy, tr1);
 #pragma unroll
     for (int i = 0; i < 3; i++) pos[i] += pacc[i];
 }

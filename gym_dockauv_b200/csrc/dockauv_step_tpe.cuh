@@ -27,6 +27,12 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     cy.ep_return = p.ep_return[i];
 
     // ---- ocean current: Current.sim (current.py:78-96) then nu_c from the PRE-step attitude (docking3d.py:348-349)
+    // sin/cos of the pre-step attitude: the only library sincos calls of the step (every later attitude is a small
+    // shift of this one, sincos_shift); shared by the current rotation and the first Runge-Kutta stage
+    T tr0[6];
+    Mth<T>::sincos_(y[0], &tr0[0], &tr0[1]);
+    Mth<T>::sincos_(y[1], &tr0[2], &tr0[3]);
+    Mth<T>::sincos_(y[2], &tr0[4], &tr0[5]);
     T nu_c[3] = {T(0), T(0), T(0)};
     if (p.has_current) {
         T Vc = p.current[i];
@@ -47,11 +53,8 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
         Mth<T>::sincos_(alpha, &sa, &ca);
         Mth<T>::sincos_(beta, &sb, &cb);
         T vn[3] = {Vc * ca * cb, Vc * sb, Vc * sa * cb};                 // current.py:71-73
-        T s0, c0, s1, c1, s2, c2, R[9];
-        Mth<T>::sincos_(y[0], &s0, &c0);
-        Mth<T>::sincos_(y[1], &s1, &c1);
-        Mth<T>::sincos_(y[2], &s2, &c2);
-        rzyx(s0, c0, s1, c1, s2, c2, R);
+        T R[9];
+        rzyx(tr0[0], tr0[1], tr0[2], tr0[3], tr0[4], tr0[5], R);
 #pragma unroll
         for (int c = 0; c < 3; c++) nu_c[c] = R[c] * vn[0] + R[3 + c] * vn[1] + R[6 + c] * vn[2];   // R^T v
     }
@@ -75,7 +78,8 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     }
 
     // ---- integrate (auvsim.py:89-108)
-    rkf45_step<T, VEH>(p, pos, y, tau, nu_c);
+    T tr1[6];
+    rkf45_step<T, VEH>(p, pos, y, tr0, tau, nu_c, tr1);
 #pragma unroll
     for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
 #pragma unroll
@@ -84,10 +88,7 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     for (int c = 0; c < 9; c++) p.state[(int64_t)(3 + c) * N + i] = y[c];
 
     // ---- post-step quantities: Theta_dot (auvsim.py:108, only euler_dot is consumed) and Rzyx for the radar
-    T sphi, cphi, sth, cth, spsi, cpsi;
-    Mth<T>::sincos_(y[0], &sphi, &cphi);
-    Mth<T>::sincos_(y[1], &sth, &cth);
-    Mth<T>::sincos_(y[2], &spsi, &cpsi);
+    const T sphi = tr1[0], cphi = tr1[1], sth = tr1[2], cth = tr1[3], spsi = tr1[4], cpsi = tr1[5];
     T ed[3];
     {
         const T *nu = y + 3;
