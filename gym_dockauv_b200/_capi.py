@@ -3,7 +3,8 @@ or was built against another ABI this module raises, and so does every env const
 import ctypes as C
 import os
 
-from .params import ABI_VERSION, DockauvBuffers, DockauvDebugOut, DockauvParams, DockauvStepOut
+from .params import (ABI_VERSION, DockauvBuffers, DockauvDebugOut, DockauvParams, DockauvRolloutOut,
+                     DockauvStepOut)
 
 LIB_PATH = os.environ.get("DOCKAUV_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
                                                         "libdockauv_b200.so")   # DOCKAUV_LIB: tuning builds only
@@ -22,6 +23,8 @@ SYMBOLS = {
     "dockauv_reset": (_i, [_vp, _vp, _vp]),
     "dockauv_step": (_i, [_vp, _vp, _i, _vp, C.POINTER(DockauvStepOut), C.POINTER(DockauvDebugOut), _i, _vp]),
     "dockauv_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(DockauvStepOut)]),
+    "dockauv_rollout": (_i, [_vp, _vp, _i, _i, C.POINTER(DockauvRolloutOut), _i, _i, _vp]),
+    "dockauv_gae": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i64, C.c_float, C.c_float, _vp, _vp, _vp]),
     "dockauv_stats_ptr": (_i, [_vp, C.POINTER(_vp)]),
     "dockauv_get_stats": (_i, [_vp, C.POINTER(C.c_double), _vp]),
     "dockauv_clear_stats": (_i, [_vp, _vp]),

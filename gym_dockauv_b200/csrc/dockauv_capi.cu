@@ -71,6 +71,15 @@ struct DockauvHandle {
     float *st_obs = nullptr;
     void *st_reward = nullptr;
     uint8_t *st_done = nullptr, *st_cond = nullptr;
+    // rollout graph cache: one captured launch sequence, re-captured when the key changes
+    cudaGraphExec_t rg_exec = nullptr;
+    int64_t rg_launches = 0;       // kernel nodes in the captured sequence
+    struct RolloutKey {
+        const void *actions = nullptr;
+        DockauvRolloutOut out = {};
+        int n_steps = 0, action_dtype = 0, auto_reset = 0;
+        uint64_t seed = 0;
+    } rg_key;
 };
 
 static int pooled_dim(int n, int b) { return (n + b - 1) / b; }
@@ -279,6 +288,7 @@ extern "C" int dockauv_destroy(DockauvHandle *h) {
     if (h->st_reward) cudaFree(h->st_reward);
     if (h->st_done) cudaFree(h->st_done);
     if (h->st_cond) cudaFree(h->st_cond);
+    if (h->rg_exec) cudaGraphExecDestroy(h->rg_exec);
     delete h;
     return DOCKAUV_OK;
 }
@@ -307,6 +317,10 @@ extern "C" int dockauv_bind(DockauvHandle *h, const DockauvBuffers *b) {
     bind_k<double>(h->kd, *b);
     bind_k<float>(h->kf, *b);
     h->bound = true;
+    if (h->rg_exec) {   // a captured rollout holds the old pointers
+        cudaGraphExecDestroy(h->rg_exec);
+        h->rg_exec = nullptr;
+    }
     return DOCKAUV_OK;
 }
 
@@ -345,6 +359,7 @@ static void set_io(KParams<T> &k, const void *actions, bool act_f32, const void 
     k.dbg_nu_c = d ? (T *)d->nu_c : nullptr;
     k.dbg_nav = d ? (T *)d->nav : nullptr;
     k.dbg_obs = d ? (T *)d->obs_f64 : nullptr;
+    k.dbg_state_dot = d ? (T *)d->state_dot : nullptr;
 }
 
 static int step_range(DockauvHandle *h, const void *actions, int action_dtype, const void *noise,
@@ -488,6 +503,124 @@ extern "C" int dockauv_step_host(DockauvHandle *h, const void *actions_host, int
             CUDA_TRY(cudaMemcpyAsync(cond_bits_host + b, h->st_cond + b, (size_t)(e - b), cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < kHostStreams; s++) CUDA_TRY(cudaStreamSynchronize(h->hs[s]));
+    return DOCKAUV_OK;
+}
+
+// ------------------------------------------------------------------------------------------- stacked rollout
+static int rollout_issue(DockauvHandle *h, const void *actions, int action_dtype, int n_steps,
+                         const DockauvRolloutOut &o, int auto_reset, cudaStream_t st) {
+    const int64_t N = h->n_envs;
+    const size_t esz = h->params.precision == DOCKAUV_F64 ? 8 : 4;
+    const size_t arow = (action_dtype == DOCKAUV_ACT_F32 ? 4 : 8) * (size_t)h->params.n_u * (size_t)N;
+    const size_t orow = (size_t)h->n_obs * (size_t)N;
+    for (int t = 0; t < n_steps; t++) {
+        DockauvStepOut so;
+        so.obs = o.obs + orow * t;
+        so.reward = (char *)o.reward + esz * (size_t)N * t;
+        so.done = o.done + (size_t)N * t;
+        so.cond_bits = o.cond_bits ? o.cond_bits + (size_t)N * t : nullptr;
+        so.terminal_obs = o.terminal_obs ? o.terminal_obs + orow * t : nullptr;
+        so.ep_return_out = o.ep_return_out ? (char *)o.ep_return_out + esz * (size_t)N * t : nullptr;
+        so.ep_len_out = o.ep_len_out ? o.ep_len_out + (size_t)N * t : nullptr;
+        int rc = step_range(h, (const char *)actions + arow * t, action_dtype, nullptr, &so, nullptr, auto_reset, 0, N, st);
+        if (rc != DOCKAUV_OK) return rc;
+    }
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_rollout(DockauvHandle *h, const void *actions_dev, int action_dtype, int n_steps,
+                               const DockauvRolloutOut *out, int auto_reset, int use_graph, void *stream) {
+    if (!h || !actions_dev || !out) return fail(DOCKAUV_EINVAL, "null argument");
+    if (!h->bound) return fail(DOCKAUV_ESTATE, "dockauv_bind must be called before dockauv_rollout");
+    if (!out->obs || !out->reward || !out->done) return fail(DOCKAUV_EINVAL, "obs, reward and done outputs are required");
+    if (action_dtype != DOCKAUV_ACT_F32 && action_dtype != DOCKAUV_ACT_F64) return fail(DOCKAUV_EINVAL, "bad action dtype");
+    if (n_steps <= 0) return fail(DOCKAUV_EINVAL, "n_steps must be positive");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out->ep_len_out)
+        CUDA_TRY(cudaMemsetAsync(out->ep_len_out, 0, sizeof(int32_t) * (size_t)h->n_envs * (size_t)n_steps, st));
+    if (!use_graph) return rollout_issue(h, actions_dev, action_dtype, n_steps, *out, auto_reset, st);
+    DockauvHandle::RolloutKey key;
+    key.actions = actions_dev;
+    key.out = *out;
+    key.n_steps = n_steps;
+    key.action_dtype = action_dtype;
+    key.auto_reset = auto_reset;
+    key.seed = h->params.seed;
+    if (!h->rg_exec || memcmp(&key, &h->rg_key, sizeof(key)) != 0) {
+        if (h->rg_exec) {
+            cudaGraphExecDestroy(h->rg_exec);
+            h->rg_exec = nullptr;
+        }
+        // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+        cudaStream_t cs = nullptr;
+        CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        int rc = DOCKAUV_OK;
+        const int64_t launches_before = h->launches;
+        if (e == cudaSuccess) {
+            rc = rollout_issue(h, actions_dev, action_dtype, n_steps, *out, auto_reset, cs);
+            e = cudaStreamEndCapture(cs, &g);
+        }
+        h->rg_launches = h->launches - launches_before;
+        h->launches = launches_before;      // captured, not launched; every replay below counts them
+        if (e == cudaSuccess && rc == DOCKAUV_OK) e = cudaGraphInstantiate(&h->rg_exec, g, 0);
+        if (g) cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+        if (rc != DOCKAUV_OK) return rc;
+        if (e != cudaSuccess) {
+            h->rg_exec = nullptr;
+            return fail(DOCKAUV_ECUDA, "rollout graph capture failed: %s", cudaGetErrorString(e));
+        }
+        memset(&h->rg_key, 0, sizeof(h->rg_key));
+        h->rg_key = key;
+    }
+    CUDA_TRY(cudaGraphLaunch(h->rg_exec, st));
+    h->launches += h->rg_launches;
+    return DOCKAUV_OK;
+}
+
+// ------------------------------------------------------------------------------------------- GAE
+template <typename R>
+__global__ void gae_kernel(const R *__restrict__ rewards, const float *__restrict__ values,
+                           const float *__restrict__ last_values, const uint8_t *__restrict__ dones, int T, int64_t N,
+                           float gamma, float lam, float *__restrict__ adv, float *__restrict__ ret) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float next_v = last_values[i], a = 0.0f;
+    // rows are env-fastest, so each step is one coalesced request per warp; the next rows are in flight while the
+    // recurrence of the current one (3 dependent FMAs) resolves
+#pragma unroll 4
+    for (int t = T - 1; t >= 0; t--) {
+        const int64_t k = (int64_t)t * N + i;
+        const float nt = dones[k] ? 0.0f : 1.0f;
+        const float v = values[k];
+        const float delta = (float)rewards[k] + gamma * next_v * nt - v;
+        a = delta + gamma * lam * nt * a;
+        adv[k] = a;
+        ret[k] = a + v;
+        next_v = v;
+    }
+}
+
+extern "C" int dockauv_gae(const void *rewards_dev, int reward_precision, const float *values_dev,
+                           const float *last_values_dev, const uint8_t *dones_dev, int n_steps, int64_t n_envs,
+                           float gamma, float gae_lambda, float *advantages_dev, float *returns_dev, void *stream) {
+    if (!rewards_dev || !values_dev || !last_values_dev || !dones_dev || !advantages_dev || !returns_dev)
+        return fail(DOCKAUV_EINVAL, "null argument");
+    if (n_steps <= 0 || n_envs <= 0) return fail(DOCKAUV_EINVAL, "n_steps and n_envs must be positive");
+    if (reward_precision != DOCKAUV_F64 && reward_precision != DOCKAUV_F32) return fail(DOCKAUV_EINVAL, "bad reward precision");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n_envs + threads - 1) / threads);
+    if (reward_precision == DOCKAUV_F64)
+        gae_kernel<double><<<blocks, threads, 0, st>>>((const double *)rewards_dev, values_dev, last_values_dev, dones_dev,
+                                                       n_steps, n_envs, gamma, gae_lambda, advantages_dev, returns_dev);
+    else
+        gae_kernel<float><<<blocks, threads, 0, st>>>((const float *)rewards_dev, values_dev, last_values_dev, dones_dev,
+                                                      n_steps, n_envs, gamma, gae_lambda, advantages_dev, returns_dev);
+    CUDA_TRY(cudaGetLastError());
     return DOCKAUV_OK;
 }
 

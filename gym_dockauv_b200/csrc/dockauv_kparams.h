@@ -54,7 +54,7 @@ struct KParams {
     uint8_t *done, *cond_bits;
     int32_t *ep_len_out;
     // debug outputs
-    T *dbg_ray_dist, *dbg_reward_arr, *dbg_euler_dot, *dbg_nu_c, *dbg_nav, *dbg_obs;
+    T *dbg_ray_dist, *dbg_reward_arr, *dbg_euler_dot, *dbg_nu_c, *dbg_nav, *dbg_obs, *dbg_state_dot;
     // hand-off between the two launches of the split layout (library-owned): T[22][n_envs] + u32[n_envs]
     T *handoff;
     uint32_t *handoff_cond;

@@ -186,6 +186,13 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
         }
         if (p.dbg_obs)
             for (int c = 0; c < 16; c++) p.dbg_obs[(int64_t)c * N + i] = o[c];
+        if (p.dbg_state_dot) {
+            // the full auv._state_dot (auvsim.py:108): right-hand side at the post-step state with the pre-step nu_c
+            T sd_pos[3] = {T(0), T(0), T(0)}, sd[9];
+            rhs9<T, VEH, true>(p, y, tr1, tau, nu_c, T(1), sd_pos, sd);
+            for (int c = 0; c < 3; c++) p.dbg_state_dot[(int64_t)c * N + i] = sd_pos[c];
+            for (int c = 0; c < 9; c++) p.dbg_state_dot[(int64_t)(3 + c) * N + i] = sd[c];
+        }
     }
 }
 

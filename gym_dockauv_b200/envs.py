@@ -21,8 +21,8 @@ import torch
 
 from . import _capi
 from .config import BASE_CONFIG, REGISTRATION_DICT
-from .params import (ACT_F32, ACT_F64, N_STATS, SCENARIO_IDS, STAT_NAMES, DockauvBuffers, DockauvDebugOut,
-                     DockauvStepOut, pack_params)
+from .params import (ACT_F32, ACT_F64, F32, F64, N_STATS, SCENARIO_IDS, STAT_NAMES, DockauvBuffers, DockauvDebugOut,
+                     DockauvRolloutOut, DockauvStepOut, pack_params)
 
 DONE_NAMES = ("Done-Goal_reached", "Done-out_pos", "Done-out_att", "Done-max_t", "Done-collision")
 
@@ -119,7 +119,7 @@ class BaseDocking3d:
         self.debug = None
         if debug_outputs:
             self.debug = dict(ray_dist=z(self.n_rays, N), reward_arr=z(13, N), euler_dot=z(3, N), nu_c=z(3, N),
-                              nav=z(3, N), obs_f64=z(self.n_observations, N))
+                              nav=z(3, N), obs_f64=z(self.n_observations, N), state_dot=z(12, N))
 
         self._handle = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -134,7 +134,7 @@ class BaseDocking3d:
         self._dbg = None
         if self.debug is not None:
             self._dbg = DockauvDebugOut(*[_ptr(self.debug[k]) for k in ("ray_dist", "reward_arr", "euler_dot", "nu_c",
-                                                                       "nav", "obs_f64")])
+                                                                       "nav", "obs_f64", "state_dot")])
         self._host = None
         self.t_total_steps = 0
 
@@ -198,6 +198,74 @@ class BaseDocking3d:
         info = {"cond_bits": self.cond_bits, "terminal_observation": self.terminal_obs,
                 "episode_return": self.ep_return_out, "episode_length": self.ep_len_out}
         return self.obs, self.reward, self.done, info
+
+    def _action_dtype(self, actions, shape):
+        if actions.device != self.device:
+            raise ValueError(f"actions live on {actions.device}, env on {self.device}; use step_host for host arrays")
+        if tuple(actions.shape) != shape:
+            raise ValueError(f"actions must have shape {shape}, got {tuple(actions.shape)}")
+        if actions.dtype == torch.float32:
+            return ACT_F32
+        if actions.dtype == torch.float64:
+            return ACT_F64
+        raise TypeError("actions must be float32 or float64")
+
+    def step_into(self, actions, obs, reward, done, cond_bits=None, terminal_obs=None, ep_return_out=None,
+                  ep_len_out=None):
+        """``step`` with caller-chosen output tensors (e.g. row t of a device-resident rollout buffer): the kernel
+        writes the observation / reward / done of this step straight into them, nothing is copied afterwards.
+        ``obs`` f32 [N, n_obs], ``reward`` env dtype [N], ``done`` uint8 [N]; all contiguous, on the env's device."""
+        adt = self._action_dtype(actions, (self.num_envs, self.n_actions))
+        for t, shape, dt in ((obs, (self.num_envs, self.n_observations), torch.float32),
+                             (reward, (self.num_envs,), self.dtype), (done, (self.num_envs,), torch.uint8)):
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"output tensor must be contiguous {dt} {shape} on {self.device}")
+        out = DockauvStepOut(*[_ptr(t) for t in (obs, reward, done, cond_bits, terminal_obs, ep_return_out,
+                                                 ep_len_out)])
+        actions = actions.contiguous()
+        _capi.check(self._lib.dockauv_step(self._handle, _ptr(actions), adt, None, C.byref(out), None,
+                                           int(self.auto_reset), self._stream()))
+        self.t_total_steps += 1
+
+    def rollout(self, actions, obs, reward, done, cond_bits=None, terminal_obs=None, ep_return_out=None,
+                ep_len_out=None, use_graph=True):
+        """T steps with actions known up front (``actions`` [T, N, n_u] on the device; random-action rollouts,
+        replayed logs) in ONE library call: row t of ``obs`` [T, N, n_obs] / ``reward`` [T, N] / ``done`` [T, N]
+        receives the outputs of step t.  With ``use_graph`` the launch sequence is captured into a CUDA graph the
+        first time and replayed afterwards (same tensors -> same graph)."""
+        T = int(actions.shape[0])
+        adt = self._action_dtype(actions, (T, self.num_envs, self.n_actions))
+        for t, shape, dt in ((obs, (T, self.num_envs, self.n_observations), torch.float32),
+                             (reward, (T, self.num_envs), self.dtype), (done, (T, self.num_envs), torch.uint8)):
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"output tensor must be contiguous {dt} {shape} on {self.device}")
+        if not actions.is_contiguous():
+            raise ValueError("actions must be contiguous")
+        out = DockauvRolloutOut(*[_ptr(t) for t in (obs, reward, done, cond_bits, terminal_obs, ep_return_out,
+                                                    ep_len_out)])
+        _capi.check(self._lib.dockauv_rollout(self._handle, _ptr(actions), adt, T, C.byref(out), int(self.auto_reset),
+                                              int(bool(use_graph)), self._stream()))
+        self.t_total_steps += T
+
+    def gae(self, rewards, values, last_values, dones, gamma, gae_lambda, advantages, returns):
+        """Generalised advantage estimation over a stacked rollout on the device (dockauv_gae): ``rewards`` [T, N]
+        in the env dtype or float32, ``values`` f32 [T, N], ``last_values`` f32 [N], ``dones`` uint8 [T, N];
+        writes ``advantages`` and ``returns`` (f32 [T, N])."""
+        T, N = rewards.shape
+        prec = F64 if rewards.dtype == torch.float64 else F32
+        if rewards.dtype not in (torch.float64, torch.float32):
+            raise TypeError("rewards must be float64 or float32")
+        for t, shape, dt in ((values, (T, N), torch.float32), (last_values, (N,), torch.float32),
+                             (dones, (T, N), torch.uint8), (advantages, (T, N), torch.float32),
+                             (returns, (T, N), torch.float32)):
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"tensor must be contiguous {dt} {shape} on {self.device}")
+        if not rewards.is_contiguous():
+            raise ValueError("rewards must be contiguous")
+        with torch.cuda.device(self.device):
+            _capi.check(self._lib.dockauv_gae(_ptr(rewards), prec, _ptr(values), _ptr(last_values), _ptr(dones), T, N,
+                                              float(gamma), float(gae_lambda), _ptr(advantages), _ptr(returns),
+                                              self._stream()))
 
     def step_host(self, actions):
         """The same step for HOST actions (numpy [N, n_u], float32 / float64): actions are copied to the GPU,

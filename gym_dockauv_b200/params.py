@@ -12,7 +12,7 @@ import numpy as np
 from . import vehicles as _veh
 from .config import validate
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_U, MAX_CAPSULES, MAX_SPHERES, MAX_RAYS, N_REWARDS, N_STATS = 8, 8, 8, 256, 13, 16
 F64, F32 = 0, 1
 ACT_F64, ACT_F32 = 0, 1
@@ -61,7 +61,12 @@ class DockauvStepOut(C.Structure):
 
 
 class DockauvDebugOut(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("ray_dist", "reward_arr", "euler_dot", "nu_c", "nav", "obs_f64")]
+    _fields_ = [(k, C.c_void_p) for k in ("ray_dist", "reward_arr", "euler_dot", "nu_c", "nav", "obs_f64", "state_dot")]
+
+
+class DockauvRolloutOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("obs", "reward", "done", "cond_bits", "terminal_obs", "ep_return_out",
+                                          "ep_len_out")]
 
 
 def skew(a):

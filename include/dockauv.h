@@ -17,6 +17,12 @@
  *   dockauv_step_host                  the same call with HOST buffers (what SB3's DummyVecEnv.step_wait
  *                                      hands over, train.py:64-71): H2D, kernel(s), D2H inside the call
  *   dockauv_get_stats / _clear_stats   FullDataStorage.update bookkeeping  utils/datastorage.py:65-74
+ *   dockauv_rollout                    the step loop of the caller: model.learn() -> collect_rollouts of SB3's
+ *                                      on-policy algorithms (train.py:64-71) and predict()'s while-loop
+ *                                      (train.py:107-118), for action sequences that are known up front
+ *   dockauv_gae                        RolloutBuffer.compute_returns_and_advantage of the PPO caller
+ *                                      (stable-baselines3 1.5.0, requirements.txt; selected at train.py:64)
+ *   DockauvDebugOut (state_dot, ...)   EpisodeDataStorage.update          utils/datastorage.py:268-288
  *
  * Conventions
  *   - plain C types only; no torch / C++ types cross this boundary.
@@ -41,7 +47,7 @@
 extern "C" {
 #endif
 
-#define DOCKAUV_ABI_VERSION 1
+#define DOCKAUV_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DOCKAUV_API __attribute__((visibility("default")))
@@ -185,7 +191,21 @@ typedef struct DockauvDebugOut {
     void *nu_c;            /* real[3][N], pre-step body-frame current (docking3d.py:349) */
     void *nav;             /* real[3][N]: delta_d, delta_theta, delta_psi */
     void *obs_f64;         /* real[n_obs][N]: observation before the float32 cast */
+    void *state_dot;       /* real[12][N]: auv._state_dot = state_dot(post-step state, pre-step nu_c), auvsim.py:108
+                              (the step itself only needs its Theta_dot part; the full vector is what
+                              EpisodeDataStorage logs, datastorage.py:277) */
 } DockauvDebugOut;
+
+/* Outputs of dockauv_rollout: the per-step outputs stacked over T steps (device pointers). */
+typedef struct DockauvRolloutOut {
+    float *obs;            /* f32[T][N][n_obs]: row t = observation returned by step t */
+    void *reward;          /* real[T][N] */
+    uint8_t *done;         /* u8[T][N] */
+    uint8_t *cond_bits;    /* u8[T][N], nullable */
+    float *terminal_obs;   /* f32[T][N][n_obs], nullable: rows of episodes that ended at step t (others untouched) */
+    void *ep_return_out;   /* real[T][N], nullable: only entries of episodes that ended at step t are written */
+    int32_t *ep_len_out;   /* int32[T][N], nullable: same; the call zero-fills it first, so length > 0 marks an end */
+} DockauvRolloutOut;
 
 typedef struct DockauvHandle DockauvHandle;
 
@@ -220,6 +240,24 @@ DOCKAUV_API int dockauv_step(DockauvHandle *h, const void *actions_dev, int acti
 DOCKAUV_API int dockauv_step_host(DockauvHandle *h, const void *actions_host, int action_dtype, float *obs_host,
                       void *reward_host, uint8_t *done_host, uint8_t *cond_bits_host, int auto_reset,
                       const DockauvStepOut *aux_dev_or_null);
+
+/* T consecutive batched steps with actions known up front (random-action rollouts, replayed action logs):
+ * actions_dev is [T][N][n_u] row-major.  Equivalent to T dockauv_step calls writing into row t of `out`, but
+ * issued from C (no per-step host round trip); with use_graph != 0 the launch sequence is captured once into a
+ * CUDA graph per (pointers, T) and replayed, which is what makes small batches launch-bound no longer.
+ * Stochastic-current handles draw their noise from the handle's Philox stream. */
+DOCKAUV_API int dockauv_rollout(DockauvHandle *h, const void *actions_dev, int action_dtype, int n_steps,
+                    const DockauvRolloutOut *out, int auto_reset, int use_graph, void *stream);
+
+/* Generalised advantage estimation over a stacked rollout, one thread per env walking t = T-1 .. 0
+ * (float32 like the caller's RolloutBuffer):
+ *   delta_t = r_t + gamma * V_{t+1} * (1 - done_t) - V_t ;  A_t = delta_t + gamma * lambda * (1 - done_t) * A_{t+1}
+ * with V_T = last_values, returns = A + V.  rewards_dev is real[T][N] in the precision given by reward_precision
+ * (DOCKAUV_F64 / DOCKAUV_F32), i.e. the `reward` rows dockauv_rollout / dockauv_step wrote; done_t is the done flag
+ * returned by step t (the next observation starts a new episode).  Needs no handle. */
+DOCKAUV_API int dockauv_gae(const void *rewards_dev, int reward_precision, const float *values_dev,
+                const float *last_values_dev, const uint8_t *dones_dev, int n_steps, int64_t n_envs, float gamma,
+                float gae_lambda, float *advantages_dev, float *returns_dev, void *stream);
 
 /* Episode statistics accumulated on the device since the last clear (DOCKAUV_STAT_*).  stats_dev points at
  * double[DOCKAUV_N_STATS] on the device: it is the send buffer of the per-rollout NCCL all-reduce. */

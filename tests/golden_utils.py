@@ -10,7 +10,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def case_names():
     return sorted(os.path.splitext(os.path.basename(p))[0]
-                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not p.endswith("unit_vectors.npz"))
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not p.endswith(("unit_vectors.npz", "episode_storage_obstacles.npz")))
 
 
 def load_case(name):

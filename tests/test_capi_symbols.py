@@ -42,7 +42,7 @@ def test_argument_validation_without_gpu():
     h = C.c_void_p()
     p.abi_version = 99
     assert lib.dockauv_create(C.byref(p), 16, 0, C.byref(h)) == -1 and b"ABI" in lib.dockauv_last_error()
-    p.abi_version = 1
+    p.abi_version = 2
     assert lib.dockauv_create(C.byref(p), 0, 0, C.byref(h)) == -1
     p.n_rays = 62
     assert lib.dockauv_create(C.byref(p), 16, 0, C.byref(h)) == -1 and b"radar" in lib.dockauv_last_error()
