@@ -387,7 +387,7 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
         e = launch_step<float>(k, h->params.vehicle, layout, st);
     }
     if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
-    if (layout == DOCKAUV_LAYOUT_SPLIT) {
+    if (layout == DOCKAUV_LAYOUT_SPLIT && dbg == nullptr) {   // with debug outputs the fused kernel serves the call
         const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
         h->launches += 2 * ((end - begin + chunk - 1) / chunk);
     } else {

@@ -9,7 +9,8 @@ namespace dockauv {
 
 // Dynamics + everything that does not need the radar.  Shared by both layouts.
 //   returns false for an env index beyond the batch.
-template <typename T, int VEH, int NU>
+//   DBG: compile the optional debug outputs in (parity tests); the throughput kernels are built without them.
+template <typename T, int VEH, int NU, bool DBG>
 __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T &spsi_out, T &cpsi_out,
                                               float obs16[16], T att_out[3]) {
     const int64_t N = p.n_envs;
@@ -174,7 +175,7 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     r[6] = lp_d;   // parked here for reward_set 2 (overwritten by the obstacle-avoidance term)
     r[7] = penalty;
 
-    {
+    if (DBG) {
         if (p.dbg_euler_dot)
             for (int c = 0; c < 3; c++) p.dbg_euler_dot[(int64_t)c * N + i] = ed[c];
         if (p.dbg_nu_c)
@@ -199,7 +200,7 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
 // Final bookkeeping of one env once the radar term `r_oa` (Reward.obstacle_avoidance, docking3d.py:767-792) and
 // the collision flag are known: reward (docking3d.py:560-595), done, counters (:380-385), statistics and the
 // SB3-VecEnv style auto-reset.  Returns the done flag.
-template <typename T>
+template <typename T, bool DBG>
 __device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T r_oa, bool collision,
                                             WarpStats &bs) {
     const int64_t N = p.n_envs;
@@ -217,7 +218,7 @@ __device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, Step
     if (p.cond_bits) p.cond_bits[i] = (uint8_t)cond;
     T ep_ret = cy.ep_return + reward;
     int32_t t_new = cy.t_steps + 1;
-    if (p.dbg_reward_arr)
+    if (DBG && p.dbg_reward_arr)
         for (int k = 0; k < 13; k++) p.dbg_reward_arr[(int64_t)k * N + i] = r[k];
     if (done) {
         if (p.ep_return_out) p.ep_return_out[i] = ep_ret;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(128) step_tpe_kernel(const __grid_constant__ K
         StepCarry<T> cy;
         T spsi, cpsi, att[3];
         float obs16[16];
-        step_dynamics<T, VEH, NU>(p, i, cy, spsi, cpsi, obs16, att);
+        step_dynamics<T, VEH, NU, true>(p, i, cy, spsi, cpsi, obs16, att);
 
         // ---- obstacles: ray-independent pre-computation + body collision (docking3d.py:444-460)
         const T R_safe = p.safety_radius;
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(128) step_tpe_kernel(const __grid_constant__ K
         }
         T r_oa = p.sum_beta_oa / oa_dot - T(1);
 
-        done = step_finish<T>(p, i, cy, r_oa, collision, bs);
+        done = step_finish<T, true>(p, i, cy, r_oa, collision, bs);
 
         // ---- observation row
         write_obs_row<T>(p, i, obs16, 16, 0, done);

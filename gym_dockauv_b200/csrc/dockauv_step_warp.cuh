@@ -76,7 +76,8 @@ constexpr int kHandoffWords = 22;    // pos[3] R[9] poison | reward terms r[0..7
 #define DOCKAUV_MINB_B 4
 #endif
 // min-CTAs hints (0 = none): the fused kernel is fastest without one; measured for the split pair in profiles/r01/NOTES.md
-template <typename T, int VEH, int NU, int RPL, int MODE>
+// DBG: debug outputs compiled in (fused kernel only; the split pair is always built without them).
+template <typename T, int VEH, int NU, int RPL, int MODE, bool DBG>
 __global__ void __launch_bounds__(kWarpEnvs, MODE == 1 ? DOCKAUV_MINB_A : (MODE == 2 ? DOCKAUV_MINB_B : 0))
 step_warp_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -100,7 +101,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
     if (MODE != 2 && active) {
         T spsi, cpsi, att[3];
         float obs16[16];
-        step_dynamics<T, VEH, NU>(p, i, cy, spsi, cpsi, obs16, att);
+        step_dynamics<T, VEH, NU, DBG>(p, i, cy, spsi, cpsi, obs16, att);
         // 0 for a finite pose, NaN otherwise: added to every ray distance so that a blown-up state poisons the
         // radar outputs exactly like the reference's NaN propagation does
         const T poison = (((cy.pos[0] + cy.pos[1]) + (cy.pos[2] + att[0])) + (att[1] + att[2])) * T(0);
@@ -141,12 +142,8 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
         T *ps = s_pose + tid * kPoseStride;
 #pragma unroll
         for (int c = 0; c < 13; c++) ps[c] = hf[(int64_t)c * N];
-#pragma unroll
-        for (int c = 0; c < 8; c++) cy.rarr[c] = hf[(int64_t)(13 + c) * N];
-        cy.delta_d = hf[(int64_t)21 * N];
-        cy.cond = p.handoff_cond[i];
-        cy.t_steps = p.t_steps[i];
-        cy.ep_return = p.ep_return[i];
+        // the reward terms and counters of the hand-off are only read in phase C: they are loaded there, so that they
+        // do not occupy ~24 registers during the whole radar phase
     }
     __syncwarp();
 
@@ -154,7 +151,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
     T my_oa_dot = p.sum_beta_oa;     // owner-lane copies of the per-env radar results (neutral values: r_oa = 0)
     bool my_col = false;
     bool my_view_empty = true;       // nothing within range and view: the owner lane writes the all-ones ray cells
-    const bool no_dbg = p.dbg_ray_dist == nullptr && p.dbg_obs == nullptr;
+    const bool no_dbg = !DBG || (p.dbg_ray_dist == nullptr && p.dbg_obs == nullptr);
     {
         T *s_pre = reinterpret_cast<T *>(smem_raw + L.pre_off) + warp * 32 * kPreStride;
         T *s_ray = reinterpret_cast<T *>(smem_raw + L.ray_off) + warp * L.ray_stride;
@@ -226,7 +223,8 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                     const T pos[3] = {pose[0], pose[1], pose[2]};
                     T *w = s_pre + lane * kPreStride;
                     T rad, dist;
-                    T q0[3], q1[3];     // obstacle end points relative to the vehicle, NED
+                    T q0[3], q1[3];     // end points of the reachable part of the obstacle axis relative to the vehicle, NED
+                    bool axis_out = false;
                     if (slot_is_cap) {
                         const T bot[3] = {ob[0], ob[1], ob[2]}, top[3] = {ob[3], ob[4], ob[5]};
                         rad = ob[6];
@@ -247,10 +245,23 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                         cross3(q.oa, q.ba, cr);
                         const T perp2 = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * (inv_n * inv_n);
                         dist = Mth<T>::sqrt_(hh * hh + perp2);
+                        // only the part of the axis within max_dist + radius of the vehicle can carry surface points a
+                        // ray reaches: clip the axis to that ball before the field-of-view test (a 40 m pillar seen
+                        // under roll / pitch otherwise has its far ends on both sides of every plane of the pyramid).
+                        // |bot + s ba - pos|^2 <= Rr^2  <=>  s in [(baoa - sqrt(D)) / baba, (baoa + sqrt(D)) / baba]
+                        const T Rr = (cull + rad) * T(1.000001);
+                        const T oaoa = q.c2a + rad * rad;
+                        const T D = q.baoa * q.baoa - q.baba * (oaoa - Rr * Rr);
+                        const T sq = Mth<T>::sqrt_(D < T(0) ? T(0) : D);
+                        const T inv_baba = inv_n * inv_n;
+                        T s_lo = (q.baoa - sq) * inv_baba, s_hi = (q.baoa + sq) * inv_baba;
+                        s_lo = s_lo > T(0) ? s_lo : T(0);
+                        s_hi = s_hi < T(1) ? s_hi : T(1);
+                        axis_out = (D < T(0)) || (s_lo > s_hi);
 #pragma unroll
                         for (int c = 0; c < 3; c++) {
-                            q0[c] = -q.oa[c];
-                            q1[c] = -q.oc2[c];
+                            q0[c] = s_lo * q.ba[c] - q.oa[c];
+                            q1[c] = s_hi * q.ba[c] - q.oa[c];
                         }
                     } else {
                         T oc[3], d2 = T(0);
@@ -271,7 +282,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                     //  - range: nearest surface point farther than max_dist;
                     //  - field of view: the obstacle lies entirely outside one of the five planes of the ray pyramid
                     //    {x >= 0, |y| <= ty x, |z| <= tz x} (body frame), in which every ray direction lies.
-                    bool outside = dist - rad > cull;
+                    bool outside = (dist - rad > cull) || axis_out;
                     {
                         T a0[3], a1[3];    // body-frame coordinates R^T q
 #pragma unroll
@@ -292,6 +303,14 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
             }
             const unsigned colb = __ballot_sync(0xffffffffu, hit_body);
             const unsigned nearb = __ballot_sync(0xffffffffu, in_range);
+#ifdef DOCKAUV_VIEW_STATS   // tuning builds: in-view (env, obstacle) pairs and envs with a non-empty view -> stats[11], [12]
+            if (lane == 0) {
+                int n_env_view = 0;
+                for (int s = 0; s < epp; s++) n_env_view += ((nearb >> (slots * s)) & slot_mask) != 0u;
+                atomicAdd(&p.stats[11], (double)__popc(nearb));
+                atomicAdd(&p.stats[12], (double)n_env_view);
+            }
+#endif
             {   // the owner lane of each env of this sub-batch keeps its collision flag for phase C
                 const int s = lane - eb;
                 if (s >= 0 && s < epp) {
@@ -386,7 +405,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                         // min positive distance over obstacles (docking3d.py:438-439), max_dist if none or farther
                         T d = (best[j] > dmax ? dmax : best[j]) + poison;
                         s_ray[ir] = d;
-                        if (p.dbg_ray_dist) p.dbg_ray_dist[(int64_t)ir * N + ie] = d;
+                        if (DBG && p.dbg_ray_dist) p.dbg_ray_dist[(int64_t)ir * N + ie] = d;
                         // (gamma_c (1 - c))^2 with c = clip(1 - d/d_max, 0, 1): 1 - c = d/d_max for d in [0, d_max]
                         const T x = d * inv_dmax;
                         const T qq = x * x;
@@ -410,7 +429,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                         T o = mx * inv_dmax;                     // clip(d / max_dist, 0, 1), docking3d.py:487
                         o = o > T(1) ? T(1) : o;
                         orow[lane] = (float)o;
-                        if (p.dbg_obs) p.dbg_obs[(int64_t)(16 + lane) * N + ie] = o;
+                        if (DBG && p.dbg_obs) p.dbg_obs[(int64_t)(16 + lane) * N + ie] = o;
                     }
                 } else {
                     for (int pc = lane; pc < p.n_rr; pc += 32) {
@@ -427,7 +446,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                         T o = mx * inv_dmax;
                         o = o > T(1) ? T(1) : o;
                         orow[pc] = (float)o;
-                        if (p.dbg_obs) p.dbg_obs[(int64_t)(16 + pc) * N + ie] = o;
+                        if (DBG && p.dbg_obs) p.dbg_obs[(int64_t)(16 + pc) * N + ie] = o;
                     }
                 }
                 __syncwarp();
@@ -437,6 +456,15 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
 
     // ------------------------------------------------------------------ phase C
     bool done = false;
+    if (MODE == 2 && active) {
+        const T *hf = p.handoff + i;
+#pragma unroll
+        for (int c = 0; c < 8; c++) cy.rarr[c] = hf[(int64_t)(13 + c) * N];
+        cy.delta_d = hf[(int64_t)21 * N];
+        cy.cond = p.handoff_cond[i];
+        cy.t_steps = p.t_steps[i];
+        cy.ep_return = p.ep_return[i];
+    }
     if (active) {
         if (my_view_empty && no_dbg && s_pose[tid * kPoseStride + 12] == T(0)) {
             float *cells = p.obs + i * p.n_obs + 16;
@@ -448,7 +476,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
             }
         }
         const T r_oa = p.sum_beta_oa / my_oa_dot - T(1);      // docking3d.py:792
-        done = step_finish<T>(p, i, cy, r_oa, my_col, bs);
+        done = step_finish<T, DBG>(p, i, cy, r_oa, my_col, bs);
     }
     __syncwarp();     // orders the pooled-cell stores of the other lanes before the row fix-up below
     // ---- rows of envs whose episode ended (~1 % per step): keep the last observation as terminal_observation and
@@ -470,12 +498,12 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
     bs.flush(p.stats, warp == 0 ? n_here : 0);
 }
 
-template <typename T, int VEH, int NU, int RPL, int MODE>
+template <typename T, int VEH, int NU, int RPL, int MODE, bool DBG>
 static cudaError_t launch_step_warp_rpl(const KParams<T> &k, cudaStream_t st) {
     const int64_t n = k.env_end - k.env_begin;
     const WarpSmem<T> L(k.n_rays);
     const int smem = MODE == 1 ? 0 : L.total;
-    auto kern = step_warp_kernel<T, VEH, NU, RPL, MODE>;
+    auto kern = step_warp_kernel<T, VEH, NU, RPL, MODE, DBG>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
@@ -485,28 +513,37 @@ static cudaError_t launch_step_warp_rpl(const KParams<T> &k, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+template <typename T>
+static bool wants_debug(const KParams<T> &k) {
+    return k.dbg_ray_dist || k.dbg_reward_arr || k.dbg_euler_dot || k.dbg_nu_c || k.dbg_nav || k.dbg_obs || k.dbg_state_dot;
+}
+
 // rays per lane: 2 covers the stock 63-ray and the 64-ray radar; 8 covers everything up to DOCKAUV_MAX_RAYS
 template <typename T, int VEH, int NU>
 static cudaError_t launch_step_warp(const KParams<T> &k, cudaStream_t st) {
-    if (k.n_rays <= 64) return launch_step_warp_rpl<T, VEH, NU, 2, 0>(k, st);
-    return launch_step_warp_rpl<T, VEH, NU, 8, 0>(k, st);
+    if (wants_debug(k))
+        return k.n_rays <= 64 ? launch_step_warp_rpl<T, VEH, NU, 2, 0, true>(k, st)
+                              : launch_step_warp_rpl<T, VEH, NU, 8, 0, true>(k, st);
+    if (k.n_rays <= 64) return launch_step_warp_rpl<T, VEH, NU, 2, 0, false>(k, st);
+    return launch_step_warp_rpl<T, VEH, NU, 8, 0, false>(k, st);
 }
 
-// layout DOCKAUV_LAYOUT_SPLIT: dynamics launch + radar launch per chunk of `chunk` envs, so that the hand-off of a
-// chunk (184 B per env) is still in L2 when the second launch reads it
+// layout DOCKAUV_LAYOUT_SPLIT: dynamics launch + radar launch per chunk of `chunk` envs (default: one pair over the
+// whole batch).  Debug outputs are only compiled into the fused kernel, which then serves the call.
 template <typename T, int VEH, int NU>
 static cudaError_t launch_step_split(const KParams<T> &k, int64_t chunk, cudaStream_t st) {
+    if (wants_debug(k)) return launch_step_warp<T, VEH, NU>(k, st);
     if (chunk <= 0) chunk = k.env_end - k.env_begin;
     chunk = ((chunk + kWarpEnvs - 1) / kWarpEnvs) * kWarpEnvs;
     for (int64_t b = k.env_begin; b < k.env_end; b += chunk) {
         KParams<T> kc = k;
         kc.env_begin = b;
         kc.env_end = b + chunk < k.env_end ? b + chunk : k.env_end;
-        cudaError_t e = launch_step_warp_rpl<T, VEH, NU, 2, 1>(kc, st);
+        cudaError_t e = launch_step_warp_rpl<T, VEH, NU, 2, 1, false>(kc, st);
         if (e != cudaSuccess) return e;
         // the radar launch does not depend on the vehicle: one instantiation serves all of them
-        e = (k.n_rays <= 64) ? launch_step_warp_rpl<T, DOCKAUV_VEHICLE_BLUEROV2, 6, 2, 2>(kc, st)
-                             : launch_step_warp_rpl<T, DOCKAUV_VEHICLE_BLUEROV2, 6, 8, 2>(kc, st);
+        e = (k.n_rays <= 64) ? launch_step_warp_rpl<T, DOCKAUV_VEHICLE_BLUEROV2, 6, 2, 2, false>(kc, st)
+                             : launch_step_warp_rpl<T, DOCKAUV_VEHICLE_BLUEROV2, 6, 8, 2, false>(kc, st);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

@@ -96,3 +96,30 @@ for a in stalls:
     agg.update(stalls[a])
 tot = sum(agg.values()) or 1
 print("stalls:", "  ".join(f"{k[6:]} {100 * v / tot:.1f}%" for k, v in agg.most_common(9)))
+
+# ---- phase shares: owner lines in dockauv_step_warp.cuh grouped by the section comments of the kernel
+import re
+marks = []
+for n, text in enumerate(src["dockauv_step_warp.cuh"], 1):
+    m = re.search(r"// -+ (phase [ABC])$|// ---- (pass 1|pass 2|clamp|2x2 max-pool|rows of envs)", text)
+    if m:
+        marks.append((n, (m.group(1) or m.group(2))))
+    if "T my_oa_dot = p.sum_beta_oa" in text:
+        marks.append((n, "B setup (ray table, pool map, first obstacle load)"))
+    if "for (int eb = 0; eb < n_warp; eb += epp)" in text:
+        marks.append((n, "B sub-batch loop head"))
+marks.sort()
+grp, gsmp = collections.Counter(), collections.Counter()
+for (f, l), v in by_line.items():
+    if f == "dockauv_step_warp.cuh":
+        name = "kernel entry"
+        for n, g in marks:
+            if l >= n:
+                name = g
+    else:
+        name = f
+    grp[name] += v
+    gsmp[name] += by_line_smp[(f, l)]
+print("\nphase shares (deduplicated):")
+for g, v in grp.most_common():
+    print(f"  {g:55s} inst {100 * v / ti:5.1f}% ({v / n_envs:6.1f}/env)  smp {100 * gsmp[g] / ts:5.1f}%")
