@@ -193,7 +193,7 @@ def run_ours(args, rank, world, local_rank):
             # per-rollout episode statistics: one small NCCL all-reduce on a side stream
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                red = stats_t.clone()
+                red = env.stats_tensor().clone()      # folds the per-CTA replicas on the side stream first
                 dist.all_reduce(red)
             n_reduces += 1
     torch.cuda.current_stream(dev).wait_stream(side)

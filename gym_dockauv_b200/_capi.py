@@ -26,6 +26,7 @@ SYMBOLS = {
     "dockauv_rollout": (_i, [_vp, _vp, _i, _i, C.POINTER(DockauvRolloutOut), _i, _i, _vp]),
     "dockauv_gae": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i64, C.c_float, C.c_float, _vp, _vp, _vp]),
     "dockauv_stats_ptr": (_i, [_vp, C.POINTER(_vp)]),
+    "dockauv_fold_stats": (_i, [_vp, _vp]),
     "dockauv_get_stats": (_i, [_vp, C.POINTER(C.c_double), _vp]),
     "dockauv_clear_stats": (_i, [_vp, _vp]),
     "dockauv_measure_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -47,6 +47,7 @@ struct DeviceGuard {
 };
 
 static const int kHostStreams = 3;
+static const size_t kStatsBytes = sizeof(double) * DOCKAUV_N_STATS * DOCKAUV_STAT_COPIES;   // replica 0 = the public vector
 
 struct DockauvHandle {
     DockauvParams params;
@@ -234,8 +235,8 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
             }
         cudaError_t e1 = cudaMalloc(&h->ray_tab, host.size());
         cudaError_t e2 = e1 == cudaSuccess ? cudaMemcpy(h->ray_tab, host.data(), host.size(), cudaMemcpyHostToDevice) : e1;
-        cudaError_t e3 = e2 == cudaSuccess ? cudaMalloc((void **)&h->stats, sizeof(double) * DOCKAUV_N_STATS) : e2;
-        cudaError_t e4 = e3 == cudaSuccess ? cudaMemset(h->stats, 0, sizeof(double) * DOCKAUV_N_STATS) : e3;
+        cudaError_t e3 = e2 == cudaSuccess ? cudaMalloc((void **)&h->stats, kStatsBytes) : e2;
+        cudaError_t e4 = e3 == cudaSuccess ? cudaMemset(h->stats, 0, kStatsBytes) : e3;
         if (e4 != cudaSuccess) {
             if (h->ray_tab) cudaFree(h->ray_tab);
             if (h->stats) cudaFree(h->stats);
@@ -247,21 +248,38 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         h->kd.stats = h->stats;
         h->kf.stats = h->stats;
     }
-    if (p->layout == DOCKAUV_LAYOUT_SPLIT ||
-        (p->layout == DOCKAUV_LAYOUT_AUTO && (p->n_capsules + p->n_spheres) > 0)) {
+    if ((p->layout == DOCKAUV_LAYOUT_SPLIT || p->layout == DOCKAUV_LAYOUT_PIPELINE || p->layout == DOCKAUV_LAYOUT_AUTO) &&
+        (p->n_capsules + p->n_spheres) > 0) {
+        // hand-off between the launches of the split / pipeline layouts: T[22][N] + cond u32[N]; the pipeline adds the
+        // view word u32[N], the ray list u64[N], the obstacle-avoidance sums T[N] and one list counter per 128 envs
         const size_t esz = p->precision == DOCKAUV_F64 ? 8 : 4;
-        const size_t words = (size_t)22 * (size_t)n_envs * esz;
-        cudaError_t e5 = cudaMalloc(&h->handoff, words + sizeof(uint32_t) * (size_t)n_envs);
+        const size_t n = (size_t)n_envs;
+        const size_t words = (size_t)22 * n * esz;
+        const size_t off_cond = words, off_info = off_cond + 4 * n, off_list = (off_info + 4 * n + 7) & ~(size_t)7;
+        const size_t off_oa = off_list + 8 * n, off_cnt = off_oa + esz * n;
+        const size_t n_cnt = n / 128 + 2;
+        cudaError_t e5 = cudaMalloc(&h->handoff, off_cnt + 4 * n_cnt);
+        if (e5 == cudaSuccess) e5 = cudaMemset((char *)h->handoff + off_cnt, 0, 4 * n_cnt);
         if (e5 != cudaSuccess) {
             cudaFree(h->ray_tab);
             cudaFree(h->stats);
+            if (h->handoff) cudaFree(h->handoff);
             delete h;
             return fail(DOCKAUV_ECUDA, "device allocation of the hand-off buffer failed: %s", cudaGetErrorString(e5));
         }
-        h->kd.handoff = (double *)h->handoff;
-        h->kf.handoff = (float *)h->handoff;
-        h->kd.handoff_cond = h->kf.handoff_cond = (uint32_t *)((char *)h->handoff + words);
-        // one launch pair over the whole batch by default: smaller chunks would keep the hand-off in L2 but lose more
+        char *base = (char *)h->handoff;
+        h->kd.handoff = (double *)base;
+        h->kf.handoff = (float *)base;
+        h->kd.handoff_cond = h->kf.handoff_cond = (uint32_t *)(base + off_cond);
+        h->kd.view_info = h->kf.view_info = (uint32_t *)(base + off_info);
+        h->kd.view_list = h->kf.view_list = (unsigned long long *)(base + off_list);
+        h->kd.oa_dot = (double *)(base + off_oa);
+        h->kf.oa_dot = (float *)(base + off_oa);
+        h->kd.view_count = h->kf.view_count = (unsigned int *)(base + off_cnt);
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        h->kd.sm_count = h->kf.sm_count = sms;
+        // one launch group over the whole batch by default: smaller chunks would keep the hand-off in L2 but lose more
         // to partial waves than they gain (0.89 ms at 1M envs per pair, 0.94 at 512K, 1.04 at 256K)
         const int64_t chunk = p->split_chunk_envs > 0 ? p->split_chunk_envs : n_envs;
         h->kd.split_chunk = h->kf.split_chunk = chunk;
@@ -387,9 +405,12 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
         e = launch_step<float>(k, h->params.vehicle, layout, st);
     }
     if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
-    if (layout == DOCKAUV_LAYOUT_SPLIT && dbg == nullptr) {   // with debug outputs the fused kernel serves the call
+    const bool staged = dbg == nullptr && (h->params.n_capsules + h->params.n_spheres) > 0;   // else: the fused kernel
+    if (layout == DOCKAUV_LAYOUT_SPLIT && staged) {
         const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
         h->launches += 2 * ((end - begin + chunk - 1) / chunk);
+    } else if (layout == DOCKAUV_LAYOUT_PIPELINE && staged) {
+        h->launches += 4;
     } else {
         h->launches += 1;
     }
@@ -631,10 +652,30 @@ extern "C" int dockauv_stats_ptr(DockauvHandle *h, double **stats_dev) {
     return DOCKAUV_OK;
 }
 
+__global__ void fold_stats_kernel(double *stats) {
+    const int k = threadIdx.x;
+    if (k >= DOCKAUV_N_STATS) return;
+    // atomic swap / add: a step kernel on another stream may be accumulating while the replicas are folded
+    double s = 0.0;
+    for (int c = 1; c < DOCKAUV_STAT_COPIES; c++)
+        s += __longlong_as_double((long long)atomicExch((unsigned long long *)&stats[c * DOCKAUV_N_STATS + k], 0ull));
+    if (s != 0.0) atomicAdd(&stats[k], s);
+}
+
+extern "C" int dockauv_fold_stats(DockauvHandle *h, void *stream) {
+    if (!h) return fail(DOCKAUV_EINVAL, "null handle");
+    DeviceGuard guard(h->device);
+    fold_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->stats);
+    CUDA_TRY(cudaGetLastError());
+    return DOCKAUV_OK;
+}
+
 extern "C" int dockauv_get_stats(DockauvHandle *h, double *stats_host, void *stream) {
     if (!h || !stats_host) return fail(DOCKAUV_EINVAL, "null argument");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = dockauv_fold_stats(h, stream);
+    if (rc != DOCKAUV_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(stats_host, h->stats, sizeof(double) * DOCKAUV_N_STATS, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return DOCKAUV_OK;
@@ -643,7 +684,7 @@ extern "C" int dockauv_get_stats(DockauvHandle *h, double *stats_host, void *str
 extern "C" int dockauv_clear_stats(DockauvHandle *h, void *stream) {
     if (!h) return fail(DOCKAUV_EINVAL, "null handle");
     DeviceGuard guard(h->device);
-    CUDA_TRY(cudaMemsetAsync(h->stats, 0, sizeof(double) * DOCKAUV_N_STATS, (cudaStream_t)stream));
+    CUDA_TRY(cudaMemsetAsync(h->stats, 0, kStatsBytes, (cudaStream_t)stream));
     return DOCKAUV_OK;
 }
 

@@ -402,6 +402,99 @@ __device__ __forceinline__ void capsule_pre(const T pos[3], const T bot[3], cons
     q.r = r;
 }
 
+// Ray-independent work for one (env, obstacle) pair, shared by every radar layout:
+//   * the record the ray tests read -- capsule: ba[3] oa[3] baba baoa c c2a c2b, sphere: oc[3] c (written if REC);
+//   * the body-collision test (shape.py:182-210 with the safety radius of auvsim.py:43): dist_line_point
+//     (shape.py:393-417) with one reciprocal instead of three divisions and hypot;
+//   * two exact radar culls.  A culled obstacle can only yield "no positive distance" or a distance beyond max_dist,
+//     both of which end as max_dist (sensor.py:117):
+//       - range: nearest surface point farther than max_dist;
+//       - field of view: the part of the obstacle a ray can reach lies entirely outside one of the five planes of the
+//         ray pyramid {x >= 0, |y| <= ty x, |z| <= tz x} (body frame), in which every ray direction lies.  Only axis
+//         points within max_dist + r of the vehicle can carry reachable surface points, so a capsule axis is first
+//         clipped to that ball (a 40 m pillar seen under roll / pitch otherwise has its far ends on both sides of every
+//         plane):  |bot + s ba - pos|^2 <= Rr^2  <=>  s in [(baoa - sqrt(D)) / baba, (baoa + sqrt(D)) / baba].
+//   pos: vehicle position, Rm: Rzyx row-major (9 words), ob: raw obstacle (capsule: bot[3] top[3] r; sphere: c[3] r)
+template <typename T, bool REC>
+__device__ __forceinline__ void obstacle_pair(const KParams<T> &p, const T pos[3], const T *Rm, const T ob[7], bool is_cap,
+                                              T *w, bool &hit_body, bool &in_view) {
+    const T cull = p.radar_max_dist * T(1.000001);
+    T rad, dist;
+    T q0[3], q1[3];     // end points of the reachable part of the obstacle axis relative to the vehicle, NED
+    bool axis_out = false;
+    if (is_cap) {
+        const T bot[3] = {ob[0], ob[1], ob[2]}, top[3] = {ob[3], ob[4], ob[5]};
+        rad = ob[6];
+        CapPre<T> q;
+        capsule_pre<T>(pos, bot, top, rad, q);
+        if (REC) {
+            w[0] = q.ba[0]; w[1] = q.ba[1]; w[2] = q.ba[2];
+            w[3] = q.oa[0]; w[4] = q.oa[1]; w[5] = q.oa[2];
+            w[6] = q.baba; w[7] = q.baoa; w[8] = q.c; w[9] = q.c2a; w[10] = q.c2b;
+        }
+        const T inv_n = T(1) / Mth<T>::sqrt_(q.baba);
+        const T sp = -q.baoa * inv_n;                                                         // (bot - pos) . d
+        const T tp = (q.oc2[0] * q.ba[0] + q.oc2[1] * q.ba[1] + q.oc2[2] * q.ba[2]) * inv_n;  // (pos - top) . d
+        T hh = sp;
+        if (tp > hh || tp != tp) hh = tp;
+        if (T(0) > hh) hh = T(0);
+        T cr[3];
+        cross3(q.oa, q.ba, cr);
+        const T perp2 = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * (inv_n * inv_n);
+        dist = Mth<T>::sqrt_(hh * hh + perp2);
+        const T Rr = (cull + rad) * T(1.000001);
+        const T oaoa = q.c2a + rad * rad;
+        const T D = q.baoa * q.baoa - q.baba * (oaoa - Rr * Rr);
+        const T sq = Mth<T>::sqrt_(D < T(0) ? T(0) : D);
+        const T inv_baba = inv_n * inv_n;
+        T s_lo = (q.baoa - sq) * inv_baba, s_hi = (q.baoa + sq) * inv_baba;
+        s_lo = s_lo > T(0) ? s_lo : T(0);
+        s_hi = s_hi < T(1) ? s_hi : T(1);
+        axis_out = (D < T(0)) || (s_lo > s_hi);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            q0[c] = s_lo * q.ba[c] - q.oa[c];
+            q1[c] = s_hi * q.ba[c] - q.oa[c];
+        }
+    } else {
+        T oc[3], d2 = T(0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            oc[c] = pos[c] - ob[c];
+            d2 += oc[c] * oc[c];
+        }
+        rad = ob[3];
+        if (REC) {
+            w[0] = oc[0]; w[1] = oc[1]; w[2] = oc[2]; w[3] = d2 - rad * rad;
+        }
+        dist = Mth<T>::sqrt_(d2);
+#pragma unroll
+        for (int c = 0; c < 3; c++) q0[c] = q1[c] = -oc[c];
+    }
+    hit_body = dist <= rad + p.safety_radius;
+    bool outside = (dist - rad > cull) || axis_out;
+    {
+        T a0[3], a1[3];    // body-frame coordinates R^T q
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            a0[c] = Rm[c] * q0[0] + Rm[3 + c] * q0[1] + Rm[6 + c] * q0[2];
+            a1[c] = Rm[c] * q1[0] + Rm[3 + c] * q1[1] + Rm[6 + c] * q1[2];
+        }
+        // (clipping the segment against all five planes at once -- exact for segments that leave the pyramid through
+        // different planes -- lists 24 % instead of 28 % of the C4 envs but costs more in the cull than it saves in the
+        // ray launch: measured, profiles/r01/NOTES.md)
+        const T rm = rad * T(1.000001) + T(1e-9);
+        const T ry = rm * p.fov_ny, rz = rm * p.fov_nz;
+        const T ty = p.fov_ty, tz = p.fov_tz;
+        outside |= (a0[0] < -rm) && (a1[0] < -rm);
+        outside |= (a0[1] - ty * a0[0] > ry) && (a1[1] - ty * a1[0] > ry);
+        outside |= (-a0[1] - ty * a0[0] > ry) && (-a1[1] - ty * a1[0] > ry);
+        outside |= (a0[2] - tz * a0[0] > rz) && (a1[2] - tz * a1[0] > rz);
+        outside |= (-a0[2] - tz * a0[0] > rz) && (-a1[2] - tz * a1[0] > rz);
+    }
+    in_view = !outside;
+}
+
 // shape.py:341-390 for one ray: infinite-cylinder root, body hit if 0 < y < baba, else end-cap sphere.
 // Returns -inf for "no intersection" and a negative distance for "behind" exactly like the reference.
 template <typename T>

@@ -206,6 +206,7 @@ struct WarpStats {
     // one same-address atomic per CTA instead of one per warp)
     __device__ __forceinline__ void flush(double *g, int n_steps) const {
         const int lane = threadIdx.x & 31;
+        g += (blockIdx.x & (DOCKAUV_STAT_COPIES - 1)) * DOCKAUV_N_STATS;   // replica of this CTA (dockauv_fold_stats)
         if (__any_sync(0xffffffffu, done)) {
             double v[DOCKAUV_STAT_ENV_STEPS];
             v[DOCKAUV_STAT_EPISODES] = done ? 1.0 : 0.0;

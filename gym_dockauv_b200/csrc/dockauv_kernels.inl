@@ -2,6 +2,7 @@
 #include "dockauv_launch.h"
 #include "dockauv_step_tpe.cuh"
 #include "dockauv_step_warp.cuh"
+#include "dockauv_step_pipe.cuh"
 
 namespace dockauv {
 
@@ -11,6 +12,7 @@ static cudaError_t launch_variant(const KParams<T> &k, int layout, cudaStream_t 
     if (n <= 0) return cudaSuccess;
     if (layout == DOCKAUV_LAYOUT_WARP_RAYS) return launch_step_warp<T, VEH, NU>(k, st);
     if (layout == DOCKAUV_LAYOUT_SPLIT) return launch_step_split<T, VEH, NU>(k, k.split_chunk, st);
+    if (layout == DOCKAUV_LAYOUT_PIPELINE) return launch_step_pipe<T, VEH, NU>(k, st);
     const int threads = 128;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
     step_tpe_kernel<T, VEH, NU><<<blocks, threads, 0, st>>>(k);

@@ -59,6 +59,13 @@ struct KParams {
     T *handoff;
     uint32_t *handoff_cond;
     int64_t split_chunk;
+    // pipeline layout (library-owned): per-env view word (in-view mask | collision | listed), compact list of the envs
+    // the ray launch has to visit (local env index | mask << 32), its counter(s), obstacle-avoidance sums
+    uint32_t *view_info;
+    unsigned long long *view_list;
+    unsigned int *view_count;
+    T *oa_dot;
+    int32_t sm_count;
     // stats accumulator (double[DOCKAUV_N_STATS])
     double *stats;
     // ray table in global memory (lane-indexed reads in the warp layout): rd_b[3][n_rays], beta_oa[n_rays]

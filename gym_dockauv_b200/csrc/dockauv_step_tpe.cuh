@@ -200,7 +200,8 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
 // Final bookkeeping of one env once the radar term `r_oa` (Reward.obstacle_avoidance, docking3d.py:767-792) and
 // the collision flag are known: reward (docking3d.py:560-595), done, counters (:380-385), statistics and the
 // SB3-VecEnv style auto-reset.  Returns the done flag.
-template <typename T, bool DBG>
+//   DEFER_RESET: the caller re-initialises finished envs itself (pipeline layout: compacted per CTA).
+template <typename T, bool DBG, bool DEFER_RESET = false>
 __device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T r_oa, bool collision,
                                             WarpStats &bs) {
     const int64_t N = p.n_envs;
@@ -231,7 +232,7 @@ __device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, Step
         bs.nan = reward != reward;      // episodes that ended on a NaN reward
     }
     if (done && p.auto_reset) {
-        reset_env<T>(p, i);
+        if (!DEFER_RESET) reset_env<T>(p, i);
     } else {
         p.ep_return[i] = ep_ret;
         p.t_steps[i] = t_new;

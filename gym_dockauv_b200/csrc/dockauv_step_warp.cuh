@@ -96,6 +96,8 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
     const int e_warp = warp * 32;                         // first env (CTA-local) of this warp
     const int n_warp = max(0, min(32, n_here - e_warp));  // envs this warp really has
 
+    // the pipeline layout appends to a list in its second launch: the first one empties it
+    if (MODE == 1 && p.view_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *p.view_count = 0u;
     // ------------------------------------------------------------------ phase A
     StepCarry<T> cy;
     if (MODE != 2 && active) {
@@ -157,8 +159,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
         T *s_ray = reinterpret_cast<T *>(smem_raw + L.ray_off) + warp * L.ray_stride;
         const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
         const int n_r = p.n_rays;
-        const T dmax = p.radar_max_dist, inv_dmax = T(1) / dmax, R_safe = p.safety_radius;
-        const T cull = dmax * T(1.000001);
+        const T dmax = p.radar_max_dist, inv_dmax = T(1) / dmax;
         // this lane's rays: body-frame direction and obstacle-avoidance weight stay in registers
         T rb[RPL][3], bw[RPL];
 #pragma unroll
@@ -190,7 +191,6 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
         const bool slot_is_cap = my_slot < n_caps, slot_used = my_slot < n_obst;
         const T *obst_row = slot_is_cap ? p.capsules + (int64_t)(my_slot * 7) * N
                                         : p.spheres + (int64_t)((my_slot - n_caps) * 4) * N;
-        const T fov_ty = p.fov_ty, fov_tz = p.fov_tz, fov_ny = p.fov_ny, fov_nz = p.fov_nz;
 
         // raw obstacle of this lane's (env, slot) pair: loaded one sub-batch ahead so that the HBM latency of the
         // next pre-pass is covered by the ray loop of the current one
@@ -222,83 +222,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                     const T *pose = s_pose + (e_warp + e) * kPoseStride;
                     const T pos[3] = {pose[0], pose[1], pose[2]};
                     T *w = s_pre + lane * kPreStride;
-                    T rad, dist;
-                    T q0[3], q1[3];     // end points of the reachable part of the obstacle axis relative to the vehicle, NED
-                    bool axis_out = false;
-                    if (slot_is_cap) {
-                        const T bot[3] = {ob[0], ob[1], ob[2]}, top[3] = {ob[3], ob[4], ob[5]};
-                        rad = ob[6];
-                        CapPre<T> q;
-                        capsule_pre<T>(pos, bot, top, rad, q);
-                        w[0] = q.ba[0]; w[1] = q.ba[1]; w[2] = q.ba[2];
-                        w[3] = q.oa[0]; w[4] = q.oa[1]; w[5] = q.oa[2];
-                        w[6] = q.baba; w[7] = q.baoa; w[8] = q.c; w[9] = q.c2a; w[10] = q.c2b;
-                        // dist_line_point (shape.py:393-417): clamped parallel part and perpendicular part of pos
-                        // relative to the axis, with one reciprocal instead of three divisions and hypot
-                        const T inv_n = T(1) / Mth<T>::sqrt_(q.baba);
-                        const T sp = -q.baoa * inv_n;                                   // (bot - pos) . d
-                        const T tp = (q.oc2[0] * q.ba[0] + q.oc2[1] * q.ba[1] + q.oc2[2] * q.ba[2]) * inv_n;  // (pos - top) . d
-                        T hh = sp;
-                        if (tp > hh || tp != tp) hh = tp;
-                        if (T(0) > hh) hh = T(0);
-                        T cr[3];
-                        cross3(q.oa, q.ba, cr);
-                        const T perp2 = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * (inv_n * inv_n);
-                        dist = Mth<T>::sqrt_(hh * hh + perp2);
-                        // only the part of the axis within max_dist + radius of the vehicle can carry surface points a
-                        // ray reaches: clip the axis to that ball before the field-of-view test (a 40 m pillar seen
-                        // under roll / pitch otherwise has its far ends on both sides of every plane of the pyramid).
-                        // |bot + s ba - pos|^2 <= Rr^2  <=>  s in [(baoa - sqrt(D)) / baba, (baoa + sqrt(D)) / baba]
-                        const T Rr = (cull + rad) * T(1.000001);
-                        const T oaoa = q.c2a + rad * rad;
-                        const T D = q.baoa * q.baoa - q.baba * (oaoa - Rr * Rr);
-                        const T sq = Mth<T>::sqrt_(D < T(0) ? T(0) : D);
-                        const T inv_baba = inv_n * inv_n;
-                        T s_lo = (q.baoa - sq) * inv_baba, s_hi = (q.baoa + sq) * inv_baba;
-                        s_lo = s_lo > T(0) ? s_lo : T(0);
-                        s_hi = s_hi < T(1) ? s_hi : T(1);
-                        axis_out = (D < T(0)) || (s_lo > s_hi);
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            q0[c] = s_lo * q.ba[c] - q.oa[c];
-                            q1[c] = s_hi * q.ba[c] - q.oa[c];
-                        }
-                    } else {
-                        T oc[3], d2 = T(0);
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            oc[c] = pos[c] - ob[c];
-                            d2 += oc[c] * oc[c];
-                        }
-                        rad = ob[3];
-                        w[0] = oc[0]; w[1] = oc[1]; w[2] = oc[2]; w[3] = d2 - rad * rad;
-                        dist = Mth<T>::sqrt_(d2);
-#pragma unroll
-                        for (int c = 0; c < 3; c++) q0[c] = q1[c] = -oc[c];
-                    }
-                    hit_body = dist <= rad + R_safe;              // shape.py:182-210 (safety radius, auvsim.py:43)
-                    // radar culls (exact: a culled obstacle can only yield "no positive distance" or a distance
-                    // beyond max_dist, both of which end as max_dist, sensor.py:117):
-                    //  - range: nearest surface point farther than max_dist;
-                    //  - field of view: the obstacle lies entirely outside one of the five planes of the ray pyramid
-                    //    {x >= 0, |y| <= ty x, |z| <= tz x} (body frame), in which every ray direction lies.
-                    bool outside = (dist - rad > cull) || axis_out;
-                    {
-                        T a0[3], a1[3];    // body-frame coordinates R^T q
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            a0[c] = pose[3 + c] * q0[0] + pose[6 + c] * q0[1] + pose[9 + c] * q0[2];
-                            a1[c] = pose[3 + c] * q1[0] + pose[6 + c] * q1[1] + pose[9 + c] * q1[2];
-                        }
-                        const T rm = rad * T(1.000001) + T(1e-9);
-                        const T ry = rm * fov_ny, rz = rm * fov_nz;
-                        outside |= (a0[0] < -rm) && (a1[0] < -rm);
-                        outside |= (a0[1] - fov_ty * a0[0] > ry) && (a1[1] - fov_ty * a1[0] > ry);
-                        outside |= (-a0[1] - fov_ty * a0[0] > ry) && (-a1[1] - fov_ty * a1[0] > ry);
-                        outside |= (a0[2] - fov_tz * a0[0] > rz) && (a1[2] - fov_tz * a1[0] > rz);
-                        outside |= (-a0[2] - fov_tz * a0[0] > rz) && (-a1[2] - fov_tz * a1[0] > rz);
-                    }
-                    in_range = !outside;
+                    obstacle_pair<T, true>(p, pos, pose + 3, ob, slot_is_cap, w, hit_body, in_range);
                 }
             }
             const unsigned colb = __ballot_sync(0xffffffffu, hit_body);
@@ -532,7 +456,7 @@ static cudaError_t launch_step_warp(const KParams<T> &k, cudaStream_t st) {
 // whole batch).  Debug outputs are only compiled into the fused kernel, which then serves the call.
 template <typename T, int VEH, int NU>
 static cudaError_t launch_step_split(const KParams<T> &k, int64_t chunk, cudaStream_t st) {
-    if (wants_debug(k)) return launch_step_warp<T, VEH, NU>(k, st);
+    if (wants_debug(k) || k.handoff == nullptr) return launch_step_warp<T, VEH, NU>(k, st);   // no obstacles: no hand-off buffer
     if (chunk <= 0) chunk = k.env_end - k.env_begin;
     chunk = ((chunk + kWarpEnvs - 1) / kWarpEnvs) * kWarpEnvs;
     for (int64_t b = k.env_begin; b < k.env_end; b += chunk) {

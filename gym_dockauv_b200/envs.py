@@ -328,6 +328,7 @@ class BaseDocking3d:
     def stats_tensor(self):
         """The device-side statistics vector (float64[16]) as a tensor view -- the all-reduce send buffer."""
         p = C.c_void_p()
+        _capi.check(self._lib.dockauv_fold_stats(self._handle, self._stream()))   # per-CTA replicas -> the public vector
         _capi.check(self._lib.dockauv_stats_ptr(self._handle, C.byref(p)))
         return _DevView(p.value, N_STATS, self.device).tensor()
 

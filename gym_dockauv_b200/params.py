@@ -16,7 +16,7 @@ ABI_VERSION = 2
 MAX_U, MAX_CAPSULES, MAX_SPHERES, MAX_RAYS, N_REWARDS, N_STATS = 8, 8, 8, 256, 13, 16
 F64, F32 = 0, 1
 ACT_F64, ACT_F32 = 0, 1
-LAYOUTS = {"auto": 0, "thread_per_env": 1, "warp_rays": 2, "split": 3}
+LAYOUTS = {"auto": 0, "thread_per_env": 1, "warp_rays": 2, "split": 3, "pipeline": 4}
 VEHICLE_IDS = {"BlueROV2": 0, "LAUV": 1}
 SCENARIO_IDS = {"SimpleDocking3d": 0, "SimpleCurrentDocking3d": 1, "CapsuleDocking3d": 2,
                 "CapsuleCurrentDocking3d": 3, "ObstaclesDocking3d": 4, "ObstaclesCurrentDocking3d": 5,

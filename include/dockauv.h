@@ -95,6 +95,8 @@ extern "C" {
 #define DOCKAUV_LAYOUT_THREAD_PER_ENV 1   /* one thread does everything for one env */
 #define DOCKAUV_LAYOUT_WARP_RAYS 2        /* dynamics thread-per-env, radar one warp per env (lanes = rays) */
 #define DOCKAUV_LAYOUT_SPLIT 3            /* the same two phases as two launches per chunk, hand-off through L2 */
+#define DOCKAUV_LAYOUT_PIPELINE 4         /* four launches: dynamics, cull (thread per env), rays (one warp per env that
+                                             has an obstacle in view, from a compact list), finish (thread per env) */
 
 /* indices into the stats vector (sums since the last clear; reduce over ranks with one all-reduce) */
 #define DOCKAUV_STAT_EPISODES 0
@@ -260,8 +262,13 @@ DOCKAUV_API int dockauv_gae(const void *rewards_dev, int reward_precision, const
                 float gae_lambda, float *advantages_dev, float *returns_dev, void *stream);
 
 /* Episode statistics accumulated on the device since the last clear (DOCKAUV_STAT_*).  stats_dev points at
- * double[DOCKAUV_N_STATS] on the device: it is the send buffer of the per-rollout NCCL all-reduce. */
+ * double[DOCKAUV_N_STATS] on the device: it is the send buffer of the per-rollout NCCL all-reduce.  The kernels
+ * accumulate into DOCKAUV_STAT_COPIES replicas of the vector (same-address atomics of 10^4 warps per step would
+ * serialise in one L2 slice); dockauv_fold_stats adds the replicas into the vector stats_dev points at -- call it on
+ * the stream before reading through the pointer.  dockauv_get_stats folds by itself. */
+#define DOCKAUV_STAT_COPIES 32
 DOCKAUV_API int dockauv_stats_ptr(DockauvHandle *h, double **stats_dev);
+DOCKAUV_API int dockauv_fold_stats(DockauvHandle *h, void *stream);
 DOCKAUV_API int dockauv_get_stats(DockauvHandle *h, double *stats_host, void *stream);
 DOCKAUV_API int dockauv_clear_stats(DockauvHandle *h, void *stream);
 

@@ -50,7 +50,7 @@ for r in csv.reader(sys.stdin):
             pass
 
 src = {}
-for f in ("dockauv_step_warp.cuh", "dockauv_step_tpe.cuh", "dockauv_device.cuh", "dockauv_env.cuh"):
+for f in ("dockauv_step_warp.cuh", "dockauv_step_pipe.cuh", "dockauv_step_tpe.cuh", "dockauv_device.cuh", "dockauv_env.cuh"):
     try:
         src[f] = open(f"{ROOT}/gym_dockauv_b200/csrc/{f}").read().split("\n")
     except OSError:
@@ -58,9 +58,10 @@ for f in ("dockauv_step_warp.cuh", "dockauv_step_tpe.cuh", "dockauv_device.cuh",
 
 
 def owner(lines):
-    w = [l for l in lines if l[0] == "dockauv_step_warp.cuh"]
-    if w:
-        return w[-1]
+    for f in ("dockauv_step_pipe.cuh", "dockauv_step_warp.cuh"):
+        w = [l for l in lines if l[0] == f]
+        if w:
+            return w[-1]
     t = [l for l in lines if l[0] == "dockauv_step_tpe.cuh"]
     if t:
         return t[-1]

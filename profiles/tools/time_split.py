@@ -11,6 +11,7 @@ pool = [torch.rand(N, 6, device="cuda", generator=gen) * 2 - 1 for _ in range(16
 out = []
 for name, kw in [("ObstaclesDocking3d", dict(layout="warp_rays", n_synthetic_spheres=3)),
                  ("ObstaclesDocking3d", dict(layout="split", n_synthetic_spheres=3, split_chunk_envs=1 << 20)),
+                 ("ObstaclesDocking3d", dict(layout="pipeline", n_synthetic_spheres=3)),
                  ("SimpleDocking3d", dict(layout="warp_rays")),
                  ("SimpleDocking3d", dict(layout="split", split_chunk_envs=1 << 20))]:
     env = envs.SCENARIOS[name](cfg, num_envs=N, seed=0, **kw)

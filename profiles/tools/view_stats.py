@@ -6,7 +6,7 @@ from gym_dockauv_b200 import envs
 from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
 cfg = dict(BASE_CONFIG); cfg["radar"] = dict(RADAR_64)
 N = 1 << 20
-env = envs.ObstaclesDocking3d(cfg, num_envs=N, seed=0, n_synthetic_spheres=3)
+env = envs.ObstaclesDocking3d(cfg, num_envs=N, seed=0, n_synthetic_spheres=3, layout=sys.argv[1] if len(sys.argv) > 1 else "auto")
 env.reset()
 gen = torch.Generator(device="cuda").manual_seed(1)
 for k in range(128):

@@ -39,13 +39,16 @@ def _env_for_case(g, layout, precision="f64", debug=True):
     return env
 
 
-@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split"])
+@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split", "pipeline"])
 @pytest.mark.parametrize("name", case_names())
 def test_cuda_matches_reference_trace(name, layout):
     import torch
     g = load_case(name)
     meta = g["meta"]
-    env = _env_for_case(g, layout)
+    # the multi-launch layouts are built without debug outputs (a debug call is served by the fused kernel), so they
+    # are compared through everything the step returns: observations, rewards, flags, state, counters
+    dbg = layout in ("thread_per_env", "warp_rays")
+    env = _env_for_case(g, layout, debug=dbg)
     E, T = g["action"].shape[:2]
     f32 = meta["action_dtype"] == "f32"
     unstable = meta["vehicle"] == "LAUV" and meta["config"]["t_step_size"] > 0.05
@@ -75,14 +78,15 @@ def test_cuda_matches_reference_trace(name, layout):
         # ---- continuous outputs
         worst["state"] = max(worst["state"], rel_err(st[m], g["state"][m, t]))
         worst["u"] = max(worst["u"], rel_err(env.u_prev.t().cpu().numpy()[m, :meta["n_u"]], g["u"][m, t]))
-        worst["ray"] = max(worst["ray"], rel_err(env.debug["ray_dist"].t().cpu().numpy()[m], g["ray_dist"][m, t]))
         worst["reward"] = max(worst["reward"], rel_err(reward.cpu().numpy()[m], g["reward"][m, t]))
-        worst["rarr"] = max(worst["rarr"], rel_err(env.debug["reward_arr"].t().cpu().numpy()[m], g["reward_arr"][m, t]))
-        nav = env.debug["nav"].t().cpu().numpy()
-        ref_nav = np.stack([g["delta_d"][:, t], g["delta_theta"][:, t], g["delta_psi"][:, t]], axis=1)
-        worst["nav"] = max(worst["nav"], rel_err(nav[m], ref_nav[m]))
-        worst["edot"] = max(worst["edot"], rel_err(env.debug["euler_dot"].t().cpu().numpy()[m], g["state_dot"][m, t, 3:6]))
-        worst["nu_c"] = max(worst["nu_c"], rel_err(env.debug["nu_c"].t().cpu().numpy()[m], g["nu_c"][m, t, :3]))
+        if dbg:
+            worst["ray"] = max(worst["ray"], rel_err(env.debug["ray_dist"].t().cpu().numpy()[m], g["ray_dist"][m, t]))
+            worst["rarr"] = max(worst["rarr"], rel_err(env.debug["reward_arr"].t().cpu().numpy()[m], g["reward_arr"][m, t]))
+            nav = env.debug["nav"].t().cpu().numpy()
+            ref_nav = np.stack([g["delta_d"][:, t], g["delta_theta"][:, t], g["delta_psi"][:, t]], axis=1)
+            worst["nav"] = max(worst["nav"], rel_err(nav[m], ref_nav[m]))
+            worst["edot"] = max(worst["edot"], rel_err(env.debug["euler_dot"].t().cpu().numpy()[m], g["state_dot"][m, t, 3:6]))
+            worst["nu_c"] = max(worst["nu_c"], rel_err(env.debug["nu_c"].t().cpu().numpy()[m], g["nu_c"][m, t, :3]))
         worst["ret"] = max(worst["ret"], rel_err(env.ep_return.cpu().numpy()[m], g["cum_reward"][m, t]))
         ob = obs.cpu().numpy()[m]
         ref_ob = g["obs"][m, t]
@@ -90,7 +94,7 @@ def test_cuda_matches_reference_trace(name, layout):
         obs_mismatch += int((~same).sum())
         assert rel_err(ob, ref_ob) < 2e-7, (name, t)
         # pre-cast observation vs the reference's float32-rounded value: half a float32 ulp of slack
-        assert rel_err(env.debug["obs_f64"].t().cpu().numpy()[m], ref_ob.astype(np.float64)) < 6.1e-8, (name, t)
+        assert not dbg or rel_err(env.debug["obs_f64"].t().cpu().numpy()[m], ref_ob.astype(np.float64)) < 6.1e-8, (name, t)
     assert compared >= (150 if unstable else int(g["ep_len"].sum()))
     for k, v in worst.items():
         assert v < TOL, (name, layout, k, v, worst)
@@ -130,7 +134,7 @@ def _oracle_rollout(config, scenario, n, steps, seed, n_synth, dtype, layout, pr
     return out
 
 
-@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split"])
+@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split", "pipeline"])
 def test_random_rollout_with_autoreset_vs_oracle(layout):
     """256 envs x 300 steps of the BASELINE C4 workload (64 rays, 5 capsules + 3 spheres), auto-reset on."""
     from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
@@ -264,22 +268,26 @@ def test_step_host_matches_device_step():
 
 
 def test_layouts_agree_bitwise_on_flags_large_batch():
-    """65,536 envs, 40 steps: the two kernel layouts give identical done flags and rewards within 1e-12."""
+    """65,536 envs, 40 steps: all kernel layouts give identical done flags / observations and rewards within 1e-12."""
     import torch
     from gym_dockauv_b200 import envs
     from gym_dockauv_b200.config import BASE_CONFIG
     n = 65536
     es = [envs.ObstaclesCurrentDocking3d(dict(BASE_CONFIG), num_envs=n, seed=4, layout=l)
-          for l in ("thread_per_env", "warp_rays")]
+          for l in ("thread_per_env", "warp_rays", "split", "pipeline")]
     for e in es:
         e.reset()
     gen = torch.Generator(device="cuda").manual_seed(0)
     for _ in range(40):
         a = torch.rand(n, 6, device="cuda", generator=gen) * 2 - 1
         outs = [e.step(a) for e in es]
-        assert torch.equal(outs[0][2], outs[1][2])
-        assert rel_err(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy()) < 1e-12
-        assert torch.equal(outs[0][0], outs[1][0])
+        for o in outs[1:]:
+            assert torch.equal(outs[0][2], o[2])
+            assert rel_err(outs[0][1].cpu().numpy(), o[1].cpu().numpy()) < 1e-12
+            assert torch.equal(outs[0][0], o[0])
+    for e in es[1:]:
+        assert rel_err(es[0].state.cpu().numpy(), e.state.cpu().numpy()) < 1e-12
+        assert torch.equal(es[0].t_steps, e.t_steps) and torch.equal(es[0].episode, e.episode)
     for e in es:
         e.close()
 
