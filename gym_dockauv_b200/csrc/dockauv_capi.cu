@@ -349,11 +349,11 @@ static bool scenario_has_current(int scn) {
 
 static int resolve_layout(const DockauvHandle *h) {
     int layout = h->params.layout;
-    // measured on B200 (profiles/r01/NOTES.md): with obstacles the two-launch split layout is ~12 % faster than the
-    // fused kernel (0.89 vs 1.00 ms per 1M envs on C4), without obstacles the fused kernel wins marginally;
+    // measured on B200 (profiles/r01/NOTES.md, 1M envs of C4): fused kernel 1.02 ms, split pair 0.82 ms, four-launch
+    // pipeline 0.70 ms; without obstacles there is no radar work to separate and the fused kernel is used;
     // thread-per-env stays as the independently written cross-check
     if (layout == DOCKAUV_LAYOUT_AUTO)
-        layout = (h->params.n_capsules + h->params.n_spheres) > 0 ? DOCKAUV_LAYOUT_SPLIT : DOCKAUV_LAYOUT_WARP_RAYS;
+        layout = (h->params.n_capsules + h->params.n_spheres) > 0 ? DOCKAUV_LAYOUT_PIPELINE : DOCKAUV_LAYOUT_WARP_RAYS;
     return layout;
 }
 

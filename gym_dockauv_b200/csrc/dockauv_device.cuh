@@ -47,6 +47,27 @@ struct Mth<double> {
     static __device__ __forceinline__ double hypot_(double x, double y) { return hypot(x, y); }
     static __device__ __forceinline__ double cos_(double x) { return cos(x); }
     static __device__ __forceinline__ double sin_(double x) { return sin(x); }
+    // Branch-free sqrt / reciprocal for the ray hit path (a handful of lanes per warp get there, so every instruction
+    // of the library versions -- ~20 + ~25 with their slow-path checks -- is paid at 1/6 lane utilisation): hardware
+    // seed (upper ~20 mantissa bits, full double range) + Newton steps; relative error ~2e-16, NaN / inf for
+    // non-positive or non-finite input like the library versions.
+    static __device__ __forceinline__ double sqrt_pos(double x) {
+        double r;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+        const double hx = 0.5 * x;
+        r = r * fma(-hx * r, r, 1.5);
+        r = r * fma(-hx * r, r, 1.5);
+        double s = x * r;
+        s = fma(0.5 * r, fma(-s, s, x), s);
+        return s;
+    }
+    static __device__ __forceinline__ double rcp_(double x) {
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        y = fma(y, fma(-x, y, 1.0), y);
+        y = fma(y, fma(-x, y, 1.0), y);
+        return y;
+    }
 };
 
 template <>
@@ -66,6 +87,8 @@ struct Mth<float> {
     static __device__ __forceinline__ float hypot_(float x, float y) { return hypotf(x, y); }
     static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
     static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
+    static __device__ __forceinline__ float sqrt_pos(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float rcp_(float x) { return 1.0f / x; }
 };
 
 // np.clip: minimum(maximum(x, lo), hi) -- NaN propagates

@@ -283,14 +283,14 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                             const T b = baba * rdoa - baoa * bard;
                             const T h = b * b - a * cc;
                             if (h > T(0)) {
-                                const T t = (-b - Mth<T>::sqrt_(h)) / a;
+                                const T t = (-b - Mth<T>::sqrt_pos(h)) * Mth<T>::rcp_(a);
                                 const T y = baoa + t * bard;
                                 T v = t;
                                 if (!(y > T(0) && y < baba)) {
                                     const bool far_end = y >= T(0);
                                     const T b2 = far_end ? rdoa - bard : rdoa;     // rd . (pos - cap end)
                                     const T h2 = b2 * b2 - (far_end ? c2b : c2a);
-                                    v = (h2 > T(0)) ? (-b2 - Mth<T>::sqrt_(h2)) : T(-1);
+                                    v = (h2 > T(0)) ? (-b2 - Mth<T>::sqrt_pos(h2 > T(0) ? h2 : T(1))) : T(-1);
                                 }
                                 if (v > T(0) && v < best[j]) best[j] = v;
                             }
@@ -307,7 +307,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
                             const T b = v0.x * rd[j][0] + v0.y * rd[j][1] + v1.x * rd[j][2];
                             const T h = b * b - v1.y;
                             if (h >= T(0)) {
-                                const T v = -b - Mth<T>::sqrt_(h);
+                                const T v = -b - (h > T(0) ? Mth<T>::sqrt_pos(h) : T(0));
                                 if (v > T(0) && v < best[j]) best[j] = v;
                             }
                         }
