@@ -61,6 +61,15 @@ struct Mth<double> {
         s = fma(0.5 * r, fma(-s, s, x), s);
         return s;
     }
+    static __device__ __forceinline__ double rsqrt_pos(double x) {      // 1 / sqrt(x), x > 0
+        double r;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+        const double hx = 0.5 * x;
+        r = r * fma(-hx * r, r, 1.5);
+        r = r * fma(-hx * r, r, 1.5);
+        r = r * fma(-hx * r, r, 1.5);
+        return r;
+    }
     static __device__ __forceinline__ double rcp_(double x) {
         double y;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -88,6 +97,7 @@ struct Mth<float> {
     static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
     static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
     static __device__ __forceinline__ float sqrt_pos(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float rsqrt_pos(float x) { return 1.0f / sqrtf(x); }
     static __device__ __forceinline__ float rcp_(float x) { return 1.0f / x; }
 };
 
@@ -455,7 +465,7 @@ __device__ __forceinline__ void obstacle_pair(const KParams<T> &p, const T pos[3
             w[3] = q.oa[0]; w[4] = q.oa[1]; w[5] = q.oa[2];
             w[6] = q.baba; w[7] = q.baoa; w[8] = q.c; w[9] = q.c2a; w[10] = q.c2b;
         }
-        const T inv_n = T(1) / Mth<T>::sqrt_(q.baba);
+        const T inv_n = Mth<T>::rsqrt_pos(q.baba);
         const T sp = -q.baoa * inv_n;                                                         // (bot - pos) . d
         const T tp = (q.oc2[0] * q.ba[0] + q.oc2[1] * q.ba[1] + q.oc2[2] * q.ba[2]) * inv_n;  // (pos - top) . d
         T hh = sp;
@@ -464,11 +474,12 @@ __device__ __forceinline__ void obstacle_pair(const KParams<T> &p, const T pos[3
         T cr[3];
         cross3(q.oa, q.ba, cr);
         const T perp2 = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * (inv_n * inv_n);
-        dist = Mth<T>::sqrt_(hh * hh + perp2);
+        const T dd = hh * hh + perp2;
+        dist = dd > T(0) ? Mth<T>::sqrt_pos(dd) : dd;        // 0 stays 0, NaN stays NaN
         const T Rr = (cull + rad) * T(1.000001);
         const T oaoa = q.c2a + rad * rad;
         const T D = q.baoa * q.baoa - q.baba * (oaoa - Rr * Rr);
-        const T sq = Mth<T>::sqrt_(D < T(0) ? T(0) : D);
+        const T sq = D > T(0) ? Mth<T>::sqrt_pos(D) : T(0);
         const T inv_baba = inv_n * inv_n;
         T s_lo = (q.baoa - sq) * inv_baba, s_hi = (q.baoa + sq) * inv_baba;
         s_lo = s_lo > T(0) ? s_lo : T(0);
@@ -490,7 +501,7 @@ __device__ __forceinline__ void obstacle_pair(const KParams<T> &p, const T pos[3
         if (REC) {
             w[0] = oc[0]; w[1] = oc[1]; w[2] = oc[2]; w[3] = d2 - rad * rad;
         }
-        dist = Mth<T>::sqrt_(d2);
+        dist = d2 > T(0) ? Mth<T>::sqrt_pos(d2) : d2;
 #pragma unroll
         for (int c = 0; c < 3; c++) q0[c] = q1[c] = -oc[c];
     }

@@ -315,7 +315,10 @@ __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS) rays_kernel
 }
 
 // ------------------------------------------------------------------------------------------------------- 4. finish
-constexpr int kFinishThreads = 256;
+#ifndef DOCKAUV_FINISH_THREADS
+#define DOCKAUV_FINISH_THREADS 256
+#endif
+constexpr int kFinishThreads = DOCKAUV_FINISH_THREADS;
 
 template <typename T>
 __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const __grid_constant__ KParams<T> p) {
@@ -379,6 +382,9 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const __grid_con
     // (b) re-initialised side by side by the first threads (dense lanes instead of one lane per warp; a separate
     //     re-initialisation launch over a global list was slower: 48 us against the ~15 us this costs)
     if (p.auto_reset && (int)threadIdx.x < n_done) reset_env<T>(p, i0 + s_reset[threadIdx.x]);
+#ifdef DOCKAUV_EXP_RESET_TWICE
+    if (p.auto_reset && (int)threadIdx.x < n_done) reset_env<T>(p, i0 + s_reset[threadIdx.x]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------- launcher
