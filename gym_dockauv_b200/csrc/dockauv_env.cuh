@@ -118,6 +118,133 @@ static __device__ __noinline__ void reset_env(const KParams<T> &p, int64_t i) {
     p.ep_return[i] = T(0);
 }
 
+// The same re-initialisation done by one WARP for one env (pipeline layout): a reset is a ~3000-instruction
+// dependent chain (11..19 Philox blocks, eight sincos, ~80 scattered stores) when a single thread walks through it,
+// and the CTA that contains the finished env waits for it.  Here lane b draws Philox block b, the draws travel by
+// shuffle, and the independent pieces go to different lanes: 0 pose / goal / counters, 1..4 pillars, 5 dock capsule
+// and unused capsule slots, 6..13 spheres, 14 current and command.  Every value is computed by the same expression
+// as in reset_env, so both produce identical bits.  Must be called by all 32 lanes.
+template <typename T>
+__device__ __forceinline__ void reset_env_warp(const KParams<T> &p, int64_t i, int lane) {
+    const int64_t N = p.n_envs;
+    const uint64_t gid = p.env_id0 + (uint64_t)i;
+    const uint32_t ep = (uint32_t)p.episode[i];
+    __syncwarp();                                    // every lane has read the episode counter before lane 0 bumps it
+    const double PI = 3.141592653589793;
+    double u[2];
+    philox_uniform_pair(p.seed, gid, ep, (uint32_t)lane, u);
+    const int scn = p.scenario;
+    const int n_synth = min(p.n_synth_sph, p.n_sph);
+    // draws of this lane's role: nine consecutive slots starting at `base`
+    int base = 0;
+    if (lane >= 1 && lane <= 4) base = 9;
+    else if (lane >= 6 && lane <= 13) base = 13 + 3 * (lane - 6);
+    else if (lane == 14) base = 10;
+    double v[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+        const int idx = base + r;
+        const double a = __shfl_sync(0xffffffffu, u[0], (idx >> 1) & 31), b = __shfl_sync(0xffffffffu, u[1], (idx >> 1) & 31);
+        v[r] = (idx & 1) ? b : a;
+    }
+    const bool has_goal_ring = scn >= DOCKAUV_SCN_CAPSULE;
+    const bool has_dock = has_goal_ring && scn != DOCKAUV_SCN_OBSTACLES_NOCAP && p.n_caps > 0;
+    const bool has_pillars = scn >= DOCKAUV_SCN_OBSTACLES;
+    const int first_pillar = has_dock ? 1 : 0;
+    const int n_pillars = has_pillars ? max(0, min(4, p.n_caps - first_pillar)) : 0;
+    if (lane == 0) {
+        p.episode[i] = (int32_t)(ep + 1);
+        double goal[3] = {0.0, 0.0, 0.0};
+        double heading = (v[0] - 0.5) * PI;                                   // :814
+        double r[3] = {v[1] - 0.5, v[2] - 0.5, v[3] - 0.5};                   // :694-696
+        {
+            double sg = (r[2] > 0.0) - (r[2] < 0.0);
+            r[2] = fabs(r[0] + r[1]) / 3 * sg;
+        }
+        double sc = 15.0 / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        double pos[3] = {r[0] * sc, r[1] * sc, r[2] * sc};
+        double max_att = (double)p.max_attitude;
+        double att[3] = {(v[4] - 0.5) * 2 * (max_att * 0.7), (v[5] - 0.5) * 2 * (max_att * 0.7),
+                         (v[6] - 0.5) * 2 * PI};                               // :699-703
+        if (has_goal_ring) {                                                   // :860-886
+            double theta = v[7] * 2 * PI;
+            double radius = 1.0 + (double)p.safety_radius;
+            double s, c;
+            sincos(theta, &s, &c);
+            goal[0] = c * radius;
+            goal[1] = s * radius;
+            goal[2] = (v[8] - 0.5) * 4.0;
+            heading = (double)ssa<double>(atan2(0.0 - goal[1], 0.0 - goal[0]));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            p.state[(int64_t)c * N + i] = (T)pos[c];
+            p.state[(int64_t)(3 + c) * N + i] = (T)att[c];
+            p.goal[(int64_t)c * N + i] = (T)goal[c];
+        }
+#pragma unroll
+        for (int c = 6; c < 12; c++) p.state[(int64_t)c * N + i] = T(0);     // auvsim.py:55-65
+        p.heading_goal[i] = (T)heading;
+        p.t_steps[i] = 0;
+        p.ep_return[i] = T(0);
+    } else if (lane <= 4) {                                                    // pillars, :919-946
+        const int k = lane - 1;
+        if (k < n_pillars) {
+            double theta = v[0] * 2 * PI;
+            for (int q = 0; q < k; q++) theta += 2 * PI / 4;
+            const double half = 2.0 * (double)p.max_dist_from_goal / 2.0;
+            double s, c;
+            sincos(theta, &s, &c);
+            const double x = c * 6, y = s * 6;
+            const double cap[7] = {x, y, half, x, y, -half, 1.0};
+            const int kc = first_pillar + k;
+#pragma unroll
+            for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+        }
+    } else if (lane == 5) {
+        if (has_dock) {
+            const double cap[7] = {0, 0, 2.0, 0, 0, -2.0, 1.0};              // bot = 2*position - top, shape.py:105-108
+#pragma unroll
+            for (int j = 0; j < 7; j++) p.capsules[(int64_t)j * N + i] = (T)cap[j];
+        }
+        for (int kc = first_pillar + n_pillars; kc < p.n_caps; kc++) {         // unused slots: far away, zero radius
+            const double cap[7] = {1e6, 1e6, 1e6, 1e6, 1e6, 1e6 + 1.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+        }
+    } else if (lane <= 13) {
+        const int ks = lane - 6;
+        if (ks < n_synth) {                                                     // BASELINE C4 extension: random unit spheres
+            double z = 2 * v[0] - 1;
+            double az = 2 * PI * v[1];
+            double rr = 4.0 + 6.0 * v[2];
+            double q = sqrt(1 - z * z), s, c;
+            sincos(az, &s, &c);
+            p.spheres[(int64_t)(ks * 4 + 0) * N + i] = (T)(rr * q * c);
+            p.spheres[(int64_t)(ks * 4 + 1) * N + i] = (T)(rr * q * s);
+            p.spheres[(int64_t)(ks * 4 + 2) * N + i] = (T)(rr * z);
+            p.spheres[(int64_t)(ks * 4 + 3) * N + i] = (T)1.0;
+        } else if (ks < p.n_sph) {
+            p.spheres[(int64_t)(ks * 4 + 0) * N + i] = (T)1e6;
+            p.spheres[(int64_t)(ks * 4 + 1) * N + i] = (T)1e6;
+            p.spheres[(int64_t)(ks * 4 + 2) * N + i] = (T)1e6;
+            p.spheres[(int64_t)(ks * 4 + 3) * N + i] = (T)0.0;
+        }
+    } else if (lane == 14) {
+        double cur[5] = {0, 0, 0, 0, 0};
+        if (scn == DOCKAUV_SCN_SIMPLE_CURRENT || scn == DOCKAUV_SCN_CAPSULE_CURRENT || scn == DOCKAUV_SCN_OBSTACLES_CURRENT) {
+            cur[1] = (v[0] - 0.5) * 2 * (PI / 2);                             // :843-848, :903-907, :983-987
+            cur[2] = (v[1] - 0.5) * 2 * PI;
+            double speed = (scn == DOCKAUV_SCN_SIMPLE_CURRENT) ? v[2] * 1.0 : 0.5;
+            cur[0] = 0.5;
+            cur[3] = cur[4] = speed;
+        }
+#pragma unroll
+        for (int c = 0; c < 5; c++) p.current[(int64_t)c * N + i] = (T)cur[c];
+        for (int k = 0; k < p.n_u; k++) p.u_prev[(int64_t)k * N + i] = T(0);
+    }
+}
+
 template <typename T>
 __global__ void reset_kernel(const __grid_constant__ KParams<T> p, const uint8_t *mask) {
     int64_t i = p.env_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

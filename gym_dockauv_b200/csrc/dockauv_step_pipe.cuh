@@ -364,9 +364,10 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const __grid_con
     // ---- finished envs of this CTA, compacted:
     __syncthreads();
     const int n_done = s_n_reset;
-    // (a) their observation rows: the last observation is kept as terminal_observation and the all-zero reset
-    //     observation is handed back (docking3d.py:269,322); one warp per row, lanes = columns (a single thread walking
-    //     its own row is a chain of 32 dependent HBM round trips that the whole CTA then waits for)
+    // one warp per finished env (lanes = columns / reset roles; a single thread walking its own row is a chain of 32
+    // dependent HBM round trips, a single-thread reset a ~3000-instruction chain, and the whole CTA would wait):
+    //  (a) the last observation is kept as terminal_observation and the all-zero reset observation is handed back
+    //      (docking3d.py:269,322);  (b) the env is re-initialised (reset_env_warp).
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_obs = p.n_obs;
         for (int e = warp; e < n_done; e += kFinishThreads / 32) {
@@ -377,14 +378,9 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const __grid_con
                 if (trow) trow[c] = row[c];
                 if (p.auto_reset) row[c] = 0.0f;
             }
+            if (p.auto_reset) reset_env_warp<T>(p, ie, lane);
         }
     }
-    // (b) re-initialised side by side by the first threads (dense lanes instead of one lane per warp; a separate
-    //     re-initialisation launch over a global list was slower: 48 us against the ~15 us this costs)
-    if (p.auto_reset && (int)threadIdx.x < n_done) reset_env<T>(p, i0 + s_reset[threadIdx.x]);
-#ifdef DOCKAUV_EXP_RESET_TWICE
-    if (p.auto_reset && (int)threadIdx.x < n_done) reset_env<T>(p, i0 + s_reset[threadIdx.x]);
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------------- launcher
