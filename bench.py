@@ -5,7 +5,8 @@ BlueROV2, 64-ray radar, 5 capsules + 3 spheres -- config C4: 1,048,576 envs per 
     python bench.py [--gpus N] [--steps K] [--warmup W]             # our arm (CUDA, through the C ABI)
     python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU arm: the oracle port on host cores
 
-One "step" = one batched env.step() over every env of the rank (one kernel launch).  Rank 0 prints ONE JSON line.
+One "step" = one batched env.step() over every env of the rank (default layout with obstacles: four launches --
+dynamics, cull, rays, finish).  Rank 0 prints ONE JSON line.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The per-step
 working set (~0.9 GB at 1M envs) is far larger than L2 (126 MB), so no explicit L2 flush is needed (stated in
 config.l2).  Actions are synthetic i.i.d. U(-1,1) float32, pre-generated on the device for `value`; the `e2e`
@@ -27,9 +28,10 @@ import numpy as np  # noqa: E402
 BYTES_PER_ENV_STEP = 898      # algorithmic HBM bytes per env-step for C4 (FP64 SoA, f32 obs/actions)
 FLOPS_PER_ENV_STEP = 17700    # algorithmic flops per env-step for C4
 HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE step_warp_kernel launch over 1,048,576 envs (FP64) from the
-# committed `ncu --set full` capture profiles/r01/v6_step_warp_ncu_raw.csv: 614.8 MB + 337.2 MB
-NCU_TRAFFIC_BYTES_1M_F64 = 951.9e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the four launches of ONE pipeline-layout step over 1,048,576 envs
+# (FP64) from the committed `ncu --set full` capture profiles/r01/v9_pipeline_ncu_raw.csv (per launch in that file)
+NCU_TRAFFIC_BYTES_1M_F64 = 1845.9e6
+LAUNCH_NAMES = ("dynamics", "cull", "rays", "finish")
 SCENARIO = "ObstaclesDocking3d"
 N_SYNTH_SPHERES = 3
 
@@ -207,6 +209,15 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     stats = env.get_stats()
+    # per-launch durations (CUDA events recorded by the library between the launches of a step, on the launching
+    # stream), in a separate short pass so that the marks do not sit inside the timed region above
+    env.enable_timing(True)
+    per_launch = []
+    for k in range(min(32, args.steps)):
+        env.step(pool[k % len(pool)])
+        per_launch.append(env.last_step_ms()[1])
+    env.enable_timing(False)
+    launch_ms = np.array(per_launch).mean(axis=0) if per_launch and per_launch[0] else np.zeros(0)
 
     # ---- end to end through the public API with host buffers (rank-local, then max over ranks)
     e2e_steps = max(3, min(args.e2e_steps, args.steps))
@@ -271,9 +282,11 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak,
                          "traffic": NCU_TRAFFIC_BYTES_1M_F64 if (N == 1 << 20 and args.precision == "f64") else None,
-                         "traffic_source": "profiles/r01/v6_step_warp_ncu_raw.csv (bytes per launch)",
+                         "traffic_source": "profiles/r01/v9_pipeline_ncu_raw.csv (bytes per step = sum of its four launches)",
                          "peak_source": hbm_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kern_ms,
+                         "launches_ms": {n: float(v) for n, v in zip(LAUNCH_NAMES, launch_ms)},
+                         "dominant_launch": (LAUNCH_NAMES[int(np.argmax(launch_ms))] if launch_ms.size else "step"),
                          "note": "the path is FP64-pipe-bound (19.7 flop/B vs machine balance ~5.7), see 'pipe'"},
             "pipe": {"bound": "fp64" if args.precision == "f64" else "fp32", "achieved": achieved_tf,
                      "peak": pipe_peak, "unit": "TFLOP/s", "frac": (achieved_tf / pipe_peak) if pipe_peak else None,
@@ -298,7 +311,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--layout", default="auto", choices=["auto", "thread_per_env", "warp_rays"])
+    ap.add_argument("--layout", default="auto", choices=["auto", "thread_per_env", "warp_rays", "split", "pipeline"])
     ap.add_argument("--burn-in", type=int, default=128)
     ap.add_argument("--rollout", type=int, default=128)
     ap.add_argument("--action-pool", type=int, default=64)

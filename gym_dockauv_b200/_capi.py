@@ -33,6 +33,7 @@ SYMBOLS = {
     "dockauv_launch_count": (_i, [_vp, C.POINTER(_i64)]),
     "dockauv_enable_timing": (_i, [_vp, _i]),
     "dockauv_last_step_ms": (_i, [_vp, C.POINTER(C.c_float)]),
+    "dockauv_last_step_launch_ms": (_i, [_vp, C.POINTER(C.c_float), _i, C.POINTER(_i)]),
 }
 
 

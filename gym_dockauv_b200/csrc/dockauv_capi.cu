@@ -64,6 +64,8 @@ struct DockauvHandle {
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
+    cudaEvent_t marks[kMaxStepLaunches + 1] = {};   // per-launch marks of the multi-launch layouts (timing enabled)
+    int n_marks = 0;
     // host pipeline
     cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
     cudaEvent_t hev[kHostStreams] = {nullptr, nullptr, nullptr};
@@ -297,6 +299,8 @@ extern "C" int dockauv_destroy(DockauvHandle *h) {
     if (h->stats) cudaFree(h->stats);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t m : h->marks)
+        if (m) cudaEventDestroy(m);
     for (int s = 0; s < kHostStreams; s++) {
         if (h->hs[s]) cudaStreamDestroy(h->hs[s]);
         if (h->hev[s]) cudaEventDestroy(h->hev[s]);
@@ -382,7 +386,7 @@ static void set_io(KParams<T> &k, const void *actions, bool act_f32, const void 
 
 static int step_range(DockauvHandle *h, const void *actions, int action_dtype, const void *noise,
                       const DockauvStepOut *out, const DockauvDebugOut *dbg, int auto_reset, int64_t begin,
-                      int64_t end, cudaStream_t st) {
+                      int64_t end, cudaStream_t st, bool with_marks = false) {
     const bool actf32 = action_dtype == DOCKAUV_ACT_F32;
     const int layout = resolve_layout(h);
     // the current is "on" when the scenario spawns one, the caller asked for it, or noise is configured
@@ -395,14 +399,14 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
         k.env_begin = begin;
         k.env_end = end;
         k.has_current = has_current;
-        e = launch_step<double>(k, h->params.vehicle, layout, st);
+        e = launch_step<double>(k, h->params.vehicle, layout, st, with_marks ? h->marks : nullptr, with_marks ? &h->n_marks : nullptr);
     } else {
         KParams<float> k = h->kf;
         set_io<float>(k, actions, actf32, noise, *out, dbg, auto_reset);
         k.env_begin = begin;
         k.env_end = end;
         k.has_current = has_current;
-        e = launch_step<float>(k, h->params.vehicle, layout, st);
+        e = launch_step<float>(k, h->params.vehicle, layout, st, with_marks ? h->marks : nullptr, with_marks ? &h->n_marks : nullptr);
     }
     if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
     const bool staged = dbg == nullptr && (h->params.n_capsules + h->params.n_spheres) > 0;   // else: the fused kernel
@@ -410,7 +414,8 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
         const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
         h->launches += 2 * ((end - begin + chunk - 1) / chunk);
     } else if (layout == DOCKAUV_LAYOUT_PIPELINE && staged) {
-        h->launches += 4;
+        const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
+        h->launches += 4 * ((end - begin + chunk - 1) / chunk);
     } else {
         h->launches += 1;
     }
@@ -448,10 +453,11 @@ extern "C" int dockauv_step(DockauvHandle *h, const void *actions_dev, int actio
         if (!h->ev0) {
             CUDA_TRY(cudaEventCreate(&h->ev0));
             CUDA_TRY(cudaEventCreate(&h->ev1));
+            for (cudaEvent_t &m : h->marks) CUDA_TRY(cudaEventCreate(&m));
         }
         CUDA_TRY(cudaEventRecord(h->ev0, st));
     }
-    int rc = step_range(h, actions_dev, action_dtype, noise_dev, out, dbg, auto_reset, 0, h->n_envs, st);
+    int rc = step_range(h, actions_dev, action_dtype, noise_dev, out, dbg, auto_reset, 0, h->n_envs, st, h->timing);
     if (rc != DOCKAUV_OK) return rc;
     if (h->timing) {
         CUDA_TRY(cudaEventRecord(h->ev1, st));
@@ -707,6 +713,17 @@ extern "C" int dockauv_last_step_ms(DockauvHandle *h, float *ms) {
     DeviceGuard guard(h->device);
     CUDA_TRY(cudaEventSynchronize(h->ev1));
     CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_last_step_launch_ms(DockauvHandle *h, float *ms, int capacity, int *n_launches) {
+    if (!h || !ms || !n_launches) return fail(DOCKAUV_EINVAL, "null argument");
+    if (!h->ev_valid) return fail(DOCKAUV_ESTATE, "no timed step recorded (dockauv_enable_timing + dockauv_step first)");
+    DeviceGuard guard(h->device);
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    const int n = h->n_marks > 0 ? h->n_marks - 1 : 0;
+    *n_launches = n;
+    for (int k = 0; k < n && k < capacity; k++) CUDA_TRY(cudaEventElapsedTime(&ms[k], h->marks[k], h->marks[k + 1]));
     return DOCKAUV_OK;
 }
 

@@ -7,12 +7,13 @@
 namespace dockauv {
 
 template <typename T, int VEH, int NU>
-static cudaError_t launch_variant(const KParams<T> &k, int layout, cudaStream_t st) {
+static cudaError_t launch_variant(const KParams<T> &k, int layout, cudaStream_t st, cudaEvent_t *marks, int *n_marks) {
     const int64_t n = k.env_end - k.env_begin;
+    if (n_marks) *n_marks = 0;
     if (n <= 0) return cudaSuccess;
     if (layout == DOCKAUV_LAYOUT_WARP_RAYS) return launch_step_warp<T, VEH, NU>(k, st);
     if (layout == DOCKAUV_LAYOUT_SPLIT) return launch_step_split<T, VEH, NU>(k, k.split_chunk, st);
-    if (layout == DOCKAUV_LAYOUT_PIPELINE) return launch_step_pipe<T, VEH, NU>(k, st);
+    if (layout == DOCKAUV_LAYOUT_PIPELINE) return launch_step_pipe<T, VEH, NU>(k, st, marks, n_marks);
     const int threads = 128;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
     step_tpe_kernel<T, VEH, NU><<<blocks, threads, 0, st>>>(k);
@@ -20,10 +21,11 @@ static cudaError_t launch_variant(const KParams<T> &k, int layout, cudaStream_t 
 }
 
 template <>
-cudaError_t launch_step<DOCKAUV_REAL>(const KParams<DOCKAUV_REAL> &k, int vehicle, int layout, cudaStream_t st) {
-    if (vehicle == DOCKAUV_VEHICLE_LAUV) return launch_variant<DOCKAUV_REAL, DOCKAUV_VEHICLE_LAUV, 3>(k, layout, st);
-    if (k.n_u == 8) return launch_variant<DOCKAUV_REAL, DOCKAUV_VEHICLE_BLUEROV2, 8>(k, layout, st);
-    return launch_variant<DOCKAUV_REAL, DOCKAUV_VEHICLE_BLUEROV2, 6>(k, layout, st);
+cudaError_t launch_step<DOCKAUV_REAL>(const KParams<DOCKAUV_REAL> &k, int vehicle, int layout, cudaStream_t st,
+                                      cudaEvent_t *marks, int *n_marks) {
+    if (vehicle == DOCKAUV_VEHICLE_LAUV) return launch_variant<DOCKAUV_REAL, DOCKAUV_VEHICLE_LAUV, 3>(k, layout, st, marks, n_marks);
+    if (k.n_u == 8) return launch_variant<DOCKAUV_REAL, DOCKAUV_VEHICLE_BLUEROV2, 8>(k, layout, st, marks, n_marks);
+    return launch_variant<DOCKAUV_REAL, DOCKAUV_VEHICLE_BLUEROV2, 6>(k, layout, st, marks, n_marks);
 }
 
 template <>

@@ -385,16 +385,36 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const __grid_con
 
 // ------------------------------------------------------------------------------------------------------- launcher
 template <typename T, int VEH, int NU>
-static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st) {
+static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEvent_t *marks = nullptr, int *n_marks = nullptr) {
     if (wants_debug(k) || k.handoff == nullptr) return launch_step_warp<T, VEH, NU>(k, st);   // no obstacles: fused kernel
+    if (k.split_chunk > 0 && k.split_chunk < k.env_end - k.env_begin && marks == nullptr) {
+        // chunked: the four launches per chunk of envs, so that a chunk's hand-off can still be in L2 when it is read
+        const int64_t chunk = ((k.split_chunk + kWarpEnvs - 1) / kWarpEnvs) * kWarpEnvs;
+        for (int64_t b = k.env_begin; b < k.env_end; b += chunk) {
+            KParams<T> kb = k;
+            kb.env_begin = b;
+            kb.env_end = b + chunk < k.env_end ? b + chunk : k.env_end;
+            kb.split_chunk = 0;
+            cudaError_t e = launch_step_pipe<T, VEH, NU>(kb, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     const int64_t n = k.env_end - k.env_begin;
     KParams<T> kc = k;
     kc.view_count = k.view_count + (k.env_begin / kWarpEnvs);   // one list counter per concurrently stepped env range
     kc.view_list = k.view_list + k.env_begin;
+    int n_mark = 0;
+    auto mark = [&]() {
+        if (marks) cudaEventRecord(marks[n_mark++], st);
+    };
+    mark();
     cudaError_t e = launch_step_warp_rpl<T, VEH, NU, 2, 1, false>(kc, st);
     if (e != cudaSuccess) return e;
+    mark();
     cull_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kc);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    mark();
     {
         const RaysSmem<T> L(k.n_rays);
         const int smem = kRayWarps * L.warp_words * (int)sizeof(T);
@@ -412,7 +432,10 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st) {
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    mark();
     finish_kernel<T><<<(unsigned)((n + kFinishThreads - 1) / kFinishThreads), kFinishThreads, 0, st>>>(kc);
+    mark();
+    if (n_marks) *n_marks = n_mark;
     return cudaGetLastError();
 }
 

@@ -340,6 +340,20 @@ class BaseDocking3d:
     def clear_stats(self):
         _capi.check(self._lib.dockauv_clear_stats(self._handle, self._stream()))
 
+    def enable_timing(self, enabled=True):
+        """CUDA-event timing of every following step (dockauv_enable_timing); read with ``last_step_ms``."""
+        _capi.check(self._lib.dockauv_enable_timing(self._handle, int(bool(enabled))))
+
+    def last_step_ms(self):
+        """(ms of the most recent timed step, [ms of each of its launches]) -- the per-launch list is empty for the
+        single-launch layouts; pipeline layout: dynamics, cull, rays, finish."""
+        ms = C.c_float()
+        _capi.check(self._lib.dockauv_last_step_ms(self._handle, C.byref(ms)))
+        per = (C.c_float * 8)()
+        n = C.c_int()
+        _capi.check(self._lib.dockauv_last_step_launch_ms(self._handle, per, 8, C.byref(n)))
+        return ms.value, [per[k] for k in range(n.value)]
+
     def launch_count(self):
         n = C.c_int64()
         _capi.check(self._lib.dockauv_launch_count(self._handle, C.byref(n)))

@@ -281,6 +281,9 @@ DOCKAUV_API int dockauv_measure_peaks(int device, double *fp64_tflops, double *f
 DOCKAUV_API int dockauv_launch_count(DockauvHandle *h, int64_t *n_launches);
 DOCKAUV_API int dockauv_enable_timing(DockauvHandle *h, int enabled);
 DOCKAUV_API int dockauv_last_step_ms(DockauvHandle *h, float *ms);
+/* Per-launch CUDA-event times (ms) of the most recent timed dockauv_step of a multi-launch layout, in launch order
+ * (DOCKAUV_LAYOUT_PIPELINE: dynamics, cull, rays, finish); *n_launches = 0 for the single-launch layouts. */
+DOCKAUV_API int dockauv_last_step_launch_ms(DockauvHandle *h, float *ms, int capacity, int *n_launches);
 
 #ifdef __cplusplus
 }
