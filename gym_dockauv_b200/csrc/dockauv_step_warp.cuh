@@ -72,6 +72,9 @@ constexpr int kHandoffWords = 22;    // pos[3] R[9] poison | reward terms r[0..7
 #ifndef DOCKAUV_MINB_A
 #define DOCKAUV_MINB_A 4
 #endif
+#ifndef DOCKAUV_A_PREFETCH
+#define DOCKAUV_A_PREFETCH 37      // CTAs ahead whose inputs the dynamics launch prefetches into L2 (0 = off)
+#endif
 #ifndef DOCKAUV_MINB_B
 #define DOCKAUV_MINB_B 4
 #endif
@@ -98,11 +101,36 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
 
     // the pipeline layout appends to a list in its second launch: the first one empties it
     if (MODE == 1 && p.view_count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *p.view_count = 0u;
+#if DOCKAUV_A_PREFETCH > 0
+    // CTAs are dispatched in blockIdx order: the inputs of a CTA a little further down the order are pulled into L2
+    // now, while this one integrates (a third of a dynamics warp's lifetime was spent waiting for its own first HBM
+    // round trip: 31 % of the launch's stall samples).  Measured: distance 8..148 CTAs 218 us, 300 235 us, 592 (one
+    // resident wave) and beyond no gain, none 253 us.  The same trick does not help the cull / finish launches.
+    if (MODE == 1) {
+        const int64_t j = i + (int64_t)DOCKAUV_A_PREFETCH * kWarpEnvs;
+        if (j < p.env_end) {
+            auto pf = [](const void *a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); };
+#pragma unroll
+            for (int c = 0; c < 12; c++) pf(p.state + (int64_t)c * N + j);
+#pragma unroll
+            for (int c = 0; c < NU; c++) pf(p.u_prev + (int64_t)c * N + j);
+#pragma unroll
+            for (int c = 0; c < 3; c++) pf(p.goal + (int64_t)c * N + j);
+            if ((lane & 3) == 0) pf((const char *)p.actions + (p.act_f32 ? 4 : 8) * NU * j);
+            if ((lane & 7) == 0) pf(p.t_steps + j);
+        }
+    }
+#endif
     // ------------------------------------------------------------------ phase A
     StepCarry<T> cy;
     if (MODE != 2 && active) {
         T spsi, cpsi, att[3];
         float obs16[16];
+#ifdef DOCKAUV_A_KSMEM
+        if (MODE == 1)    // dynamics launch of the multi-launch layouts: stage derivatives in shared memory (36 words / thread)
+            step_dynamics<T, VEH, NU, DBG, true>(p, i, cy, spsi, cpsi, obs16, att, reinterpret_cast<T *>(smem_raw) + tid, kWarpEnvs);
+        else
+#endif
         step_dynamics<T, VEH, NU, DBG>(p, i, cy, spsi, cpsi, obs16, att);
         // 0 for a finite pose, NaN otherwise: added to every ray distance so that a blown-up state poisons the
         // radar outputs exactly like the reference's NaN propagation does
@@ -426,7 +454,11 @@ template <typename T, int VEH, int NU, int RPL, int MODE, bool DBG>
 static cudaError_t launch_step_warp_rpl(const KParams<T> &k, cudaStream_t st) {
     const int64_t n = k.env_end - k.env_begin;
     const WarpSmem<T> L(k.n_rays);
+#ifdef DOCKAUV_A_KSMEM
+    const int smem = MODE == 1 ? 36 * kWarpEnvs * (int)sizeof(T) : L.total;
+#else
     const int smem = MODE == 1 ? 0 : L.total;
+#endif
     auto kern = step_warp_kernel<T, VEH, NU, RPL, MODE, DBG>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
