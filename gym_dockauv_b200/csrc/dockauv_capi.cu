@@ -250,8 +250,7 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         h->kd.stats = h->stats;
         h->kf.stats = h->stats;
     }
-    if ((p->layout == DOCKAUV_LAYOUT_SPLIT || p->layout == DOCKAUV_LAYOUT_PIPELINE || p->layout == DOCKAUV_LAYOUT_AUTO) &&
-        (p->n_capsules + p->n_spheres) > 0) {
+    if (p->layout == DOCKAUV_LAYOUT_SPLIT || p->layout == DOCKAUV_LAYOUT_PIPELINE || p->layout == DOCKAUV_LAYOUT_AUTO) {
         // hand-off between the launches of the split / pipeline layouts: T[22][N] + cond u32[N]; the pipeline adds the
         // view word u32[N], the ray list u64[N], the obstacle-avoidance sums T[N] and one list counter per 128 envs
         const size_t esz = p->precision == DOCKAUV_F64 ? 8 : 4;
@@ -261,7 +260,7 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         const size_t off_oa = off_list + 8 * n, off_cnt = off_oa + esz * n;
         const size_t n_cnt = n / 128 + 2;
         cudaError_t e5 = cudaMalloc(&h->handoff, off_cnt + 4 * n_cnt);
-        if (e5 == cudaSuccess) e5 = cudaMemset((char *)h->handoff + off_cnt, 0, 4 * n_cnt);
+        if (e5 == cudaSuccess) e5 = cudaMemset(h->handoff, 0, off_cnt + 4 * n_cnt);   // view words / counters start at 0
         if (e5 != cudaSuccess) {
             cudaFree(h->ray_tab);
             cudaFree(h->stats);
@@ -353,11 +352,10 @@ static bool scenario_has_current(int scn) {
 
 static int resolve_layout(const DockauvHandle *h) {
     int layout = h->params.layout;
-    // measured on B200 (profiles/r01/NOTES.md, 1M envs of C4): fused kernel 1.02 ms, split pair 0.82 ms, four-launch
-    // pipeline 0.70 ms; without obstacles there is no radar work to separate and the fused kernel is used;
+    // measured on B200 (profiles/r01/NOTES.md, 1M envs of C4): fused kernel 0.91 ms, split pair 0.74 ms, four-launch
+    // pipeline 0.61 ms; without obstacles the pipeline is dynamics + finish only (0.30 ms against 0.45 ms fused);
     // thread-per-env stays as the independently written cross-check
-    if (layout == DOCKAUV_LAYOUT_AUTO)
-        layout = (h->params.n_capsules + h->params.n_spheres) > 0 ? DOCKAUV_LAYOUT_PIPELINE : DOCKAUV_LAYOUT_WARP_RAYS;
+    if (layout == DOCKAUV_LAYOUT_AUTO) layout = DOCKAUV_LAYOUT_PIPELINE;
     return layout;
 }
 
@@ -409,13 +407,14 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
         e = launch_step<float>(k, h->params.vehicle, layout, st, with_marks ? h->marks : nullptr, with_marks ? &h->n_marks : nullptr);
     }
     if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
-    const bool staged = dbg == nullptr && (h->params.n_capsules + h->params.n_spheres) > 0;   // else: the fused kernel
+    const bool staged = dbg == nullptr;   // else: the fused kernel
+    const bool has_obstacles = (h->params.n_capsules + h->params.n_spheres) > 0;
     if (layout == DOCKAUV_LAYOUT_SPLIT && staged) {
         const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
         h->launches += 2 * ((end - begin + chunk - 1) / chunk);
     } else if (layout == DOCKAUV_LAYOUT_PIPELINE && staged) {
         const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
-        h->launches += 4 * ((end - begin + chunk - 1) / chunk);
+        h->launches += (has_obstacles ? 4 : 2) * ((end - begin + chunk - 1) / chunk);
     } else {
         h->launches += 1;
     }

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------------- launcher
 template <typename T, int VEH, int NU>
 static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEvent_t *marks = nullptr, int *n_marks = nullptr) {
-    if (wants_debug(k) || k.handoff == nullptr) return launch_step_warp<T, VEH, NU>(k, st);   // no obstacles: fused kernel
+    if (wants_debug(k) || k.handoff == nullptr) return launch_step_warp<T, VEH, NU>(k, st);   // debug outputs: fused kernel
     if (k.split_chunk > 0 && k.split_chunk < k.env_end - k.env_begin && marks == nullptr) {
         // chunked: the four launches per chunk of envs, so that a chunk's hand-off can still be in L2 when it is read
         const int64_t chunk = ((k.split_chunk + kWarpEnvs - 1) / kWarpEnvs) * kWarpEnvs;
@@ -412,10 +412,12 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     cudaError_t e = launch_step_warp_rpl<T, VEH, NU, 2, 1, false>(kc, st);
     if (e != cudaSuccess) return e;
     mark();
-    cull_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kc);
+    // scenarios without obstacles: no cull, no rays (the view words stay at their initial 0 = nothing in view, no collision)
+    const bool has_obstacles = k.n_caps + k.n_sph > 0;
+    if (has_obstacles) cull_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kc);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     mark();
-    {
+    if (has_obstacles) {
         const RaysSmem<T> L(k.n_rays);
         const int smem = kRayWarps * L.warp_words * (int)sizeof(T);
         int64_t blocks = (int64_t)(k.sm_count > 0 ? k.sm_count : 148) * 8;

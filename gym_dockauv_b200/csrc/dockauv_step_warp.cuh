@@ -106,7 +106,7 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
     // now, while this one integrates (a third of a dynamics warp's lifetime was spent waiting for its own first HBM
     // round trip: 31 % of the launch's stall samples).  Measured: distance 8..148 CTAs 218 us, 300 235 us, 592 (one
     // resident wave) and beyond no gain, none 253 us.  The same trick does not help the cull / finish launches.
-    if (MODE == 1) {
+    if (MODE != 2) {
         const int64_t j = i + (int64_t)DOCKAUV_A_PREFETCH * kWarpEnvs;
         if (j < p.env_end) {
             auto pf = [](const void *a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); };

@@ -13,7 +13,8 @@ for name, kw in [("ObstaclesDocking3d", dict(layout="warp_rays", n_synthetic_sph
                  ("ObstaclesDocking3d", dict(layout="split", n_synthetic_spheres=3, split_chunk_envs=1 << 20)),
                  ("ObstaclesDocking3d", dict(layout="pipeline", n_synthetic_spheres=3)),
                  ("SimpleDocking3d", dict(layout="warp_rays")),
-                 ("SimpleDocking3d", dict(layout="split", split_chunk_envs=1 << 20))]:
+                 ("SimpleDocking3d", dict(layout="split", split_chunk_envs=1 << 20)),
+                 ("SimpleDocking3d", dict(layout="pipeline"))]:
     env = envs.SCENARIOS[name](cfg, num_envs=N, seed=0, **kw)
     env.reset()
     for k in range(100):
