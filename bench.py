@@ -32,6 +32,8 @@ HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 # (FP64) from the committed `ncu --set full` capture profiles/r01/v9_pipeline_ncu_raw.csv (per launch in that file)
 NCU_TRAFFIC_BYTES_1M_F64 = 1845.9e6
 LAUNCH_NAMES = ("dynamics", "cull", "rays", "finish")
+WORKLOAD = ("C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions U(-1,1) f32, "
+            "auto-reset of finished envs")
 SCENARIO = "ObstaclesDocking3d"
 N_SYNTH_SPHERES = 3
 
@@ -138,7 +140,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions, auto-reset",
+        "config": {"workload": WORKLOAD,
                    "envs_per_step": n, "sample": f"{n} envs per step (bounded sample of the 1,048,576-env workload)"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{n} envs x {args.steps} steps, oracle/dockauv_oracle.c with OpenMP on {threads} threads"},
@@ -270,8 +272,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": "C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, "
-                                   "random actions U(-1,1) f32, in-kernel auto-reset",
+            "config": {"workload": WORKLOAD,
                        "envs_per_gpu": N, "envs_total": world * N, "layout": args.layout, "burn_in_steps": args.burn_in,
                        "rollout_steps": args.rollout, "stats_allreduces": n_reduces,
                        "l2": "working set per step ~0.9 GB per GPU >> 126 MB L2, no flush needed"},

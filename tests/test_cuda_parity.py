@@ -134,6 +134,25 @@ def _oracle_rollout(config, scenario, n, steps, seed, n_synth, dtype, layout, pr
     return out
 
 
+@pytest.mark.parametrize("layout", ["warp_rays", "split", "pipeline"])
+@pytest.mark.parametrize("radar,n_synth", [
+    (dict(alpha=60, beta=80, ray_per_deg=5, blocksize_reduce=2), 3),     # 13 x 17 = 221 rays (8 per lane), 63 pooled cells
+    (dict(alpha=70, beta=70, ray_per_deg=10, blocksize_reduce=3), 8),    # 3 x 3 pooling blocks; 13 obstacles (16-slot path)
+    (dict(alpha=60, beta=80, ray_per_deg=10, blocksize_reduce=1), 0),    # no pooling: 63 cells, n_obs = 79
+])
+def test_radar_extremes_vs_oracle(layout, radar, n_synth):
+    """Edge sizes of the radar path: close to DOCKAUV_MAX_RAYS rays, pooled grids wider than a warp, block sizes other
+    than 2 (generic pooling), more than 8 obstacles per env."""
+    from gym_dockauv_b200.config import BASE_CONFIG
+    deg = np.pi / 180
+    cfg = dict(BASE_CONFIG)
+    cfg["radar"] = dict(freq=1, alpha=radar["alpha"] * deg, beta=radar["beta"] * deg, ray_per_deg=radar["ray_per_deg"] * deg,
+                        max_dist=10, blocksize_reduce=radar["blocksize_reduce"])
+    r = _oracle_rollout(cfg, "ObstaclesDocking3d", 192, 120, seed=9, n_synth=n_synth, dtype=np.float64, layout=layout)
+    assert r["done_mismatch"] == 0
+    assert r["worst_state"] < TOL and r["worst_reward"] < TOL and r["obs_worst"] < 2e-7, r
+
+
 @pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split", "pipeline"])
 def test_random_rollout_with_autoreset_vs_oracle(layout):
     """256 envs x 300 steps of the BASELINE C4 workload (64 rays, 5 capsules + 3 spheres), auto-reset on."""
