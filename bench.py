@@ -32,6 +32,9 @@ HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 # (FP64) from the committed `ncu --set full` capture profiles/r01/v10_pipeline_ncu_raw.csv (per launch in that file)
 NCU_TRAFFIC_BYTES_1M_F64 = 1846.6e6
 LAUNCH_NAMES = ("dynamics", "cull", "rays", "finish")
+# sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active per launch, same capture (fraction of the FP64 pipe's
+# issue slots actually used -- the executed counterpart of the algorithmic `pipe.frac`)
+NCU_FP64_PIPE_BUSY = {"dynamics": 0.512, "cull": 0.473, "rays": 0.371, "finish": 0.106}
 WORKLOAD = ("C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions U(-1,1) f32, "
             "auto-reset of finished envs")
 SCENARIO = "ObstaclesDocking3d"
@@ -292,6 +295,9 @@ def run_ours(args, rank, world, local_rank):
             "pipe": {"bound": "fp64" if args.precision == "f64" else "fp32", "achieved": achieved_tf,
                      "peak": pipe_peak, "unit": "TFLOP/s", "frac": (achieved_tf / pipe_peak) if pipe_peak else None,
                      "flops_per_env_step": FLOPS_PER_ENV_STEP,
+                     "executed_pipe_busy_ncu": NCU_FP64_PIPE_BUSY if args.precision == "f64" else None,
+                     "note": "frac counts the contract's 17.7 kflop per env-step; the culls skip most ray tests, so the "
+                             "pipe itself is ~40 % busy (ncu, per launch above): the launches are latency-bound",
                      "peak_source": "dockauv_measure_peaks FMA micro-kernel on this GPU"},
             "episode_stats": {k: stats[k] for k in ("episodes", "sum_return", "sum_length", "done_collision",
                                                     "done_out_att", "env_steps")},
