@@ -554,6 +554,92 @@ __device__ __forceinline__ void obstacle_pair(const KParams<T> &p, const T pos[3
     in_view = !outside;
 }
 
+// The culls and the body-collision test of obstacle_pair in FLOAT, for the cull launch (FP64 runs at half rate and was
+// that launch's busiest pipe).  Differences of positions are formed in T and rounded once, everything after that is
+// float with explicit slack, so the result can only err on the safe side:
+//   * in_view: every threshold is widened by far more than the float rounding error (lengths 2e-3 m, axis parameter
+//     1e-3, discriminant 1e-5 relative), so "culled" here implies "culled" in exact arithmetic;
+//   * hit: 0 = clear, 1 = collision, 2 = within 2e-3 m of the threshold -- the caller decides those in T.
+template <typename T>
+__device__ __forceinline__ void cull_pair_f32(const KParams<T> &p, const T pos[3], const float Rm[9], const T ob[7],
+                                              bool is_cap, int &hit, bool &in_view) {
+    const float eps = 2e-3f;
+    const float cull = (float)p.radar_max_dist * 1.0001f + eps;
+    float rad, dist;
+    float q0[3], q1[3];
+    bool axis_out = false;
+    if (is_cap) {
+        float ba[3], oa[3], oc2[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            ba[c] = (float)(ob[3 + c] - ob[c]);
+            oa[c] = (float)(pos[c] - ob[c]);
+            oc2[c] = (float)(pos[c] - ob[3 + c]);
+        }
+        rad = (float)ob[6];
+        const float baba = ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2];
+        const float baoa = oa[0] * ba[0] + oa[1] * ba[1] + oa[2] * ba[2];
+        const float oaoa = oa[0] * oa[0] + oa[1] * oa[1] + oa[2] * oa[2];
+        const float inv_n = rsqrtf(baba);
+        const float sp = -baoa * inv_n;
+        const float tp = (oc2[0] * ba[0] + oc2[1] * ba[1] + oc2[2] * ba[2]) * inv_n;
+        float hh = sp;
+        if (tp > hh || tp != tp) hh = tp;
+        if (0.0f > hh) hh = 0.0f;
+        float cr[3];
+        cross3(oa, ba, cr);
+        const float inv_baba = inv_n * inv_n;
+        const float perp2 = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * inv_baba;
+        dist = sqrtf(hh * hh + perp2);
+        const float Rr = cull + rad;
+        const float t1 = baoa * baoa, t2 = baba * (oaoa - Rr * Rr);
+        const float D = t1 - t2, tolD = 1e-5f * (t1 + fabsf(t2));
+        axis_out = D < -tolD;
+        const float sq = sqrtf(fmaxf(D, 0.0f) + tolD);
+        float s_lo = (baoa - sq) * inv_baba - 1e-3f, s_hi = (baoa + sq) * inv_baba + 1e-3f;
+        s_lo = s_lo > 0.0f ? s_lo : 0.0f;
+        s_hi = s_hi < 1.0f ? s_hi : 1.0f;
+        axis_out |= s_lo > s_hi;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            q0[c] = s_lo * ba[c] - oa[c];
+            q1[c] = s_hi * ba[c] - oa[c];
+        }
+    } else {
+        float d2 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float oc = (float)(pos[c] - ob[c]);
+            d2 += oc * oc;
+            q0[c] = q1[c] = -oc;
+        }
+        rad = (float)ob[3];
+        dist = sqrtf(d2);
+    }
+    const float thr = rad + (float)p.safety_radius;
+    hit = (dist <= thr - eps) ? 1 : ((dist > thr + eps) ? 0 : 2);        // NaN -> 2
+    bool outside = (dist - rad > cull) || axis_out;
+    {
+        float a0[3], a1[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            a0[c] = Rm[c] * q0[0] + Rm[3 + c] * q0[1] + Rm[6 + c] * q0[2];
+            a1[c] = Rm[c] * q1[0] + Rm[3 + c] * q1[1] + Rm[6 + c] * q1[2];
+        }
+        // same half-space tests as obstacle_pair; the float error of a signed distance (~1e-6 * 60 m) and of the
+        // converted plane slopes (~6e-8 * 40 m) is far inside the eps added to the radius
+        const float rm = rad * 1.0001f + eps;
+        const float ty = (float)p.fov_ty, tz = (float)p.fov_tz;
+        const float ry = rm * (float)p.fov_ny, rz = rm * (float)p.fov_nz;
+        outside |= (a0[0] < -rm) && (a1[0] < -rm);
+        outside |= (a0[1] - ty * a0[0] > ry) && (a1[1] - ty * a1[0] > ry);
+        outside |= (-a0[1] - ty * a0[0] > ry) && (-a1[1] - ty * a1[0] > ry);
+        outside |= (a0[2] - tz * a0[0] > rz) && (a1[2] - tz * a1[0] > rz);
+        outside |= (-a0[2] - tz * a0[0] > rz) && (-a1[2] - tz * a1[0] > rz);
+    }
+    in_view = !outside;
+}
+
 // shape.py:341-390 for one ray: infinite-cylinder root, body hit if 0 < y < baba, else end-cap sphere.
 // Returns -inf for "no intersection" and a negative distance for "behind" exactly like the reference.
 template <typename T>

@@ -3,8 +3,9 @@
 //   1. dynamics   step_warp_kernel<MODE 1> (dockauv_step_warp.cuh): thread per env, writes the post-step pose and the
 //                 radar-independent reward terms to the hand-off buffer.
 //   2. cull       cull_kernel: thread per env.  Walks over the env's obstacles (coalesced SoA loads), does the body
-//                 collision test and the exact range / field-of-view culls, and appends the envs that have anything in
-//                 view (28 % of them on the C4 workload) to a compact list.
+//                 collision test and the range / field-of-view culls -- in float with conservative slack, the collision
+//                 re-decided in T when it is within 2 mm of the threshold (cull_pair_f32) -- and appends the envs that
+//                 have anything in view (28 % of them on the C4 workload) to a compact list.
 //   3. rays       rays_kernel: persistent grid, one warp per LISTED env (lanes = rays), data of the next list entry
 //                 prefetched while the current one is cast.  Writes the pooled ray cells of the observation row and the
 //                 obstacle-avoidance sum.
@@ -23,6 +24,9 @@ namespace dockauv {
 
 #ifndef DOCKAUV_MINB_CULL
 #define DOCKAUV_MINB_CULL 4
+#endif
+#ifndef DOCKAUV_CULL_F32
+#define DOCKAUV_CULL_F32 1        // culls + collision pre-test of the cull launch in float with conservative slack (0 = all in T)
 #endif
 #ifndef DOCKAUV_MINB_RAYS
 #define DOCKAUV_MINB_RAYS 4
@@ -47,6 +51,11 @@ __global__ void __launch_bounds__(256, DOCKAUV_MINB_CULL) cull_kernel(const __gr
 #pragma unroll
         for (int c = 0; c < 9; c++) Rm[c] = hf[(int64_t)(3 + c) * N];
         const T poison = hf[(int64_t)12 * N];
+#if DOCKAUV_CULL_F32
+        float Rf[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) Rf[c] = (float)Rm[c];
+#endif
         const int n_caps = p.n_caps, n_sph = p.n_sph;
         // next obstacle's words are requested before the current one is evaluated
         T ob[7], nx[7];
@@ -71,7 +80,18 @@ __global__ void __launch_bounds__(256, DOCKAUV_MINB_CULL) cull_kernel(const __gr
             for (int c = 0; c < 7; c++) ob[c] = nx[c];
             load(k + 1, nx);
             bool hit, view;
+#if DOCKAUV_CULL_F32
+            // float fast path (conservative culls, collision decided unless within 2 mm of the threshold)
+            int hit3;
+            cull_pair_f32<T>(p, pos, Rf, ob, k < n_caps, hit3, view);
+            hit = hit3 == 1;
+            if (hit3 == 2) {
+                bool view64;
+                obstacle_pair<T, false>(p, pos, Rm, ob, k < n_caps, nullptr, hit, view64);
+            }
+#else
             obstacle_pair<T, false>(p, pos, Rm, ob, k < n_caps, nullptr, hit, view);
+#endif
             info |= view ? (1u << k) : 0u;
             info |= hit ? kViewCollision : 0u;
         }
