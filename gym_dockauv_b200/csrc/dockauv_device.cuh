@@ -554,6 +554,9 @@ __device__ __forceinline__ void obstacle_pair(const KParams<T> &p, const T pos[3
     in_view = !outside;
 }
 
+#ifndef DOCKAUV_CULL_CLIP
+#define DOCKAUV_CULL_CLIP 1
+#endif
 // The culls and the body-collision test of obstacle_pair in FLOAT, for the cull launch (FP64 runs at half rate and was
 // that launch's busiest pipe).  Differences of positions are formed in T and rounded once, everything after that is
 // float with explicit slack, so the result can only err on the safe side:
@@ -631,11 +634,36 @@ __device__ __forceinline__ void cull_pair_f32(const KParams<T> &p, const T pos[3
         const float rm = rad * 1.0001f + eps;
         const float ty = (float)p.fov_ty, tz = (float)p.fov_tz;
         const float ry = rm * (float)p.fov_ny, rz = rm * (float)p.fov_nz;
+#if DOCKAUV_CULL_CLIP
+        // an axis point can carry a surface point inside the pyramid only if it is within r of the inner side of ALL
+        // five planes; each signed distance is linear along the axis, so each plane keeps an interval of the segment
+        // parameter and the obstacle is out of view when their intersection is empty (this also catches segments that
+        // leave the pyramid through different planes).  Crossing parameters widened by 1e-3.
+        float t_lo = 0.0f, t_hi = 1.0f;
+        bool empty = false;
+        auto clip = [&](float g0, float g1) {            // keep { t : g0 + t (g1 - g0) <= 0 }
+            const bool o0 = g0 > 0.0f, o1 = g1 > 0.0f;
+            empty |= o0 && o1;
+            if (o0 != o1) {
+                float ts = __fdividef(g0, g0 - g1);
+                ts = fminf(fmaxf(ts, 0.0f), 1.0f);       // NaN -> 0
+                if (o0) t_lo = fmaxf(t_lo, ts - 1e-3f);
+                else t_hi = fminf(t_hi, ts + 1e-3f);
+            }
+        };
+        clip(-a0[0] - rm, -a1[0] - rm);
+        clip(a0[1] - ty * a0[0] - ry, a1[1] - ty * a1[0] - ry);
+        clip(-a0[1] - ty * a0[0] - ry, -a1[1] - ty * a1[0] - ry);
+        clip(a0[2] - tz * a0[0] - rz, a1[2] - tz * a1[0] - rz);
+        clip(-a0[2] - tz * a0[0] - rz, -a1[2] - tz * a1[0] - rz);
+        outside |= empty || (t_lo > t_hi);
+#else
         outside |= (a0[0] < -rm) && (a1[0] < -rm);
         outside |= (a0[1] - ty * a0[0] > ry) && (a1[1] - ty * a1[0] > ry);
         outside |= (-a0[1] - ty * a0[0] > ry) && (-a1[1] - ty * a1[0] > ry);
         outside |= (a0[2] - tz * a0[0] > rz) && (a1[2] - tz * a1[0] > rz);
         outside |= (-a0[2] - tz * a0[0] > rz) && (-a1[2] - tz * a1[0] > rz);
+#endif
     }
     in_view = !outside;
 }
