@@ -160,11 +160,7 @@ static void fill_kparams(const DockauvParams &s, int64_t n_envs, KParams<T> &k) 
     k.has_noise = s.cur_sigma > 0.0;
     k.radar_max_dist = (T)s.radar_max_dist;
     double sb = 0.0;
-    for (int i = 0; i < s.n_rays; i++) {
-        for (int c = 0; c < 3; c++) k.rd_b[3 * i + c] = (T)s.rd_b[3 * i + c];
-        k.beta_oa[i] = (T)s.beta_oa[i];
-        sb += s.beta_oa[i];
-    }
+    for (int i = 0; i < s.n_rays; i++) sb += s.beta_oa[i];
     k.sum_beta_oa = (T)sb;
     // bounding pyramid of the ray fan (used by the warp layout's field-of-view cull); a ray with x <= 0 disables it
     double ty = 0.0, tz = 0.0;

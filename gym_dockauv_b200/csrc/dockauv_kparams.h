@@ -1,5 +1,5 @@
 // dockauv_kparams.h -- device-side parameter block (passed by value as a __grid_constant__ kernel argument, so
-// every field sits in the constant bank and uniform reads broadcast to the whole warp).
+// every field sits in the constant bank and uniform reads broadcast to the whole warp); ~2.7 KB.
 #pragma once
 #include <stdint.h>
 
@@ -68,11 +68,9 @@ struct KParams {
     int32_t sm_count;
     // stats accumulator (double[DOCKAUV_N_STATS])
     double *stats;
-    // ray table in global memory (lane-indexed reads in the warp layout): rd_b[3][n_rays], beta_oa[n_rays]
+    // ray table in global memory (handle-owned): rd_b[3][n_rays] then beta_oa[n_rays].  It is not part of this block:
+    // the block travels with every launch, and 8 KB of ray table made it 11 KB
     const T *ray_tab;
-    // ray table in the constant bank (uniform reads in the thread-per-env layout)
-    T rd_b[DOCKAUV_MAX_RAYS * 3];
-    T beta_oa[DOCKAUV_MAX_RAYS];
 };
 
 }  // namespace dockauv

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(128) step_tpe_kernel(const __grid_constant__ K
         for (int ir = 0; ir < n_r; ir++) {
             T d = dmax;
             if (any_obstacle) {
-                const T *b = p.rd_b + 3 * ir;
+                const T b[3] = {p.ray_tab[ir], p.ray_tab[n_r + ir], p.ray_tab[2 * n_r + ir]};   // uniform loads
                 T rd[3];
 #pragma unroll
                 for (int c = 0; c < 3; c++) rd[c] = cy.R[3 * c] * b[0] + cy.R[3 * c + 1] * b[1] + cy.R[3 * c + 2] * b[2];
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(128) step_tpe_kernel(const __grid_constant__ K
             T c = clipv(T(1) - d / dmax, T(0), T(1));
             T q = (T(1) - c) * (T(1) - c);
             T mx = (q != q) ? q : (q > T(0.001) ? q : T(0.001));
-            oa_dot += mx * p.beta_oa[ir];
+            oa_dot += mx * p.ray_tab[3 * n_r + ir];
         }
         T r_oa = p.sum_beta_oa / oa_dot - T(1);
 
