@@ -5,8 +5,8 @@ BlueROV2, 64-ray radar, 5 capsules + 3 spheres -- config C4: 1,048,576 envs per 
     python bench.py [--gpus N] [--steps K] [--warmup W]             # our arm (CUDA, through the C ABI)
     python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU arm: the oracle port on host cores
 
-One "step" = one batched env.step() over every env of the rank (default layout with obstacles: four launches --
-dynamics, cull, rays, finish).  Rank 0 prints ONE JSON line.
+One "step" = one batched env.step() over every env of the rank (default layout: four launches -- dynamics, cull, rays,
+finish -- for each half of the batch, the halves on two streams).  Rank 0 prints ONE JSON line.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The per-step
 working set (~0.9 GB at 1M envs) is far larger than L2 (126 MB), so no explicit L2 flush is needed (stated in
 config.l2).  Actions are synthetic i.i.d. U(-1,1) float32, pre-generated on the device for `value`; the `e2e`

@@ -472,6 +472,15 @@ static int step_parts(DockauvHandle *h, const void *actions, int action_dtype, c
     return DOCKAUV_OK;
 }
 
+// one batched step on the device: in parts for large batches of the pipeline layout, else one launch group
+static int step_device(DockauvHandle *h, const void *actions, int action_dtype, const void *noise,
+                       const DockauvStepOut *out, const DockauvDebugOut *dbg, int auto_reset, cudaStream_t st, bool timing) {
+    if (DOCKAUV_STEP_PARTS > 1 && !timing && dbg == nullptr && h->n_envs >= (int64_t)1 << 19 &&
+        resolve_layout(h) == DOCKAUV_LAYOUT_PIPELINE && h->params.split_chunk_envs == 0)
+        return step_parts(h, actions, action_dtype, noise, out, auto_reset, st);
+    return step_range(h, actions, action_dtype, noise, out, dbg, auto_reset, 0, h->n_envs, st, timing);
+}
+
 extern "C" int dockauv_step(DockauvHandle *h, const void *actions_dev, int action_dtype, const void *noise_dev,
                             const DockauvStepOut *out, const DockauvDebugOut *dbg, int auto_reset, void *stream) {
     if (!h || !actions_dev || !out) return fail(DOCKAUV_EINVAL, "null argument");
@@ -488,12 +497,7 @@ extern "C" int dockauv_step(DockauvHandle *h, const void *actions_dev, int actio
         }
         CUDA_TRY(cudaEventRecord(h->ev0, st));
     }
-    int rc;
-    if (DOCKAUV_STEP_PARTS > 1 && !h->timing && dbg == nullptr && h->n_envs >= (int64_t)1 << 19 &&
-        resolve_layout(h) == DOCKAUV_LAYOUT_PIPELINE && h->params.split_chunk_envs == 0)
-        rc = step_parts(h, actions_dev, action_dtype, noise_dev, out, auto_reset, st);
-    else
-        rc = step_range(h, actions_dev, action_dtype, noise_dev, out, dbg, auto_reset, 0, h->n_envs, st, h->timing);
+    int rc = step_device(h, actions_dev, action_dtype, noise_dev, out, dbg, auto_reset, st, h->timing);
     if (rc != DOCKAUV_OK) return rc;
     if (h->timing) {
         CUDA_TRY(cudaEventRecord(h->ev1, st));
@@ -603,7 +607,7 @@ static int rollout_issue(DockauvHandle *h, const void *actions, int action_dtype
         so.terminal_obs = o.terminal_obs ? o.terminal_obs + orow * t : nullptr;
         so.ep_return_out = o.ep_return_out ? (char *)o.ep_return_out + esz * (size_t)N * t : nullptr;
         so.ep_len_out = o.ep_len_out ? o.ep_len_out + (size_t)N * t : nullptr;
-        int rc = step_range(h, (const char *)actions + arow * t, action_dtype, nullptr, &so, nullptr, auto_reset, 0, N, st);
+        int rc = step_device(h, (const char *)actions + arow * t, action_dtype, nullptr, &so, nullptr, auto_reset, st, false);
         if (rc != DOCKAUV_OK) return rc;
     }
     return DOCKAUV_OK;

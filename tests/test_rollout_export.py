@@ -20,11 +20,11 @@ def _cfg64():
     return cfg
 
 
+@pytest.mark.parametrize("N,T", [(4096, 24), (1 << 19, 5)])     # the large batch is stepped in two parts on two streams
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_rollout_equals_individual_steps(use_graph):
+def test_rollout_equals_individual_steps(use_graph, N, T):
     import torch
     from gym_dockauv_b200 import envs
-    N, T = 4096, 24
     kw = dict(num_envs=N, seed=3, n_synthetic_spheres=3)
     a = torch.rand(T, N, 6, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0)) * 2 - 1
     e1 = envs.ObstaclesDocking3d(_cfg64(), **kw)
