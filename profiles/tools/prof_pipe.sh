@@ -1,5 +1,5 @@
-# full ncu capture of one steady-state launch of each kernel of the pipeline layout (C4): gpurun_out/prof_pipe_$TAG.ncu-rep
+# full ncu capture of one steady-state step of the pipeline layout (C4, two halves x four launches): gpurun_out/prof_pipe_$TAG.ncu-rep
 TAG=${TAG:-cur}
 mkdir -p gpurun_out
 python profiles/tools/run_scenario.py ObstaclesDocking3d pipeline 3 135 || exit 1
-ncu --set full --clock-control none --import-source on -k "regex:step_warp|cull_kernel|rays_kernel|finish_kernel" --launch-skip 528 --launch-count 4 -f -o gpurun_out/prof_pipe_$TAG python profiles/tools/run_scenario.py ObstaclesDocking3d pipeline 3 135 > gpurun_out/prof_pipe_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:step_warp|cull_kernel|rays_kernel|finish_kernel" --launch-skip 1056 --launch-count 8 -f -o gpurun_out/prof_pipe_$TAG python profiles/tools/run_scenario.py ObstaclesDocking3d pipeline 3 135 > gpurun_out/prof_pipe_$TAG.log 2>&1
