@@ -346,86 +346,61 @@ __device__ __forceinline__ void stage_trig(const T tr0[6], const T d[3], T tr[6]
     if (WPSI) sincos_shift<T>(tr0[4], tr0[5], d[2], &tr[4], &tr[5]);
 }
 
-// Storage of the stage derivatives k1..k4 (k5 is consumed at once): registers, or this thread's column of a shared-memory
-// block (word (j, i) at base[(9 j + i) * stride], stride = threads per CTA: conflict-free).  The dynamics launch of the
-// multi-launch layouts uses the shared form: 72 registers less to spill.
-template <typename T, bool SMEM>
-struct KStore;
-template <typename T>
-struct KStore<T, false> {
-    T k[4][9];
-    __device__ __forceinline__ KStore(T *, int) {}
-    __device__ __forceinline__ T get(int j, int i) const { return k[j][i]; }
-    __device__ __forceinline__ void set(int j, int i, T v) { k[j][i] = v; }
-};
-template <typename T>
-struct KStore<T, true> {
-    T *base;
-    int stride;
-    __device__ __forceinline__ KStore(T *b, int s) : base(b), stride(s) {}
-    __device__ __forceinline__ T get(int j, int i) const { return base[(9 * j + i) * stride]; }
-    __device__ __forceinline__ void set(int j, int i, T v) { base[(9 * j + i) * stride] = v; }
-};
-
 // utils/odesolver45.py:18-26 on the reduced state; the 4th-order result is written back to pos / y.
 //   tr0: sin/cos of the pre-step attitude y[0:3]; tr1 (out): sin/cos of the post-step attitude (before ssa, which
 //   does not change them).
-template <typename T, int VEH, bool SMEM>
+template <typename T, int VEH>
 __device__ __forceinline__ void rkf45_step(const KParams<T> &p, T pos[3], T y[9], const T tr0[6], const T tau[6],
-                                           const T nu_c[3], T tr1[6], KStore<T, SMEM> &ks) {
+                                           const T nu_c[3], T tr1[6]) {
     const T h = p.h;
-    T kc[9], yt[9], dy[9], tr[6];
+    T k1[9], k2[9], k3[9], k4[9], k5[9], yt[9], dy[9], tr[6];
     T pacc[3] = {T(0), T(0), T(0)};
-    rhs9<T, VEH, true>(p, y, tr0, tau, nu_c, h * T(25.0 / 216.0), pacc, kc);
+    rhs9<T, VEH, true>(p, y, tr0, tau, nu_c, h * T(25.0 / 216.0), pacc, k1);
     {
         const T a = h * T(0.25);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            ks.set(0, i, kc[i]);
-            dy[i] = a * kc[i];
+            dy[i] = a * k1[i];
             yt[i] = y[i] + dy[i];
         }
     }
     stage_trig<T, false>(tr0, dy, tr);
-    rhs9<T, VEH, false>(p, yt, tr, tau, nu_c, T(0), pacc, kc);   // b2 = 0: no position contribution
+    rhs9<T, VEH, false>(p, yt, tr, tau, nu_c, T(0), pacc, k2);   // b2 = 0: no position contribution
     {
         const T a = h * T(3.0 / 32.0), b = h * T(9.0 / 32.0);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            ks.set(1, i, kc[i]);
-            dy[i] = a * ks.get(0, i) + b * kc[i];
+            dy[i] = a * k1[i] + b * k2[i];
             yt[i] = y[i] + dy[i];
         }
     }
     stage_trig<T, true>(tr0, dy, tr);
-    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(1408.0 / 2565.0), pacc, kc);
+    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(1408.0 / 2565.0), pacc, k3);
     {
         const T a = h * T(1932.0 / 2197.0), b = h * T(-7200.0 / 2197.0), c = h * T(7296.0 / 2197.0);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            ks.set(2, i, kc[i]);
-            dy[i] = a * ks.get(0, i) + b * ks.get(1, i) + c * kc[i];
+            dy[i] = a * k1[i] + b * k2[i] + c * k3[i];
             yt[i] = y[i] + dy[i];
         }
     }
     stage_trig<T, true>(tr0, dy, tr);
-    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(2197.0 / 4104.0), pacc, kc);
+    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(2197.0 / 4104.0), pacc, k4);
     {
         const T a = h * T(439.0 / 216.0), b = h * T(-8.0), c = h * T(3680.0 / 513.0), d = h * T(-845.0 / 4104.0);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            ks.set(3, i, kc[i]);
-            dy[i] = a * ks.get(0, i) + b * ks.get(1, i) + c * ks.get(2, i) + d * kc[i];
+            dy[i] = a * k1[i] + b * k2[i] + c * k3[i] + d * k4[i];
             yt[i] = y[i] + dy[i];
         }
     }
     stage_trig<T, true>(tr0, dy, tr);
-    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(-1.0 / 5.0), pacc, kc);
+    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(-1.0 / 5.0), pacc, k5);
     {
         const T a = h * T(25.0 / 216.0), c = h * T(1408.0 / 2565.0), d = h * T(2197.0 / 4104.0), e = h * T(-1.0 / 5.0);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            dy[i] = a * ks.get(0, i) + c * ks.get(2, i) + d * ks.get(3, i) + e * kc[i];
+            dy[i] = a * k1[i] + c * k3[i] + d * k4[i] + e * k5[i];
             y[i] = y[i] + dy[i];
         }
     }

@@ -10,10 +10,9 @@ namespace dockauv {
 // Dynamics + everything that does not need the radar.  Shared by both layouts.
 //   returns false for an env index beyond the batch.
 //   DBG: compile the optional debug outputs in (parity tests); the throughput kernels are built without them.
-//   KSMEM: RK stage derivatives in shared memory (sk = this thread's column, sk_stride = threads per CTA).
-template <typename T, int VEH, int NU, bool DBG, bool KSMEM = false>
+template <typename T, int VEH, int NU, bool DBG>
 __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T &spsi_out, T &cpsi_out,
-                                              float obs16[16], T att_out[3], T *sk = nullptr, int sk_stride = 0) {
+                                              float obs16[16], T att_out[3]) {
     const int64_t N = p.n_envs;
     T pos[3], y[9];
 #pragma unroll
@@ -81,10 +80,7 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
 
     // ---- integrate (auvsim.py:89-108)
     T tr1[6];
-    {
-        KStore<T, KSMEM> ks(sk, sk_stride);
-        rkf45_step<T, VEH, KSMEM>(p, pos, y, tr0, tau, nu_c, tr1, ks);
-    }
+    rkf45_step<T, VEH>(p, pos, y, tr0, tau, nu_c, tr1);
 #pragma unroll
     for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
 #pragma unroll

@@ -126,11 +126,6 @@ step_warp_kernel(const __grid_constant__ KParams<T> p) {
     if (MODE != 2 && active) {
         T spsi, cpsi, att[3];
         float obs16[16];
-#ifdef DOCKAUV_A_KSMEM
-        if (MODE == 1)    // dynamics launch of the multi-launch layouts: stage derivatives in shared memory (36 words / thread)
-            step_dynamics<T, VEH, NU, DBG, true>(p, i, cy, spsi, cpsi, obs16, att, reinterpret_cast<T *>(smem_raw) + tid, kWarpEnvs);
-        else
-#endif
         step_dynamics<T, VEH, NU, DBG>(p, i, cy, spsi, cpsi, obs16, att);
         // 0 for a finite pose, NaN otherwise: added to every ray distance so that a blown-up state poisons the
         // radar outputs exactly like the reference's NaN propagation does
@@ -454,11 +449,7 @@ template <typename T, int VEH, int NU, int RPL, int MODE, bool DBG>
 static cudaError_t launch_step_warp_rpl(const KParams<T> &k, cudaStream_t st) {
     const int64_t n = k.env_end - k.env_begin;
     const WarpSmem<T> L(k.n_rays);
-#ifdef DOCKAUV_A_KSMEM
-    const int smem = MODE == 1 ? 36 * kWarpEnvs * (int)sizeof(T) : L.total;
-#else
     const int smem = MODE == 1 ? 0 : L.total;
-#endif
     auto kern = step_warp_kernel<T, VEH, NU, RPL, MODE, DBG>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
