@@ -25,15 +25,9 @@ namespace dockauv {
 #ifndef DOCKAUV_MINB_CULL
 #define DOCKAUV_MINB_CULL 4
 #endif
-#ifndef DOCKAUV_CULL_F32
-#define DOCKAUV_CULL_F32 1        // culls + collision pre-test of the cull launch in float with conservative slack (0 = all in T)
-#endif
 #ifndef DOCKAUV_MINB_RAYS
 #define DOCKAUV_MINB_RAYS 4
 #endif
-
-constexpr uint32_t kViewCollision = 1u << 16;   // view_info bits: 0..15 in-view mask (capsules first), 16 collision,
-constexpr uint32_t kViewListed = 1u << 17;      // 17 the env is on the ray list
 
 // ------------------------------------------------------------------------------------------------------- 2. cull
 template <typename T>
@@ -41,83 +35,16 @@ __global__ void __launch_bounds__(256, DOCKAUV_MINB_CULL) cull_kernel(const __gr
     const int64_t N = p.n_envs;
     const int64_t i = p.env_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < p.env_end;
-    bool listed = false;
-    uint32_t info = 0;
+    T pos[3] = {T(0), T(0), T(0)}, Rm[9] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)}, poison = T(0);
     if (active) {
         const T *hf = p.handoff + i;
-        T pos[3], Rm[9];
 #pragma unroll
         for (int c = 0; c < 3; c++) pos[c] = hf[(int64_t)c * N];
 #pragma unroll
         for (int c = 0; c < 9; c++) Rm[c] = hf[(int64_t)(3 + c) * N];
-        const T poison = hf[(int64_t)12 * N];
-#if DOCKAUV_CULL_F32
-        float Rf[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) Rf[c] = (float)Rm[c];
-#endif
-        const int n_caps = p.n_caps, n_sph = p.n_sph;
-        // next obstacle's words are requested before the current one is evaluated
-        T ob[7], nx[7];
-#pragma unroll
-        for (int c = 0; c < 7; c++) nx[c] = T(0);
-        const int n_obst = n_caps + n_sph;
-        auto load = [&](int k, T o[7]) {
-            if (k < n_caps) {
-                const T *g = p.capsules + (int64_t)(k * 7) * N + i;
-#pragma unroll
-                for (int c = 0; c < 7; c++) o[c] = g[(int64_t)c * N];
-            } else if (k < n_obst) {
-                const T *g = p.spheres + (int64_t)((k - n_caps) * 4) * N + i;
-#pragma unroll
-                for (int c = 0; c < 4; c++) o[c] = g[(int64_t)c * N];
-            }
-        };
-        load(0, nx);
-#pragma unroll 1
-        for (int k = 0; k < n_obst; k++) {
-#pragma unroll
-            for (int c = 0; c < 7; c++) ob[c] = nx[c];
-            load(k + 1, nx);
-            bool hit, view;
-#if DOCKAUV_CULL_F32
-            // float fast path (conservative culls, collision decided unless within 2 mm of the threshold)
-            int hit3;
-            cull_pair_f32<T>(p, pos, Rf, ob, k < n_caps, hit3, view);
-            hit = hit3 == 1;
-            if (hit3 == 2) {
-                bool view64;
-                obstacle_pair<T, false>(p, pos, Rm, ob, k < n_caps, nullptr, hit, view64);
-            }
-#else
-            obstacle_pair<T, false>(p, pos, Rm, ob, k < n_caps, nullptr, hit, view);
-#endif
-            info |= view ? (1u << k) : 0u;
-            info |= hit ? kViewCollision : 0u;
-        }
-        // a non-finite pose poisons the rays like the reference's NaN propagation: such envs go through the ray launch
-        listed = (info & 0xffffu) != 0u || !(poison == T(0));
-        if (listed) info |= kViewListed;
-        p.view_info[i] = info;
+        poison = hf[(int64_t)12 * N];
     }
-#ifdef DOCKAUV_VIEW_STATS   // tuning builds: in-view (env, obstacle) pairs and listed envs -> stats[11], [12]
-    if (active) {
-        atomicAdd(&p.stats[11], (double)__popc(info & 0xffffu));
-        atomicAdd(&p.stats[12], listed ? 1.0 : 0.0);
-    }
-#endif
-    // warp-aggregated append: one atomic per warp
-    const unsigned lm = __ballot_sync(0xffffffffu, listed);
-    if (lm) {
-        const int lane = threadIdx.x & 31;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(p.view_count, (unsigned)__popc(lm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (listed) {
-            const unsigned k = base + __popc(lm & ((1u << lane) - 1u));
-            p.view_list[k] = (unsigned long long)(uint32_t)(i - p.env_begin) | ((unsigned long long)(info & 0xffffu) << 32);
-        }
-    }
+    cull_env<T>(p, i, active, pos, Rm, poison);
 }
 
 // ------------------------------------------------------------------------------------------------------- 3. rays
@@ -429,11 +356,11 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
         if (marks) cudaEventRecord(marks[n_mark++], st);
     };
     mark();
+    // scenarios without obstacles: no cull, no rays (the view words stay at their initial 0 = nothing in view, no collision)
+    const bool has_obstacles = k.n_caps + k.n_sph > 0;
     cudaError_t e = launch_step_warp_rpl<T, VEH, NU, 2, 1, false>(kc, st);
     if (e != cudaSuccess) return e;
     mark();
-    // scenarios without obstacles: no cull, no rays (the view words stay at their initial 0 = nothing in view, no collision)
-    const bool has_obstacles = k.n_caps + k.n_sph > 0;
     if (has_obstacles) cull_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kc);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     mark();

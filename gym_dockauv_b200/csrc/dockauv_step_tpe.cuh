@@ -3,7 +3,7 @@
 // reads); per-env capsule pre-computations live in a small local array.  This is the simple layout used for
 // scenarios without obstacles (BASELINE config C2) and as the cross-check of the warp-cooperative radar layout.
 #pragma once
-#include "dockauv_env.cuh"
+#include "dockauv_cull.cuh"
 
 namespace dockauv {
 
