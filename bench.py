@@ -29,12 +29,12 @@ BYTES_PER_ENV_STEP = 898      # algorithmic HBM bytes per env-st
 FLOPS_PER_ENV_STEP = 17700    # algorithmic flops per env-step for C4
 HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum of the eight launches (two halves x four) of ONE step over 1,048,576 envs
-# (FP64) from the committed `ncu --set full` capture profiles/r01/v12_pipeline_ncu_raw.csv (per launch in that file)
-NCU_TRAFFIC_BYTES_1M_F64 = 1762.5e6
+# (FP64) from the committed `ncu --set full` capture profiles/r01/v13_pipeline_ncu_raw.csv (per launch in that file)
+NCU_TRAFFIC_BYTES_1M_F64 = 1756.4e6
 LAUNCH_NAMES = ("dynamics", "cull", "rays", "finish")
 # sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active per launch, same capture (fraction of the FP64 pipe's
 # issue slots actually used -- the executed counterpart of the algorithmic `pipe.frac`)
-NCU_FP64_PIPE_BUSY = {"dynamics": 0.485, "cull": 0.031, "rays": 0.366, "finish": 0.104}
+NCU_FP64_PIPE_BUSY = {"dynamics": 0.496, "cull": 0.031, "rays": 0.367, "finish": 0.105}
 WORKLOAD = ("C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions U(-1,1) f32, "
             "auto-reset of finished envs")
 SCENARIO = "ObstaclesDocking3d"
@@ -286,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak,
                          "traffic": NCU_TRAFFIC_BYTES_1M_F64 if (N == 1 << 20 and args.precision == "f64") else None,
-                         "traffic_source": "profiles/r01/v12_pipeline_ncu_raw.csv (bytes per step = sum of its eight launches)",
+                         "traffic_source": "profiles/r01/v13_pipeline_ncu_raw.csv (bytes per step = sum of its eight launches)",
                          "peak_source": hbm_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kern_ms,
                          "launches_ms": {n: float(v) for n, v in zip(LAUNCH_NAMES, launch_ms)},

@@ -139,25 +139,24 @@ __device__ __forceinline__ T ssa(T x) {
 // |d| <= 0.5 sin d and cos d - 1 are short Taylor polynomials (truncation < 5e-17 relative) instead of a library
 // sincos (~150 instructions with its range reduction); larger shifts and NaN / inf take the library call.
 // The result differs from sincos(a + d) by ~1 ulp, three orders of magnitude inside the 1e-9 budget.
+// Taylor coefficients of sin d / d - 1 and cos d - 1 in d^2, in constant memory: a 64-bit literal costs two UMOVs in
+// front of every DFMA that uses it, a constant-bank word one load (or none)
+__constant__ double kTaylorSin[6] = {1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0};
+__constant__ double kTaylorCos[7] = {-1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0,
+                                     1.0 / 24.0, -0.5};
+
 template <typename T>
 __device__ __forceinline__ void sincos_shift(T s0, T c0, T d, T *s, T *c) {
     T sd, cm1;
     if (Mth<T>::abs_(d) <= T(0.5)) {
         const T d2 = d * d;
-        T ps = T(1.0 / 6227020800.0);
-        ps = ps * d2 + T(-1.0 / 39916800.0);
-        ps = ps * d2 + T(1.0 / 362880.0);
-        ps = ps * d2 + T(-1.0 / 5040.0);
-        ps = ps * d2 + T(1.0 / 120.0);
-        ps = ps * d2 + T(-1.0 / 6.0);
+        T ps = (T)kTaylorSin[0];
+#pragma unroll
+        for (int k = 1; k < 6; k++) ps = ps * d2 + (T)kTaylorSin[k];
         sd = (d * d2) * ps + d;
-        T pc = T(-1.0 / 87178291200.0);
-        pc = pc * d2 + T(1.0 / 479001600.0);
-        pc = pc * d2 + T(-1.0 / 3628800.0);
-        pc = pc * d2 + T(1.0 / 40320.0);
-        pc = pc * d2 + T(-1.0 / 720.0);
-        pc = pc * d2 + T(1.0 / 24.0);
-        pc = pc * d2 + T(-0.5);
+        T pc = (T)kTaylorCos[0];
+#pragma unroll
+        for (int k = 1; k < 7; k++) pc = pc * d2 + (T)kTaylorCos[k];
         cm1 = d2 * pc;
     } else {
         T cd;
