@@ -464,7 +464,7 @@ static int step_parts(DockauvHandle *h, const void *actions, int action_dtype, c
     int rc = ensure_streams(h);
     if (rc != DOCKAUV_OK) return rc;
     const int64_t N = h->n_envs;
-    const int64_t part = ((N / DOCKAUV_STEP_PARTS + 4095) / 4096) * 4096;
+    const int64_t part = (((N + DOCKAUV_STEP_PARTS - 1) / DOCKAUV_STEP_PARTS + 4095) / 4096) * 4096;   // at most PARTS ranges
     CUDA_TRY(cudaEventRecord(h->ev_fork, st));
     int s = 0;
     for (int64_t b = 0; b < N; b += part, s++) {
@@ -617,7 +617,7 @@ static int rollout_issue(DockauvHandle *h, const void *actions, int action_dtype
         // its own stream, forked from / joined to the caller's stream once per rollout instead of once per step
         int rc = ensure_streams(h);
         if (rc != DOCKAUV_OK) return rc;
-        const int64_t part = ((N / DOCKAUV_STEP_PARTS + 4095) / 4096) * 4096;
+        const int64_t part = (((N + DOCKAUV_STEP_PARTS - 1) / DOCKAUV_STEP_PARTS + 4095) / 4096) * 4096;   // at most PARTS ranges
         CUDA_TRY(cudaEventRecord(h->ev_fork, st));
         int s = 0;
         for (int64_t b = 0; b < N; b += part, s++) {

@@ -311,6 +311,31 @@ def test_layouts_agree_bitwise_on_flags_large_batch():
         e.close()
 
 
+def test_step_in_parts_equals_one_launch_group():
+    """A batch that is stepped in two parts on two streams (>= 524,288 envs, odd size) gives the same bits as the same
+    envs stepped as one launch group (split_chunk_envs = N disables the parts)."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
+    cfg = dict(BASE_CONFIG)
+    cfg["radar"] = dict(RADAR_64)
+    n = (1 << 19) + 4097
+    es = [envs.ObstaclesDocking3d(cfg, num_envs=n, seed=21, n_synthetic_spheres=3, split_chunk_envs=c) for c in (0, n)]
+    for e in es:
+        e.reset()
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(12):
+        a = torch.rand(n, 6, device="cuda", generator=gen) * 2 - 1
+        (o0, r0, d0, _), (o1, r1, d1, _) = [e.step(a) for e in es]
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(d0, d1)
+    assert torch.equal(es[0].state, es[1].state) and torch.equal(es[0].episode, es[1].episode)
+    s0, s1 = es[0].get_stats(), es[1].get_stats()
+    assert s0["env_steps"] == s1["env_steps"] == 12 * n and s0["episodes"] == s1["episodes"]
+    assert es[0].launch_count() - es[1].launch_count() == 12 * 4      # 8 launches per step against 4
+    for e in es:
+        e.close()
+
+
 def test_scale_invariants_full_size():
     """BASELINE-size batch (1,048,576 envs, C4 workload): size-independent properties instead of the oracle --
     observation bounds, zero rows exactly where done, statistics add up, determinism across two identical runs."""
