@@ -1,5 +1,6 @@
 """Batched docking environments: the reference's gym.Env contract (gym_dockauv/envs/docking3d.py:31-402),
-vectorised over N independent envs that live in HBM and are stepped by one sm_100a kernel launch.
+vectorised over N independent envs that live in HBM and are stepped by a short sequence of sm_100a kernel launches
+(dynamics, cull, rays, finish; include/dockauv.h).
 
     env = ObstaclesDocking3d(env_config, num_envs=1 << 20, device="cuda:0")
     obs = env.reset(seed=0)                      # f32 [N, n_obs], all zeros like the reference's reset()

@@ -27,9 +27,13 @@
  * Conventions
  *   - plain C types only; no torch / C++ types cross this boundary.
  *   - all `*_dev` pointers are device pointers on the handle's device.  The library never allocates, frees
- *     or keeps caller buffers beyond what dockauv_bind() registered; the caller (PyTorch) owns them.
+ *     or keeps caller buffers beyond what dockauv_bind() registered; the caller (PyTorch) owns them.  The
+ *     handle owns its ray table, the statistics vector, the hand-off buffers between the launches of a step
+ *     (~210 bytes per env) and, lazily, device staging for dockauv_step_host.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are asynchronous and
- *     stream-ordered; one handle must not be used from two threads at once.
+ *     stream-ordered; one handle must not be used from two threads at once.  Large batches (>= 524,288 envs)
+ *     are stepped as two halves on two handle-owned streams that are forked from / joined to `stream` by
+ *     events, so everything stays ordered with respect to `stream` (and capturable into a CUDA graph).
  *   - every function returns 0 on success, a negative DOCKAUV_E* code otherwise; dockauv_last_error()
  *     returns a human-readable description of the last failure on the calling thread.
  *   - there is NO CPU fallback: without a usable CUDA device dockauv_create fails with DOCKAUV_ECUDA.
