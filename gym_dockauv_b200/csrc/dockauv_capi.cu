@@ -46,6 +46,9 @@ struct DeviceGuard {
     }
 };
 
+#ifndef DOCKAUV_HOST_CHUNKS
+#define DOCKAUV_HOST_CHUNKS 12     // chunks of dockauv_step_host (copies of chunk c + 1 overlap the launches of chunk c)
+#endif
 static const int kHostStreams = 3;
 static const size_t kStatsBytes = sizeof(double) * DOCKAUV_N_STATS * DOCKAUV_STAT_COPIES;   // replica 0 = the public vector
 
@@ -540,7 +543,7 @@ extern "C" int dockauv_step_host(DockauvHandle *h, const void *actions_host, int
     int rc = ensure_host_pipeline(h, asz * (size_t)N);
     if (rc != DOCKAUV_OK) return rc;
     // chunks: multiples of 4096 envs, at most 12 per call so copies of chunk c+1 overlap the kernel of chunk c
-    int64_t chunk = (N + 11) / 12;
+    int64_t chunk = (N + DOCKAUV_HOST_CHUNKS - 1) / DOCKAUV_HOST_CHUNKS;
     chunk = ((chunk + 4095) / 4096) * 4096;
     if (chunk < 16384) chunk = 16384;
     DockauvStepOut out;
