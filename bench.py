@@ -161,6 +161,12 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its version banner (and any debug output) to STDOUT by default; stdout carries only the one
+        # JSON line, so NCCL's log goes to stderr
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, the image's default)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = workload_config()
     N = args.envs_per_gpu
