@@ -31,7 +31,7 @@
  *     handle owns its ray table, the statistics vector, the hand-off buffers between the launches of a step
  *     (~210 bytes per env) and, lazily, device staging for dockauv_step_host.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are asynchronous and
- *     stream-ordered; one handle must not be used from two threads at once.  Large batches (>= 524,288 envs)
+ *     stream-ordered; one handle must not be used from two threads at once.  Large batches (>= 131,072 envs)
  *     are stepped as two halves on two handle-owned streams that are forked from / joined to `stream` by
  *     events, so everything stays ordered with respect to `stream` (and capturable into a CUDA graph).
  *   - every function returns 0 on success, a negative DOCKAUV_E* code otherwise; dockauv_last_error()

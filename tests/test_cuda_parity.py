@@ -312,7 +312,7 @@ def test_layouts_agree_bitwise_on_flags_large_batch():
 
 
 def test_step_in_parts_equals_one_launch_group():
-    """A batch that is stepped in two parts on two streams (>= 524,288 envs, odd size) gives the same bits as the same
+    """A batch that is stepped in two parts on two streams (>= 131,072 envs, odd size) gives the same bits as the same
     envs stepped as one launch group (split_chunk_envs = N disables the parts)."""
     import torch
     from gym_dockauv_b200 import envs
