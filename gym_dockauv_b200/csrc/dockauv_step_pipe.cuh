@@ -268,13 +268,16 @@ __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWa
 }
 
 // ------------------------------------------------------------------------------------------------------- 4. finish
+#ifndef DOCKAUV_MINB_FINISH
+#define DOCKAUV_MINB_FINISH 4      // 64 registers; 5 (48 registers, 40 B spills) measured the same
+#endif
 #ifndef DOCKAUV_FINISH_THREADS
 #define DOCKAUV_FINISH_THREADS 256
 #endif
 constexpr int kFinishThreads = DOCKAUV_FINISH_THREADS;
 
 template <typename T>
-__global__ void __launch_bounds__(kFinishThreads) finish_kernel(const __grid_constant__ KParams<T> p) {
+__global__ void __launch_bounds__(kFinishThreads, DOCKAUV_MINB_FINISH) finish_kernel(const __grid_constant__ KParams<T> p) {
     __shared__ int s_n_reset;
     __shared__ int s_reset[kFinishThreads];
     const int64_t N = p.n_envs;
