@@ -48,6 +48,14 @@ def test_argument_validation_without_gpu():
     assert lib.dockauv_create(C.byref(p), 16, 0, C.byref(h)) == -1 and b"radar" in lib.dockauv_last_error()
     assert lib.dockauv_step(None, None, 0, None, None, None, 0, None) == -1
     assert lib.dockauv_destroy(None) == 0
+    # the caller-side entry points validate their arguments before touching the device
+    assert lib.dockauv_rollout(None, None, 0, 4, None, 1, 1, None) == -1
+    assert lib.dockauv_gae(None, 0, None, None, None, 4, 16, 0.99, 0.95, None, None, None) == -1
+    assert lib.dockauv_fold_stats(None, None) == -1
+    n = C.c_int()
+    ms = (C.c_float * 4)()
+    assert lib.dockauv_last_step_launch_ms(None, ms, 4, C.byref(n)) == -1
+    assert lib.dockauv_step_host(None, None, 0, None, None, None, None, 1, None) == -1
 
 
 def test_no_cpu_fallback():
