@@ -564,6 +564,10 @@ extern "C" int dockauv_step_host(DockauvHandle *h, const void *actions_host, int
     // small outputs (reward, done, cond_bits) leave once per group of 2 * kHostStreams consecutive chunks (waiting for a
     // group is one event per stream): 36 small copies per step cost ~0.3 ms of copy-engine overhead on top of the
     // 2.6 ms the bytes need.
+    // work issued earlier on the legacy default stream (PyTorch's default current stream: a preceding dockauv_step,
+    // reset or set_state) is ordered before the internal streams start; callers on other streams synchronise themselves
+    CUDA_TRY(cudaEventRecord(h->ev_fork, (cudaStream_t)0));
+    for (int s = 0; s < kHostStreams; s++) CUDA_TRY(cudaStreamWaitEvent(h->hs[s], h->ev_fork, 0));
     int c = 0;
     int64_t group_begin = 0;
     auto flush_small = [&](int64_t gb, int64_t ge, int last_stream) -> int {

@@ -287,6 +287,9 @@ class BaseDocking3d:
             self._host = dict(obs=pin(N, self.n_observations, dtype=torch.float32), reward=pin(N, dtype=self.dtype),
                               done=pin(N, dtype=torch.uint8), cond=pin(N, dtype=torch.uint8))
         hb = self._host
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != 0:       # the library orders itself after the legacy default stream only
+            cur.synchronize()
         _capi.check(self._lib.dockauv_step_host(self._handle, C.c_void_p(a.ctypes.data), adt,
                                                 C.c_void_p(hb["obs"].data_ptr()), C.c_void_p(hb["reward"].data_ptr()),
                                                 C.c_void_p(hb["done"].data_ptr()), C.c_void_p(hb["cond"].data_ptr()),

@@ -240,7 +240,9 @@ DOCKAUV_API int dockauv_step(DockauvHandle *h, const void *actions_dev, int acti
 
 /* Same step with HOST buffers (pinned memory recommended): actions are copied in, obs/reward/done (and
  * cond_bits if non-NULL) are copied out, pipelined in chunks over the handle's internal streams; returns
- * after the results are in host memory.  reward_host is double[N] or float[N] per the handle precision.
+ * after the results are in host memory.  The call is ordered after work already issued on the legacy default
+ * stream; a caller that drives the handle from another stream synchronises that stream first.
+ * reward_host is double[N] or float[N] per the handle precision.
  * aux_dev_or_null: optional DEVICE buffers for the per-episode extras (only terminal_obs, ep_return_out and
  * ep_len_out are read from it); they stay on the device, the caller fetches the few finished rows it needs. */
 DOCKAUV_API int dockauv_step_host(DockauvHandle *h, const void *actions_host, int action_dtype, float *obs_host,
