@@ -1,18 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the gym_dockauv step hot path on B200 (BASELINE.json metric: env-steps/s, ObstaclesDocking3d,
-BlueROV2, 64-ray radar, 5 capsules + 3 spheres -- config C4: 1,048,576 envs per GPU, weak scaling to C5).
+BlueROV2, 64-ray radar, 5 capsules + 3 spheres).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]             # our arm (CUDA, through the C ABI)
-    python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU arm: the oracle port on host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W     # CPU arm: the oracle port on all host cores
+    python bench.py --config C2|C3|C4 --scaling weak|strong ...          # the other BASELINE configs / sharding modes
 
-One "step" = one batched env.step() over every env of the rank (default layout: four launches -- dynamics, cull, rays,
+Default = config C4 with 1,048,576 envs PER GPU (weak scaling; at 8 GPUs this is config C5: 8M envs, auto-reset, one
+NCCL all-reduce of the episode statistics per rollout).  `--scaling strong` shards 1,048,576 envs TOTAL over the ranks
+(config C4 as BASELINE.json words it); a run with more than one rank also measures that strong-scaling point in a second
+pass and reports it as `strong` next to the weak-scaling `value`.
+
+One "step" = one batched env.step() over every env of the rank (three launches -- dynamics, cull + finish, rays +
 finish -- for each half of the batch, the halves on two streams).  Rank 0 prints ONE JSON line.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The per-step
-working set (~0.9 GB at 1M envs) is far larger than L2 (126 MB), so no explicit L2 flush is needed (stated in
-config.l2).  Actions are synthetic i.i.d. U(-1,1) float32, pre-generated on the device for `value`; the `e2e`
-number goes through env.step_host() with pinned HOST actions in and HOST obs/reward/done out every step.
+working set (~0.9 GB at 1M envs) is far larger than L2 (126 MB), so no explicit L2 flush is needed at the default size
+(stated in config.l2; smaller configs rotate through a pool of action tensors and say so).  Actions are synthetic
+i.i.d. U(-1,1) float32, pre-generated on the device for `value`; the `e2e` number goes through env.step_host() with
+pinned HOST actions in and HOST obs/reward/done out every step.
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -25,26 +34,42 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-BYTES_PER_ENV_STEP = 898      # algorithmic HBM bytes per env-step for C4 (FP64 SoA, f32 obs/actions)
-FLOPS_PER_ENV_STEP = 17700    # algorithmic flops per env-step for C4
 HBM_FALLBACK_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
-# dram__bytes_read.sum + dram__bytes_write.sum of the eight launches (two halves x four) of ONE step over 1,048,576 envs
-# (FP64) from the committed `ncu --set full` capture profiles/r01/v13_pipeline_ncu_raw.csv (per launch in that file)
-NCU_TRAFFIC_BYTES_1M_F64 = 1756.4e6
-LAUNCH_NAMES = ("dynamics", "cull", "rays", "finish")
-# sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active per launch, same capture (fraction of the FP64 pipe's
-# issue slots actually used -- the executed counterpart of the algorithmic `pipe.frac`)
-NCU_FP64_PIPE_BUSY = {"dynamics": 0.496, "cull": 0.031, "rays": 0.367, "finish": 0.105}
-WORKLOAD = ("C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions U(-1,1) f32, "
-            "auto-reset of finished envs")
-SCENARIO = "ObstaclesDocking3d"
+FP64_NOMINAL_TFLOPS = 37.2    # 148 SMs x 64 FP64 FMA / clk x 2 x 1.965 GHz
 N_SYNTH_SPHERES = 3
 
+# BASELINE.json configs with the ALGORITHMIC figures of SURVEY.md 8(d), per env-step and split over the launches of the
+# pipeline: dynamics = the 6-DOF integration + navigation errors + obs[0:16] + radar-free reward terms;
+# cull = body-collision tests + (for envs with nothing in view) reward / done / counters; rays = 64 rays x (rotate 25 +
+# 5 capsules x 33 + 3 spheres x 10 + pool / OA 8).  Bytes: every persistent item read once and written once.
+CONFIGS = {
+    "C2": dict(scenario="SimpleDocking3d", vehicle="BlueROV2", envs=65536, radar64=False, n_synth=0, h=0.1,
+               bytes=538, flops=2900, launch_flops=dict(dynamics=2900, cull_finish=0, rays_finish=0),
+               launch_bytes=dict(dynamics=458, cull_finish=80, rays_finish=0),
+               workload="C2: SimpleDocking3d, BlueROV2, 65,536 envs, dynamics + reward only (no obstacles: every ray "
+                        "reads max_dist), random actions U(-1,1) f32, auto-reset"),
+    "C3": dict(scenario="CapsuleCurrentDocking3d", vehicle="LAUV", envs=262144, radar64=False, n_synth=0, h=0.02,
+               bytes=534, flops=7250, launch_flops=dict(dynamics=3050, cull_finish=35, rays_finish=4165),
+               launch_bytes=dict(dynamics=398, cull_finish=136, rays_finish=0),
+               workload="C3: CapsuleCurrentDocking3d, LAUV with ocean current, 262,144 envs, docking-capsule collision "
+                        "checks, t_step_size 0.02 (the reference's integrator diverges at its stock 0.1 for this "
+                        "vehicle, SURVEY.md 8c), random actions U(-1,1) f32, auto-reset"),
+    "C4": dict(scenario="ObstaclesDocking3d", vehicle="BlueROV2", envs=1 << 20, radar64=True, n_synth=N_SYNTH_SPHERES, h=0.1,
+               bytes=898, flops=17700, launch_flops=dict(dynamics=2900, cull_finish=205, rays_finish=14592),
+               launch_bytes=dict(dynamics=458, cull_finish=440, rays_finish=0),
+               workload="C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions "
+                        "U(-1,1) f32, auto-reset of finished envs"),
+}
+LAUNCH_NAMES = ("dynamics", "cull_finish", "rays_finish")
 
-def workload_config():
+
+def workload_config(c):
     from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
     cfg = dict(BASE_CONFIG)
-    cfg["radar"] = dict(RADAR_64)
+    cfg["vehicle"] = c["vehicle"]
+    cfg["t_step_size"] = c["h"]
+    if c["radar64"]:
+        cfg["radar"] = dict(RADAR_64)
     return cfg
 
 
@@ -55,6 +80,46 @@ def measured_hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources: the committed ncu figures are only quoted while the kernels they came from are
+    the ones being run."""
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "gym_dockauv_b200", "csrc", "*"))):
+        with open(f, "rb") as fh:
+            h.update(os.path.basename(f).encode())
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_figures(config_name):
+    """Per-launch DRAM traffic and FP64-pipe utilisation from the committed `ncu --set full` capture (written by
+    profiles/tools/ncu_launch_json.py); None when the capture belongs to other kernel sources."""
+    path = os.path.join(ROOT, "profiles", "r02", f"ncu_per_launch_{config_name}.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except Exception:
+        return None, "no committed capture for this config"
+    if d.get("kernel_source_hash") != kernel_source_hash():
+        return None, f"{os.path.relpath(path, ROOT)} was captured from other kernel sources (stale) -- not quoted"
+    return d, os.path.relpath(path, ROOT)
+
+
+def recorded_numpy_baseline(config_name):
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02", "reference_numpy_cpu.json")) as f:
+            d = json.load(f)
+    except Exception:
+        return None
+    case = d["cases"].get("C4" if config_name == "C4" else "C1")
+    if case is None:
+        return None
+    return {"kind": d["kind"], "unit": d["unit"], "value": case["all_cores"]["value"], "cores": case["all_cores"]["cores"],
+            "value_one_core": case["one_process"]["value"], "workload": case["workload"], "cpu": d["cpu"], "date": d["date"],
+            "how": "unmodified /root/reference (numpy) timed in the build container by profiles/tools/time_reference_numpy.py; "
+                   "/root/reference does not exist on the GPU box, so this figure is recorded, not live"}
 
 
 class ClockSampler:
@@ -103,13 +168,42 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rate(n_envs, seconds, n_threads=0, steps_cap=10 ** 9, warmup=1):
+def host_threads():
+    """Host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0
+    alone while the other ranks exit, so it takes every core of its affinity mask and passes the count explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pins the process to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host memory is allocated,
+    so that first-touch places the step_host staging buffers on the GPU's NUMA node.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = sorted(cpus & allowed)
+        if pick:
+            os.sched_setaffinity(0, pick)
+            return {"cpus": f"{pick[0]}-{pick[-1]} ({len(pick)})", "source": "nvmlDeviceGetCpuAffinity"}
+        return {"cpus": None, "source": "NVML affinity outside the allowed cpuset; left unchanged"}
+    except Exception as ex:  # noqa: BLE001
+        return {"cpus": None, "source": f"unavailable ({type(ex).__name__})"}
+
+
+def cpu_port_rate(c, n_envs, seconds, n_threads, steps_cap=10 ** 9, warmup=1):
     """Times the oracle port (oracle/dockauv_oracle.c, OpenMP over envs) on this host's cores."""
     from oracle import oracle as orc
-    cfg = workload_config()
-    bo = orc.BatchOracle(cfg, SCENARIO, n_envs, seed=0, n_extra_spheres=N_SYNTH_SPHERES, n_threads=n_threads)
+    cfg = workload_config(c)
+    bo = orc.BatchOracle(cfg, c["scenario"], n_envs, seed=0, n_extra_spheres=c["n_synth"], n_threads=n_threads)
+    n_u = bo.P.n_u
     rng = np.random.default_rng(1)
-    pool = [rng.uniform(-1, 1, (n_envs, 6)).astype(np.float32) for _ in range(4)]
+    pool = [rng.uniform(-1, 1, (n_envs, n_u)).astype(np.float32) for _ in range(4)]
     for i in range(warmup):
         bo.step(pool[i % 4])
     t0 = time.perf_counter()
@@ -118,45 +212,65 @@ def cpu_port_rate(n_envs, seconds, n_threads=0, steps_cap=10 ** 9, warmup=1):
         bo.step(pool[k % 4])
         k += 1
     dt = time.perf_counter() - t0
-    threads = n_threads if n_threads > 0 else orc.lib().orc_max_threads()
-    return n_envs * k / dt, threads, k, dt
+    return n_envs * k / dt, k, dt
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle as orc
+    c = CONFIGS[args.config]
     n = args.ref_envs
-    cfg = workload_config()
-    bo = orc.BatchOracle(cfg, SCENARIO, n, seed=0, n_extra_spheres=N_SYNTH_SPHERES)
+    threads = host_threads()
+    cfg = workload_config(c)
+    bo = orc.BatchOracle(cfg, c["scenario"], n, seed=0, n_extra_spheres=c["n_synth"], n_threads=threads)
+    n_u = bo.P.n_u
     rng = np.random.default_rng(1)
-    pool = [rng.uniform(-1, 1, (n, 6)).astype(np.float32) for _ in range(4)]
+    pool = [rng.uniform(-1, 1, (n, n_u)).astype(np.float32) for _ in range(4)]
     for i in range(args.warmup):
         bo.step(pool[i % 4])
     t0 = time.perf_counter()
     for k in range(args.steps):
         bo.step(pool[k % 4])
     dt = time.perf_counter() - t0
-    threads = orc.lib().orc_max_threads()
     value = n * args.steps / dt
     line = {
         "impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "envs_per_step": n, "sample": f"{n} envs per step (bounded sample of the 1,048,576-env workload)"},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": c["workload"],
+                   "envs_per_step": n, "sample": f"{n} envs per step (bounded sample of the {c['envs']:,}-env workload)"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} envs x {args.steps} steps, oracle/dockauv_oracle.c with OpenMP on {threads} threads"},
+                         "sample": f"{n} envs x {args.steps} steps, oracle/dockauv_oracle.c with OpenMP on {threads} threads "
+                                   f"(num_threads passed explicitly; rank 0 only, the other ranks exit)"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    nb = recorded_numpy_baseline(args.config)
+    if nb:
+        line["cpu_baseline_numpy"] = nb
     print(json.dumps(line), flush=True)
 
 
+def timed_steps(env, pool, steps, dev):
+    """K steps bracketed by CUDA events on the launching stream; returns (total ms, per-step ms array)."""
+    import torch
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for k in range(steps):
+        env.step(pool[k % len(pool)])
+        evs[k + 1].record()
+    torch.cuda.synchronize(dev)
+    return evs[0].elapsed_time(evs[-1]), np.array([evs[k].elapsed_time(evs[k + 1]) for k in range(steps)])
+
+
 def run_ours(args, rank, world, local_rank):
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"cpus": None, "source": "disabled"}
     import torch
     import torch.distributed as dist
     from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.params import N_STATS, STAT_NAMES
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -168,13 +282,29 @@ def run_ours(args, rank, world, local_rank):
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    cfg = workload_config()
-    N = args.envs_per_gpu
-    env = envs.ObstaclesDocking3d(cfg, num_envs=N, device=dev, precision=args.precision, seed=args.seed,
-                                  env_id0=rank * N, n_synthetic_spheres=N_SYNTH_SPHERES, layout=args.layout)
-    env.reset()
+    c = CONFIGS[args.config]
+    cfg = workload_config(c)
+    if args.envs_per_gpu > 0:
+        N = args.envs_per_gpu
+    elif args.scaling == "strong":
+        N = c["envs"] // world
+    else:
+        N = c["envs"]
+    esz = 8 if args.precision == "f64" else 4
+
+    def make_env(n, id0):
+        e = envs.SCENARIOS[c["scenario"]](cfg, num_envs=n, device=dev, precision=args.precision, seed=args.seed,
+                                          env_id0=id0, n_synthetic_spheres=c["n_synth"], layout=args.layout)
+        e.reset()
+        return e
+
+    env = make_env(N, rank * N)
+    # a pool of action tensors: the timed loop never reads the same actions twice in a row; with pool_bytes >> L2 the
+    # inputs of small configs do not stay L2-resident either
+    n_pool = args.action_pool if N * env.n_actions * 4 * args.action_pool <= (2 << 30) else max(4, (2 << 30) // (N * env.n_actions * 4))
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = [torch.rand(N, env.n_actions, device=dev, generator=gen) * 2 - 1 for _ in range(args.action_pool)]
+    pool = [torch.rand(N, env.n_actions, device=dev, generator=gen) * 2 - 1 for _ in range(n_pool)]
+    pool_mb = N * env.n_actions * 4 * n_pool / 1e6
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -188,26 +318,27 @@ def run_ours(args, rank, world, local_rank):
         env.step(pool[k % len(pool)])
     for k in range(args.warmup):
         env.step(pool[k % len(pool)])
-    stats_t = env.stats_tensor()
     env.clear_stats()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = env.launch_count()
+    # ---- the timed region: K steps; one statistics all-reduce per rollout on a side stream, at least one
+    rollout = max(1, min(args.rollout, args.steps))
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     side = torch.cuda.Stream(dev)
-    n_reduces = 0
+    reduced, n_reduces = None, 0
     evs[0].record()
     for k in range(args.steps):
         env.step(pool[k % len(pool)])
         evs[k + 1].record()
-        if world > 1 and (k + 1) % args.rollout == 0:
-            # per-rollout episode statistics: one small NCCL all-reduce on a side stream
+        if world > 1 and (k + 1) % rollout == 0:
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                red = env.stats_tensor().clone()      # folds the per-CTA replicas on the side stream first
-                dist.all_reduce(red)
+                local = env.stats_tensor().clone()      # folds the per-CTA replicas on the side stream first
+                reduced = local.clone()
+                dist.all_reduce(reduced)
             n_reduces += 1
     torch.cuda.current_stream(dev).wait_stream(side)
     barrier()
@@ -220,7 +351,18 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     stats = env.get_stats()
-    # per-launch durations (CUDA events recorded by the library between the launches of a step, on the launching
+    # the reduced vector of the last all-reduce must be the sum of the rank-local vectors it was made from
+    allreduce_check = None
+    if world > 1 and reduced is not None:
+        gathered = [torch.zeros(N_STATS, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        total = torch.stack(gathered).sum(0)
+        ok = bool(torch.allclose(total, reduced, rtol=1e-12, atol=0.0))
+        allreduce_check = {"equals_sum_of_rank_vectors": ok,
+                           "reduced": {k: float(reduced[i]) for i, k in enumerate(STAT_NAMES)},
+                           "rank0_local_env_steps": float(gathered[0][STAT_NAMES.index("env_steps")])}
+
+    # ---- per-launch durations (CUDA events recorded by the library between the launches of a step, on the launching
     # stream), in a separate short pass so that the marks do not sit inside the timed region above
     env.enable_timing(True)
     per_launch = []
@@ -250,16 +392,59 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s_max = float(t.item())
-    esz = 8 if args.precision == "f64" else 4
     h2d = N * env.n_actions * 4
     d2h = N * (env.n_observations * 4 + esz + 1 + 1)
+    # ---- the copy ceiling of that path: the same bytes as plain pinned cudaMemcpyAsync, H2D and D2H on two streams,
+    # every rank at the same time (what the PCIe links and host memory of this box give with no kernel at all)
+    hb_in = torch.empty(h2d, dtype=torch.uint8).pin_memory()
+    hb_out = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+    db_in = torch.empty(h2d, dtype=torch.uint8, device=dev)
+    db_out = torch.empty(d2h, dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_round():
+        with torch.cuda.stream(s_in):
+            db_in.copy_(hb_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hb_out.copy_(db_out, non_blocking=True)
+    copy_round()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_round()
+    torch.cuda.synchronize(dev)
+    copy_s = time.perf_counter() - t0
+    t = torch.tensor([copy_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    copy_s_max = float(t.item())
+    env.close()
+    del pool, env
+
+    # ---- strong-scaling point of the same run (config as BASELINE.json words it: the config's envs TOTAL, sharded)
+    strong = None
+    if world > 1 and args.scaling == "weak" and args.envs_per_gpu <= 0 and not args.no_strong_pass:
+        Ns = c["envs"] // world
+        env_s = make_env(Ns, rank * Ns)
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        pool_s = [torch.rand(Ns, env_s.n_actions, device=dev, generator=gen) * 2 - 1 for _ in range(args.action_pool)]
+        for k in range(args.burn_in + args.warmup):
+            env_s.step(pool_s[k % len(pool_s)])
+        barrier()
+        ms_s, _ = timed_steps(env_s, pool_s, args.steps, dev)
+        t = torch.tensor([ms_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "envs_total": Ns * world, "envs_per_gpu": Ns, "steps": args.steps,
+                  "ms_per_step": float(t.item()) / args.steps, "value": Ns * world * args.steps / (float(t.item()) * 1e-3),
+                  "unit": "env-steps/s", "note": "second pass of the same run: the config's envs TOTAL sharded over the "
+                                                 "ranks (BASELINE.json configs[3]); the headline `value` is weak scaling"}
+        env_s.close()
 
     if rank == 0:
         value = world * N * args.steps / (total_ms_max * 1e-3)
         kern_ms = float(step_ms.mean())
         per_gpu_rate = N / (kern_ms * 1e-3)
         hbm_peak, hbm_src = measured_hbm_peak()
-        achieved_gbs = per_gpu_rate * BYTES_PER_ENV_STEP / 1e9
         fp64_peak = fp32_peak = None
         try:
             import ctypes as C
@@ -269,49 +454,85 @@ def run_ours(args, rank, world, local_rank):
             fp64_peak, fp32_peak = a.value, b.value
         except Exception as ex:  # noqa: BLE001
             print(f"peak measurement failed: {ex}", file=sys.stderr)
+        pipe_name = "fp64" if args.precision == "f64" else "fp32"
         pipe_peak = fp64_peak if args.precision == "f64" else fp32_peak
-        achieved_tf = per_gpu_rate * FLOPS_PER_ENV_STEP / 1e12
+        names = LAUNCH_NAMES[:len(launch_ms)]
+        launches_ms = {n: float(v) for n, v in zip(names, launch_ms)}
+        dominant = names[int(np.argmax(launch_ms))] if len(launch_ms) else None
+        ncu, ncu_src = ncu_figures(args.config)
+        ncu_ok = ncu is not None and args.precision == ncu.get("precision", "f64") and dominant in ncu.get("launches", {})
+        roofline = {"bound": pipe_name, "unit": "TFLOP/s", "peak": pipe_peak,
+                    "peak_source": "dockauv_measure_peaks: 8-chain FMA micro-kernel on this GPU, live (MEASURED_PEAKS.json "
+                                   f"carries no FP64 figure; nominal {FP64_NOMINAL_TFLOPS} TFLOP/s at 1.965 GHz)"}
+        if dominant is not None and pipe_peak:
+            dms = launches_ms[dominant]
+            ach = c["launch_flops"][dominant] * N / (dms * 1e-3) / 1e12
+            ach_gbs = c["launch_bytes"][dominant] * N / (dms * 1e-3) / 1e9
+            roofline.update({
+                "kernel": dominant, "kernel_ms": dms, "algorithmic_flops_per_env": c["launch_flops"][dominant],
+                "achieved": ach, "frac": ach / pipe_peak, "frac_of_nominal": ach / FP64_NOMINAL_TFLOPS if pipe_name == "fp64" else None,
+                "executed_pipe_frac": (ncu["launches"][dominant].get("fp64_pipe_pct", 0.0) / 100.0) if ncu_ok else None,
+                "traffic": (ncu["launches"][dominant]["dram_bytes_per_env"] * N) if ncu_ok else None,
+                "traffic_source": ncu_src,
+                "hbm": {"algorithmic_bytes_per_env": c["launch_bytes"][dominant], "achieved": ach_gbs, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
+                "how": "achieved = algorithmic flops of the launch x envs per launch / its CUDA-event duration, measured "
+                       "live between the launches of a step on the launching stream; the whole batch in one stream for "
+                       "this pass (the timed region steps it as two halves on two streams)"})
+        step_tf = per_gpu_rate * c["flops"] / 1e12
+        step_gbs = per_gpu_rate * c["bytes"] / 1e9
+        roofline["step"] = {"ms": kern_ms, "launches_ms": launches_ms,
+                            "flops_per_env_step": c["flops"], "bytes_per_env_step": c["bytes"],
+                            "fp_achieved_tflops": step_tf, "fp_frac": (step_tf / pipe_peak) if pipe_peak else None,
+                            "hbm_achieved_gbs": step_gbs, "hbm_frac": step_gbs / hbm_peak,
+                            "traffic": (ncu["step_dram_bytes_per_env"] * N) if ncu_ok else None,
+                            "executed_pipe_frac_time_weighted": ncu.get("fp64_pipe_frac_time_weighted") if ncu_ok else None,
+                            "note": "algorithmic figures of SURVEY.md 8(d) over the whole step; fp_frac counts the contract's "
+                                    "brute-force 64 x 8 ray tests, most of which the culls skip, so it can exceed what the "
+                                    "pipe executes -- executed_pipe_frac is the hardware figure"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, threads, k_cpu, dt_cpu = cpu_port_rate(args.ref_envs, args.cpu_seconds)
+            os.sched_setaffinity(0, all_cpus)        # the CPU baseline takes every host core, not just the GPU's NUMA node
+            threads = host_threads()
+            rate, k_cpu, dt_cpu = cpu_port_rate(c, args.ref_envs, args.cpu_seconds, threads)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                    "sample": f"{args.ref_envs} envs x {k_cpu} steps ({dt_cpu:.1f} s) of the same workload, "
                              f"oracle/dockauv_oracle.c with OpenMP on {threads} threads"}
+        e2e_value = world * N * e2e_steps / e2e_s_max
+        copy_value = world * N * e2e_steps / copy_s_max
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": WORKLOAD,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": c["workload"], "name": args.config,
                        "envs_per_gpu": N, "envs_total": world * N, "layout": args.layout, "burn_in_steps": args.burn_in,
-                       "rollout_steps": args.rollout, "stats_allreduces": n_reduces,
-                       "l2": "working set per step ~0.9 GB per GPU >> 126 MB L2, no flush needed"},
-            "e2e": {"value": world * N * e2e_steps / e2e_s_max, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "env.step_host (dockauv_step_host)"},
+                       "rollout_steps": rollout, "stats_allreduces": n_reduces,
+                       "l2": (f"working set per step ~{N * (c['bytes'] + 350) / 1e9:.2f} GB per GPU vs 126 MB L2; actions rotate "
+                              f"through a pool of {n_pool} tensors ({pool_mb:.0f} MB); no explicit flush"),
+                       "host_affinity": numa},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "env.step_host (dockauv_step_host)",
+                    "copy_ceiling": {"value": copy_value, "unit": "env-steps/s",
+                                     "gbs_per_gpu": (h2d + d2h) * e2e_steps / copy_s_max / 1e9,
+                                     "how": "the same H2D + D2H bytes per step as plain pinned cudaMemcpyAsync on two "
+                                            "streams, all ranks at once, no kernel"},
+                    "frac_of_copy_ceiling": e2e_value / copy_value},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak,
-                         "traffic": NCU_TRAFFIC_BYTES_1M_F64 if (N == 1 << 20 and args.precision == "f64") else None,
-                         "traffic_source": "profiles/r01/v13_pipeline_ncu_raw.csv (bytes per step = sum of its eight launches)",
-                         "peak_source": hbm_src,
-                         "bytes_per_env_step": BYTES_PER_ENV_STEP, "kernel_ms": kern_ms,
-                         "launches_ms": {n: float(v) for n, v in zip(LAUNCH_NAMES, launch_ms)},
-                         "dominant_launch": (LAUNCH_NAMES[int(np.argmax(launch_ms))] if launch_ms.size else "step"),
-                         "note": "the path is FP64-pipe-bound (19.7 flop/B vs machine balance ~5.7), see 'pipe'"},
-            "pipe": {"bound": "fp64" if args.precision == "f64" else "fp32", "achieved": achieved_tf,
-                     "peak": pipe_peak, "unit": "TFLOP/s", "frac": (achieved_tf / pipe_peak) if pipe_peak else None,
-                     "flops_per_env_step": FLOPS_PER_ENV_STEP,
-                     "executed_pipe_busy_ncu": NCU_FP64_PIPE_BUSY if args.precision == "f64" else None,
-                     "note": "frac counts the contract's 17.7 kflop per env-step; the culls skip most ray tests, so the "
-                             "pipe itself is ~40 % busy (ncu, per launch above): the launches are latency-bound",
-                     "peak_source": "dockauv_measure_peaks FMA micro-kernel on this GPU"},
+            "roofline": roofline,
             "episode_stats": {k: stats[k] for k in ("episodes", "sum_return", "sum_length", "done_collision",
                                                     "done_out_att", "env_steps")},
         }
+        if allreduce_check is not None:
+            line["stats_allreduce"] = allreduce_check
+        if strong is not None:
+            line["strong"] = strong
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        nb = recorded_numpy_baseline(args.config)
+        if nb:
+            line["cpu_baseline_numpy"] = nb
         print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -322,9 +543,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--config", default="C4", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--layout", default="auto", choices=["auto", "thread_per_env", "warp_rays", "split", "pipeline"])
+    ap.add_argument("--layout", default="auto", choices=["auto", "thread_per_env", "warp_rays", "pipeline"])
     ap.add_argument("--burn-in", type=int, default=128)
     ap.add_argument("--rollout", type=int, default=128)
     ap.add_argument("--action-pool", type=int, default=64)
@@ -333,6 +556,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong-pass", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -21,7 +21,10 @@ SYMBOLS = {
     "dockauv_bind": (_i, [_vp, C.POINTER(DockauvBuffers)]),
     "dockauv_set_seed": (_i, [_vp, C.c_uint64]),
     "dockauv_reset": (_i, [_vp, _vp, _vp]),
+    "dockauv_refresh_obstacles": (_i, [_vp, _vp]),
     "dockauv_step": (_i, [_vp, _vp, _i, _vp, C.POINTER(DockauvStepOut), C.POINTER(DockauvDebugOut), _i, _vp]),
+    "dockauv_enable_step_graph": (_i, [_vp, _i]),
+    "dockauv_step_graph_captures": (_i, [_vp, C.POINTER(_i64)]),
     "dockauv_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, C.POINTER(DockauvStepOut)]),
     "dockauv_rollout": (_i, [_vp, _vp, _i, _i, C.POINTER(DockauvRolloutOut), _i, _i, _vp]),
     "dockauv_gae": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i64, C.c_float, C.c_float, _vp, _vp, _vp]),
@@ -31,6 +34,7 @@ SYMBOLS = {
     "dockauv_clear_stats": (_i, [_vp, _vp]),
     "dockauv_measure_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dockauv_launch_count": (_i, [_vp, C.POINTER(_i64)]),
+    "dockauv_rollout_captures": (_i, [_vp, C.POINTER(_i64)]),
     "dockauv_enable_timing": (_i, [_vp, _i]),
     "dockauv_last_step_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "dockauv_last_step_launch_ms": (_i, [_vp, C.POINTER(C.c_float), _i, C.POINTER(_i)]),

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -61,7 +62,7 @@ struct DockauvHandle {
     KParams<double> kd;
     KParams<float> kf;
     void *ray_tab = nullptr;
-    void *handoff = nullptr;       // split layout only
+    void *pipe_buf = nullptr;      // pipeline layout: per-env records, float obstacle records, ray list + counters
     double *stats = nullptr;
     int64_t launches = 0;
     bool timing = false;
@@ -84,12 +85,55 @@ struct DockauvHandle {
     struct RolloutKey {
         const void *actions = nullptr;
         DockauvRolloutOut out = {};
-        int n_steps = 0, action_dtype = 0, auto_reset = 0;
+        int64_t n_steps = 0, action_dtype = 0, auto_reset = 0;      // 64-bit fields: no padding bytes in the key
         uint64_t seed = 0;
+        bool operator==(const RolloutKey &o) const {
+            return actions == o.actions && out.obs == o.out.obs && out.reward == o.out.reward && out.done == o.out.done &&
+                   out.cond_bits == o.out.cond_bits && out.terminal_obs == o.out.terminal_obs &&
+                   out.ep_return_out == o.out.ep_return_out && out.ep_len_out == o.out.ep_len_out &&
+                   out.delta_d_out == o.out.delta_d_out && n_steps == o.n_steps && action_dtype == o.action_dtype &&
+                   auto_reset == o.auto_reset && seed == o.seed;
+        }
     } rg_key;
+    int64_t rg_captures = 0;       // how many times a rollout graph was captured (tests: replays must not re-capture)
+    // step graph cache: the launch sequence of ONE dockauv_step (launches of both halves, fork / join events) captured per
+    // set of pointers and replayed; trainers alternate between a handful of action / output tensors
+    struct StepKey {
+        const void *actions = nullptr, *noise = nullptr;
+        DockauvStepOut out = {};
+        int64_t action_dtype = 0, auto_reset = 0;
+        uint64_t seed = 0;
+        bool operator==(const StepKey &o) const {
+            return actions == o.actions && noise == o.noise && out.obs == o.out.obs && out.reward == o.out.reward &&
+                   out.done == o.out.done && out.cond_bits == o.out.cond_bits && out.terminal_obs == o.out.terminal_obs &&
+                   out.ep_return_out == o.out.ep_return_out && out.ep_len_out == o.out.ep_len_out &&
+                   out.delta_d_out == o.out.delta_d_out && action_dtype == o.action_dtype && auto_reset == o.auto_reset &&
+                   seed == o.seed;
+        }
+    };
+    struct StepGraph {
+        StepKey key;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+    };
+    std::vector<StepGraph> sg;
+    size_t sg_next = 0;            // slot replaced next once the cache is full
+    bool sg_enabled = true;
+    int64_t sg_captures = 0;
 };
 
 static int pooled_dim(int n, int b) { return (n + b - 1) / b; }
+
+static void drop_graphs(DockauvHandle *h) {      // captured launch sequences hold the old pointers / seed
+    if (h->rg_exec) {
+        cudaGraphExecDestroy(h->rg_exec);
+        h->rg_exec = nullptr;
+    }
+    for (auto &g : h->sg)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->sg.clear();
+    h->sg_next = 0;
+}
 
 extern "C" int dockauv_abi_version(void) { return DOCKAUV_ABI_VERSION; }
 extern "C" const char *dockauv_last_error(void) { return g_err; }
@@ -181,6 +225,21 @@ static void fill_kparams(const DockauvParams &s, int64_t n_envs, KParams<T> &k) 
     if (!fan_ok) ty = tz = 1e30;
     ty *= 1.0 + 1e-9;
     tz *= 1.0 + 1e-9;
+    // M_inv with nothing outside the diagonal and [0,4] [4,0] [1,3] [3,1] (centre of gravity offset along z only: both
+    // stock vehicles): the kernels then skip the 26 exact zeros of the dense product
+    bool sparse = true;
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c < 6; c++) {
+            const bool allowed = r == c || (r == 0 && c == 4) || (r == 4 && c == 0) || (r == 1 && c == 3) || (r == 3 && c == 1);
+            if (!allowed && s.M_inv[6 * r + c] != 0.0) sparse = false;
+        }
+#ifdef DOCKAUV_FORCE_DENSE_MINV      // tuning builds
+    sparse = false;
+#endif
+    k.sparse_minv = sparse ? 1 : 0;
+    // the cull launch works on float records relative to the goal: every coordinate that matters is within
+    // max_dist_from_goal + max_dist of it; beyond ~2 km the float rounding would eat the 2 mm slack -> exact culls
+    k.cull_exact = (s.max_dist_from_goal + s.radar_max_dist > 2000.0) ? 1 : 0;
     k.fov_ty = (T)ty;
     k.fov_tz = (T)tz;
     k.fov_ny = (T)std::sqrt(1.0 + ty * ty);
@@ -207,8 +266,20 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
     if (p->n_rays <= 0 || p->n_rays > DOCKAUV_MAX_RAYS || p->n_rays != p->n_vert * p->n_horiz || p->block_reduce <= 0)
         return fail(DOCKAUV_EINVAL, "bad radar geometry (n_rays=%d, %d x %d, block %d)", p->n_rays, p->n_vert,
                     p->n_horiz, p->block_reduce);
+    if (p->n_synthetic_spheres < 0 || p->n_synthetic_spheres > p->n_spheres)
+        return fail(DOCKAUV_EINVAL, "n_synthetic_spheres must be in 0..n_spheres");
+    if (!(p->h > 0.0)) return fail(DOCKAUV_EINVAL, "t_step_size must be positive");
+    if (p->max_timesteps <= 0) return fail(DOCKAUV_EINVAL, "max_timesteps must be positive");
+    if (!(p->u_max > 0.0) || !(p->v_max > 0.0) || !(p->w_max > 0.0) || !(p->p_max > 0.0) || !(p->q_max > 0.0) ||
+        !(p->r_max > 0.0) || !(p->max_attitude > 0.0))
+        return fail(DOCKAUV_EINVAL, "u_max .. r_max and max_attitude must be positive (they normalise the observation)");
+    if (!(p->max_dist_from_goal > 0.0) || !(p->dist_goal_reached_tol > 0.0) || !(p->radar_max_dist > 0.0))
+        return fail(DOCKAUV_EINVAL, "max_dist_from_goal, dist_goal_reached_tol and the radar's max_dist must be positive");
     if (p->reward_set != 1 && p->reward_set != 2) return fail(DOCKAUV_EINVAL, "reward_set must be 1 or 2");
     if (p->scenario < 0 || p->scenario > DOCKAUV_SCN_OBSTACLES_NOCAP) return fail(DOCKAUV_EINVAL, "bad scenario");
+    if (p->layout != DOCKAUV_LAYOUT_AUTO && p->layout != DOCKAUV_LAYOUT_THREAD_PER_ENV && p->layout != DOCKAUV_LAYOUT_WARP_RAYS &&
+        p->layout != DOCKAUV_LAYOUT_PIPELINE)
+        return fail(DOCKAUV_EINVAL, "unknown layout %d", p->layout);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -250,40 +321,37 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         h->kd.stats = h->stats;
         h->kf.stats = h->stats;
     }
-    if (p->layout == DOCKAUV_LAYOUT_SPLIT || p->layout == DOCKAUV_LAYOUT_PIPELINE || p->layout == DOCKAUV_LAYOUT_AUTO) {
-        // hand-off between the launches of the split / pipeline layouts: T[22][N] + cond u32[N]; the pipeline adds the
-        // view word u32[N], the ray list u64[N], the obstacle-avoidance sums T[N] and one list counter per 128 envs
+    if (p->layout == DOCKAUV_LAYOUT_PIPELINE || p->layout == DOCKAUV_LAYOUT_AUTO) {
+        // library-owned buffers of the pipeline layout: per-env record T[16] (128-byte aligned), float obstacle records
+        // float4[2 n_caps + n_sph], the ray list u64 and one list counter per 128 envs
         const size_t esz = p->precision == DOCKAUV_F64 ? 8 : 4;
         const size_t n = (size_t)n_envs;
-        const size_t words = (size_t)22 * n * esz;
-        const size_t off_cond = words, off_info = off_cond + 4 * n, off_list = (off_info + 4 * n + 7) & ~(size_t)7;
-        const size_t off_oa = off_list + 8 * n, off_cnt = off_oa + esz * n;
-        const size_t n_cnt = n / 128 + 2;
-        cudaError_t e5 = cudaMalloc(&h->handoff, off_cnt + 4 * n_cnt);
-        if (e5 == cudaSuccess) e5 = cudaMemset(h->handoff, 0, off_cnt + 4 * n_cnt);   // view words / counters start at 0
+        const int n_obsf = 2 * p->n_capsules + p->n_spheres;
+        const size_t off_rec = 0, off_obsf = off_rec + 16 * esz * n, off_list = off_obsf + 16 * (size_t)n_obsf * n;
+        const size_t off_cnt = off_list + 8 * n;
+        const size_t n_cnt = 2 * (n / 128 + 2);      // two list counters per concurrently stepped env range
+        cudaError_t e5 = cudaMalloc(&h->pipe_buf, off_cnt + 4 * n_cnt);
+        if (e5 == cudaSuccess) e5 = cudaMemset(h->pipe_buf, 0, off_cnt + 4 * n_cnt);
         if (e5 != cudaSuccess) {
             cudaFree(h->ray_tab);
             cudaFree(h->stats);
-            if (h->handoff) cudaFree(h->handoff);
+            if (h->pipe_buf) cudaFree(h->pipe_buf);
             delete h;
-            return fail(DOCKAUV_ECUDA, "device allocation of the hand-off buffer failed: %s", cudaGetErrorString(e5));
+            return fail(DOCKAUV_ECUDA, "device allocation of the pipeline buffers failed: %s", cudaGetErrorString(e5));
         }
-        char *base = (char *)h->handoff;
-        h->kd.handoff = (double *)base;
-        h->kf.handoff = (float *)base;
-        h->kd.handoff_cond = h->kf.handoff_cond = (uint32_t *)(base + off_cond);
-        h->kd.view_info = h->kf.view_info = (uint32_t *)(base + off_info);
+        char *base = (char *)h->pipe_buf;
+        h->kd.rec = (double *)(base + off_rec);
+        h->kf.rec = (float *)(base + off_rec);
+        h->kd.obsf = h->kf.obsf = n_obsf > 0 ? (float4 *)(base + off_obsf) : nullptr;
+        h->kd.n_obsf = h->kf.n_obsf = n_obsf;
         h->kd.view_list = h->kf.view_list = (unsigned long long *)(base + off_list);
-        h->kd.oa_dot = (double *)(base + off_oa);
-        h->kf.oa_dot = (float *)(base + off_oa);
         h->kd.view_count = h->kf.view_count = (unsigned int *)(base + off_cnt);
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         h->kd.sm_count = h->kf.sm_count = sms;
-        // one launch group over the whole batch by default: smaller chunks would keep the hand-off in L2 but lose more
-        // to partial waves than they gain (0.89 ms at 1M envs per pair, 0.94 at 512K, 1.04 at 256K)
-        const int64_t chunk = p->split_chunk_envs > 0 ? p->split_chunk_envs : n_envs;
-        h->kd.split_chunk = h->kf.split_chunk = chunk;
+        // one launch group over the whole batch by default: smaller chunks would keep the records in L2 but lose more
+        // to partial waves than they gain (measured, profiles/r01/NOTES.md)
+        h->kd.chunk_envs = h->kf.chunk_envs = p->split_chunk_envs > 0 ? p->split_chunk_envs : 0;
     }
     *out = h;
     return DOCKAUV_OK;
@@ -294,7 +362,7 @@ extern "C" int dockauv_destroy(DockauvHandle *h) {
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     if (h->ray_tab) cudaFree(h->ray_tab);
-    if (h->handoff) cudaFree(h->handoff);
+    if (h->pipe_buf) cudaFree(h->pipe_buf);
     if (h->stats) cudaFree(h->stats);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -310,7 +378,7 @@ extern "C" int dockauv_destroy(DockauvHandle *h) {
     if (h->st_reward) cudaFree(h->st_reward);
     if (h->st_done) cudaFree(h->st_done);
     if (h->st_cond) cudaFree(h->st_cond);
-    if (h->rg_exec) cudaGraphExecDestroy(h->rg_exec);
+    drop_graphs(h);
     delete h;
     return DOCKAUV_OK;
 }
@@ -339,10 +407,13 @@ extern "C" int dockauv_bind(DockauvHandle *h, const DockauvBuffers *b) {
     bind_k<double>(h->kd, *b);
     bind_k<float>(h->kf, *b);
     h->bound = true;
-    if (h->rg_exec) {   // a captured rollout holds the old pointers
-        cudaGraphExecDestroy(h->rg_exec);
-        h->rg_exec = nullptr;
+    {   // float obstacle records of whatever the buffers hold now (later writers: dockauv_reset, dockauv_refresh_obstacles)
+        DeviceGuard guard(h->device);
+        if (h->params.precision == DOCKAUV_F64) CUDA_TRY(launch_refresh_obstacles<double>(h->kd, (cudaStream_t)0));
+        else CUDA_TRY(launch_refresh_obstacles<float>(h->kf, (cudaStream_t)0));
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
     }
+    drop_graphs(h);
     return DOCKAUV_OK;
 }
 
@@ -353,9 +424,8 @@ static bool scenario_has_current(int scn) {
 
 static int resolve_layout(const DockauvHandle *h) {
     int layout = h->params.layout;
-    // measured on B200 (profiles/r01/NOTES.md, 1M envs of C4): fused kernel 0.91 ms, split pair 0.74 ms, four-launch
-    // pipeline 0.61 ms; without obstacles the pipeline is dynamics + finish only (0.30 ms against 0.45 ms fused);
-    // thread-per-env stays as the independently written cross-check
+    // measured on B200 (1M envs of C4): fused kernel 0.91 ms, three-launch pipeline 0.5 ms; without obstacles the pipeline
+    // is dynamics + finish only; thread-per-env stays as the independently written cross-check
     if (layout == DOCKAUV_LAYOUT_AUTO) layout = DOCKAUV_LAYOUT_PIPELINE;
     return layout;
 }
@@ -372,6 +442,7 @@ static void set_io(KParams<T> &k, const void *actions, bool act_f32, const void 
     k.done = o.done;
     k.cond_bits = o.cond_bits;
     k.ep_len_out = o.ep_len_out;
+    k.delta_d_out = (T *)o.delta_d_out;
     k.auto_reset = auto_reset ? 1 : 0;
     k.act_f32 = act_f32 ? 1 : 0;
     k.dbg_ray_dist = d ? (T *)d->ray_dist : nullptr;
@@ -409,13 +480,9 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
     }
     if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
     const bool staged = dbg == nullptr;   // else: the fused kernel
-    const bool has_obstacles = (h->params.n_capsules + h->params.n_spheres) > 0;
-    if (layout == DOCKAUV_LAYOUT_SPLIT && staged) {
-        const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
-        h->launches += 2 * ((end - begin + chunk - 1) / chunk);
-    } else if (layout == DOCKAUV_LAYOUT_PIPELINE && staged) {
-        const int64_t chunk = h->kd.split_chunk > 0 ? h->kd.split_chunk : (end - begin);
-        h->launches += (has_obstacles ? 4 : 2) * ((end - begin + chunk - 1) / chunk);
+    if (layout == DOCKAUV_LAYOUT_PIPELINE && staged) {
+        const int64_t chunk = h->kd.chunk_envs > 0 ? h->kd.chunk_envs : (end - begin);
+        h->launches += 3 * ((end - begin + chunk - 1) / chunk);
     } else {
         h->launches += 1;
     }
@@ -437,6 +504,18 @@ extern "C" int dockauv_reset(DockauvHandle *h, const uint8_t *mask_dev, void *st
     cudaStream_t st = (cudaStream_t)stream;
     if (h->params.precision == DOCKAUV_F64) CUDA_TRY(launch_reset<double>(h->kd, mask_dev, st));
     else CUDA_TRY(launch_reset<float>(h->kf, mask_dev, st));
+    h->launches += 1;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_refresh_obstacles(DockauvHandle *h, void *stream) {
+    if (!h) return fail(DOCKAUV_EINVAL, "null handle");
+    if (!h->bound) return fail(DOCKAUV_ESTATE, "dockauv_bind must be called before dockauv_refresh_obstacles");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->kd.obsf == nullptr) return DOCKAUV_OK;
+    if (h->params.precision == DOCKAUV_F64) CUDA_TRY(launch_refresh_obstacles<double>(h->kd, st));
+    else CUDA_TRY(launch_refresh_obstacles<float>(h->kf, st));
     h->launches += 1;
     return DOCKAUV_OK;
 }
@@ -465,6 +544,14 @@ static bool steps_in_parts(const DockauvHandle *h) {
            h->params.split_chunk_envs == 0;
 }
 
+// obs / terminal_obs rows are written in 16-byte pieces when n_obs is a multiple of 4
+static int check_rows(const DockauvHandle *h, const float *obs, const float *terminal_obs) {
+    if ((h->n_obs & 3) == 0 && ((((uintptr_t)obs) & 15u) != 0 || (((uintptr_t)terminal_obs) & 15u) != 0))
+        return fail(DOCKAUV_EINVAL, "obs and terminal_obs must be 16-byte aligned (n_obs = %d is a multiple of 4: rows are "
+                                    "written with 128-bit stores)", h->n_obs);
+    return DOCKAUV_OK;
+}
+
 static int step_parts(DockauvHandle *h, const void *actions, int action_dtype, const void *noise,
                       const DockauvStepOut *out, int auto_reset, cudaStream_t st) {
     int rc = ensure_streams(h);
@@ -490,12 +577,75 @@ static int step_device(DockauvHandle *h, const void *actions, int action_dtype, 
     return step_range(h, actions, action_dtype, noise, out, dbg, auto_reset, 0, h->n_envs, st, timing);
 }
 
+#ifndef DOCKAUV_STEP_GRAPHS
+#define DOCKAUV_STEP_GRAPHS 96     // cached step graphs per handle (a trainer alternates between a few tensors; bench.py's pool: 64)
+#endif
+// One dockauv_step as a CUDA graph: the launch sequence (both halves, their fork / join events) is captured once per set
+// of pointers and replayed -- one graph launch instead of six kernel launches and four event operations, and no
+// launch-to-launch gaps on the device (what makes a 65,536-env step 24 us instead of 29).
+static int step_graph(DockauvHandle *h, const void *actions, int action_dtype, const void *noise, const DockauvStepOut *out,
+                      int auto_reset, cudaStream_t st) {
+    DockauvHandle::StepKey key;
+    key.actions = actions;
+    key.noise = noise;
+    key.out = *out;
+    key.action_dtype = action_dtype;
+    key.auto_reset = auto_reset;
+    key.seed = h->params.seed;
+    DockauvHandle::StepGraph *g = nullptr;
+    for (auto &c : h->sg)
+        if (c.key == key) {
+            g = &c;
+            break;
+        }
+    if (g == nullptr) {
+        // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+        cudaStream_t cs = nullptr;
+        CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        int rc = DOCKAUV_OK;
+        const int64_t before = h->launches;
+        if (e == cudaSuccess) {
+            rc = step_device(h, actions, action_dtype, noise, out, nullptr, auto_reset, cs, false);
+            e = cudaStreamEndCapture(cs, &graph);
+        }
+        const int64_t n_launch = h->launches - before;
+        h->launches = before;       // captured, not launched; every replay counts them
+        if (e == cudaSuccess && rc == DOCKAUV_OK) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        if (rc != DOCKAUV_OK) return rc;
+        if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step graph capture failed: %s", cudaGetErrorString(e));
+        DockauvHandle::StepGraph fresh;
+        fresh.key = key;
+        fresh.exec = exec;
+        fresh.launches = n_launch;
+        if (h->sg.size() < (size_t)DOCKAUV_STEP_GRAPHS) {
+            h->sg.push_back(fresh);
+            g = &h->sg.back();
+        } else {
+            DockauvHandle::StepGraph &victim = h->sg[h->sg_next];
+            h->sg_next = (h->sg_next + 1) % h->sg.size();
+            cudaGraphExecDestroy(victim.exec);
+            victim = fresh;
+            g = &victim;
+        }
+        h->sg_captures += 1;
+    }
+    CUDA_TRY(cudaGraphLaunch(g->exec, st));
+    h->launches += g->launches;
+    return DOCKAUV_OK;
+}
+
 extern "C" int dockauv_step(DockauvHandle *h, const void *actions_dev, int action_dtype, const void *noise_dev,
                             const DockauvStepOut *out, const DockauvDebugOut *dbg, int auto_reset, void *stream) {
     if (!h || !actions_dev || !out) return fail(DOCKAUV_EINVAL, "null argument");
     if (!h->bound) return fail(DOCKAUV_ESTATE, "dockauv_bind must be called before dockauv_step");
     if (!out->obs || !out->reward || !out->done) return fail(DOCKAUV_EINVAL, "obs, reward and done outputs are required");
     if (action_dtype != DOCKAUV_ACT_F32 && action_dtype != DOCKAUV_ACT_F64) return fail(DOCKAUV_EINVAL, "bad action dtype");
+    if (check_rows(h, out->obs, out->terminal_obs) != DOCKAUV_OK) return DOCKAUV_EINVAL;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (h->timing) {
@@ -506,12 +656,29 @@ extern "C" int dockauv_step(DockauvHandle *h, const void *actions_dev, int actio
         }
         CUDA_TRY(cudaEventRecord(h->ev0, st));
     }
+    if (!h->timing && dbg == nullptr && h->sg_enabled) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+            return step_graph(h, actions_dev, action_dtype, noise_dev, out, auto_reset, st);
+    }
     int rc = step_device(h, actions_dev, action_dtype, noise_dev, out, dbg, auto_reset, st, h->timing);
     if (rc != DOCKAUV_OK) return rc;
     if (h->timing) {
         CUDA_TRY(cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
     }
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_enable_step_graph(DockauvHandle *h, int enabled) {
+    if (!h) return fail(DOCKAUV_EINVAL, "null handle");
+    h->sg_enabled = enabled != 0;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_step_graph_captures(DockauvHandle *h, int64_t *n) {
+    if (!h || !n) return fail(DOCKAUV_EINVAL, "null argument");
+    *n = h->sg_captures;
     return DOCKAUV_OK;
 }
 
@@ -559,6 +726,8 @@ extern "C" int dockauv_step_host(DockauvHandle *h, const void *actions_host, int
         out.terminal_obs = aux->terminal_obs;
         out.ep_return_out = aux->ep_return_out;
         out.ep_len_out = aux->ep_len_out;
+        out.delta_d_out = aux->delta_d_out;
+        if (check_rows(h, out.obs, out.terminal_obs) != DOCKAUV_OK) return DOCKAUV_EINVAL;
     }
     // Per chunk: actions in, the step's launches, the observation rows out (the bulk of the bytes, one copy).  The
     // small outputs (reward, done, cond_bits) leave once per group of 2 * kHostStreams consecutive chunks (waiting for a
@@ -620,6 +789,7 @@ static int rollout_issue(DockauvHandle *h, const void *actions, int action_dtype
         so.terminal_obs = o.terminal_obs ? o.terminal_obs + orow * t : nullptr;
         so.ep_return_out = o.ep_return_out ? (char *)o.ep_return_out + esz * (size_t)N * t : nullptr;
         so.ep_len_out = o.ep_len_out ? o.ep_len_out + (size_t)N * t : nullptr;
+        so.delta_d_out = o.delta_d_out ? (char *)o.delta_d_out + esz * (size_t)N * t : nullptr;
         return so;
     };
     if (steps_in_parts(h)) {
@@ -658,6 +828,7 @@ extern "C" int dockauv_rollout(DockauvHandle *h, const void *actions_dev, int ac
     if (!out->obs || !out->reward || !out->done) return fail(DOCKAUV_EINVAL, "obs, reward and done outputs are required");
     if (action_dtype != DOCKAUV_ACT_F32 && action_dtype != DOCKAUV_ACT_F64) return fail(DOCKAUV_EINVAL, "bad action dtype");
     if (n_steps <= 0) return fail(DOCKAUV_EINVAL, "n_steps must be positive");
+    if (check_rows(h, out->obs, out->terminal_obs) != DOCKAUV_OK) return DOCKAUV_EINVAL;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (out->ep_len_out)
@@ -670,7 +841,7 @@ extern "C" int dockauv_rollout(DockauvHandle *h, const void *actions_dev, int ac
     key.action_dtype = action_dtype;
     key.auto_reset = auto_reset;
     key.seed = h->params.seed;
-    if (!h->rg_exec || memcmp(&key, &h->rg_key, sizeof(key)) != 0) {
+    if (!h->rg_exec || !(key == h->rg_key)) {
         if (h->rg_exec) {
             cudaGraphExecDestroy(h->rg_exec);
             h->rg_exec = nullptr;
@@ -696,8 +867,8 @@ extern "C" int dockauv_rollout(DockauvHandle *h, const void *actions_dev, int ac
             h->rg_exec = nullptr;
             return fail(DOCKAUV_ECUDA, "rollout graph capture failed: %s", cudaGetErrorString(e));
         }
-        memset(&h->rg_key, 0, sizeof(h->rg_key));
         h->rg_key = key;
+        h->rg_captures += 1;
     }
     CUDA_TRY(cudaGraphLaunch(h->rg_exec, st));
     h->launches += h->rg_launches;
@@ -793,6 +964,12 @@ extern "C" int dockauv_clear_stats(DockauvHandle *h, void *stream) {
 extern "C" int dockauv_launch_count(DockauvHandle *h, int64_t *n) {
     if (!h || !n) return fail(DOCKAUV_EINVAL, "null argument");
     *n = h->launches;
+    return DOCKAUV_OK;
+}
+
+extern "C" int dockauv_rollout_captures(DockauvHandle *h, int64_t *n) {
+    if (!h || !n) return fail(DOCKAUV_EINVAL, "null argument");
+    *n = h->rg_captures;
     return DOCKAUV_OK;
 }
 

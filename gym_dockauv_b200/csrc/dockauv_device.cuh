@@ -225,7 +225,7 @@ __device__ __forceinline__ void cross3(const T a[3], const T b[3], T o[3]) {
 // Kinetic part of auvsim.py:152-158:  nu_dot = M^-1 (B(nu) u - D(nu) nu - C(nu) nu - G(eta)).
 //   tau : BlueROV2 -> precomputed B u (B is constant, BlueROV2.py:74-75); LAUV -> the low-passed command u[3]
 //   sphi, cphi, sth, cth : sin/cos of roll and pitch
-template <typename T, int VEH>
+template <typename T, int VEH, bool SPM = false>
 __device__ __forceinline__ void nu_dot(const KParams<T> &p, const T nu[6], const T tau[6], T sphi, T cphi, T sth,
                                        T cth, T out[6]) {
     const T *n1 = nu, *n2 = nu + 3;
@@ -296,12 +296,25 @@ __device__ __forceinline__ void nu_dot(const KParams<T> &p, const T nu[6], const
         f[4] -= p.G_r[2] * sth + p.G_r[0] * cc;
         f[5] -= -p.G_r[0] * cs - p.G_r[1] * sth;
     }
+    if (SPM) {
+        // M_inv of a vehicle whose centre of gravity is offset along z only (both stock vehicles): ten non-zeros, the
+        // diagonal and [0,4] [4,0] [1,3] [3,1].  The dense product adds exact zeros for the other 26 entries -- unless
+        // a component of f is inf / NaN, in which case 0 * f poisons EVERY row; `z` keeps that behaviour.
+        const T z = (((f[0] + f[1]) + (f[2] + f[3])) + (f[4] + f[5])) * T(0);
+        out[0] = p.M_inv[0] * f[0] + (p.M_inv[4] * f[4] + z);
+        out[1] = p.M_inv[7] * f[1] + (p.M_inv[9] * f[3] + z);
+        out[2] = p.M_inv[14] * f[2] + z;
+        out[3] = p.M_inv[19] * f[1] + (p.M_inv[21] * f[3] + z);
+        out[4] = p.M_inv[24] * f[0] + (p.M_inv[28] * f[4] + z);
+        out[5] = p.M_inv[35] * f[5] + z;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        T s = p.M_inv[6 * i] * f[0];
+        for (int i = 0; i < 6; i++) {
+            T s = p.M_inv[6 * i] * f[0];
 #pragma unroll
-        for (int k = 1; k < 6; k++) s += p.M_inv[6 * i + k] * f[k];
-        out[i] = s;
+            for (int k = 1; k < 6; k++) s += p.M_inv[6 * i + k] * f[k];
+            out[i] = s;
+        }
     }
 }
 
@@ -316,7 +329,8 @@ __device__ __forceinline__ void rzyx(T sphi, T cphi, T sth, T cth, T spsi, T cps
 // One evaluation of the reduced right-hand side (auvsim.py:110-160) at y = (Theta, nu_r).
 //   tr = sin/cos of (phi, theta, psi) at y: {sphi, cphi, sth, cth, spsi, cpsi} (psi only read if WPOS)
 //   k[0:3] = T(phi, theta) nu2 (geomutils.py:72-75), k[3:9] = nu_dot;  if WPOS, pacc += wpos * R(Theta) (nu1 + nu_c).
-template <typename T, int VEH, bool WPOS>
+//   CUR = false: no ocean current (nu_c is not read).
+template <typename T, int VEH, bool WPOS, bool SPM = false, bool CUR = true>
 __device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T tr[6], const T tau[6], const T nu_c[3],
                                      T wpos, T pacc[3], T k[9]) {
     const T sphi = tr[0], cphi = tr[1], sth = tr[2], cth = tr[3];
@@ -330,11 +344,16 @@ __device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T 
     if (WPOS) {
         T R[9];
         rzyx(sphi, cphi, sth, cth, tr[4], tr[5], R);
-        T v[3] = {nu[0] + nu_c[0], nu[1] + nu_c[1], nu[2] + nu_c[2]};
+        T v[3];
+        if (CUR) {
+            v[0] = nu[0] + nu_c[0]; v[1] = nu[1] + nu_c[1]; v[2] = nu[2] + nu_c[2];
+        } else {
+            v[0] = nu[0]; v[1] = nu[1]; v[2] = nu[2];
+        }
 #pragma unroll
         for (int i = 0; i < 3; i++) pacc[i] += wpos * (R[3 * i] * v[0] + R[3 * i + 1] * v[1] + R[3 * i + 2] * v[2]);
     }
-    nu_dot<T, VEH>(p, nu, tau, sphi, cphi, sth, cth, k + 3);
+    nu_dot<T, VEH, SPM>(p, nu, tau, sphi, cphi, sth, cth, k + 3);
 }
 
 // sin/cos of the stage attitude Theta0 + d from the pre-step values tr0 (psi skipped when the stage has no position weight)
@@ -345,67 +364,98 @@ __device__ __forceinline__ void stage_trig(const T tr0[6], const T d[3], T tr[6]
     if (WPSI) sincos_shift<T>(tr0[4], tr0[5], d[2], &tr[4], &tr[5]);
 }
 
-// utils/odesolver45.py:18-26 on the reduced state; the 4th-order result is written back to pos / y.
+// utils/odesolver45.py:18-26 on the reduced state y = (Theta, nu_r); the 4th-order result is written back to y and the
+// position increment h sum(b_i R(Theta_i)(nu1_i + nu_c)) is returned in pacc (position does not feed back).
 //   tr0: sin/cos of the pre-step attitude y[0:3]; tr1 (out): sin/cos of the post-step attitude (before ssa, which
 //   does not change them).
-template <typename T, int VEH>
-__device__ __forceinline__ void rkf45_step(const KParams<T> &p, T pos[3], T y[9], const T tr0[6], const T tau[6],
-                                           const T nu_c[3], T tr1[6]) {
+// Register pressure decides the speed of this function (the dynamics launch is latency-bound at 16 warps per SM), so
+// the stage derivatives are not kept until they are last used: as soon as k3 exists, the partial sums of the two
+// combinations that still need k1..k3 (the stage-5 input and the result) are formed and k1..k3 die; the sums are
+// continued with k4 / k5 in the same left-to-right order as written in the tableau, so nothing changes numerically.
+template <typename T, int VEH, bool SPM = false, bool CUR = true>
+__device__ __forceinline__ void rkf45_step(const KParams<T> &p, T y[9], const T tr0[6], const T tau[6], const T nu_c[3],
+                                           T pacc[3], T tr1[6]) {
     const T h = p.h;
-    T k1[9], k2[9], k3[9], k4[9], k5[9], yt[9], dy[9], tr[6];
-    T pacc[3] = {T(0), T(0), T(0)};
-    rhs9<T, VEH, true>(p, y, tr0, tau, nu_c, h * T(25.0 / 216.0), pacc, k1);
+    T yt[9], dy[9], tr[6];
+    T d5[9], dw[9];      // running sums: stage-5 input increment, result increment
+    pacc[0] = pacc[1] = pacc[2] = T(0);
     {
-        const T a = h * T(0.25);
+        T k1[9], k2[9], k3[9];
+        rhs9<T, VEH, true, SPM, CUR>(p, y, tr0, tau, nu_c, h * T(25.0 / 216.0), pacc, k1);
+        {
+            const T a = h * T(0.25);
 #pragma unroll
-        for (int i = 0; i < 9; i++) {
-            dy[i] = a * k1[i];
-            yt[i] = y[i] + dy[i];
+            for (int i = 0; i < 9; i++) {
+                dy[i] = a * k1[i];
+                yt[i] = y[i] + dy[i];
+            }
+        }
+        stage_trig<T, false>(tr0, dy, tr);
+        rhs9<T, VEH, false, SPM, CUR>(p, yt, tr, tau, nu_c, T(0), pacc, k2);   // b2 = 0: no position contribution
+        {
+            const T a = h * T(3.0 / 32.0), b = h * T(9.0 / 32.0);
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                dy[i] = a * k1[i] + b * k2[i];
+                yt[i] = y[i] + dy[i];
+            }
+        }
+        stage_trig<T, true>(tr0, dy, tr);
+        rhs9<T, VEH, true, SPM, CUR>(p, yt, tr, tau, nu_c, h * T(1408.0 / 2565.0), pacc, k3);
+        {
+            const T a = h * T(1932.0 / 2197.0), b = h * T(-7200.0 / 2197.0), c = h * T(7296.0 / 2197.0);
+            const T a5 = h * T(439.0 / 216.0), b5 = h * T(-8.0), c5 = h * T(3680.0 / 513.0);
+            const T aw = h * T(25.0 / 216.0), cw = h * T(1408.0 / 2565.0);
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                dy[i] = a * k1[i] + b * k2[i] + c * k3[i];
+                yt[i] = y[i] + dy[i];
+                d5[i] = a5 * k1[i] + b5 * k2[i] + c5 * k3[i];
+                dw[i] = aw * k1[i] + cw * k3[i];
+            }
         }
     }
-    stage_trig<T, false>(tr0, dy, tr);
-    rhs9<T, VEH, false>(p, yt, tr, tau, nu_c, T(0), pacc, k2);   // b2 = 0: no position contribution
-    {
-        const T a = h * T(3.0 / 32.0), b = h * T(9.0 / 32.0);
+#ifdef DOCKAUV_RK_FOLD
+    // tuning variant: from here on the velocity components carry y inside the running sums (y[3..8] is dead two stages
+    // earlier); the attitude components keep their increments, which sincos_shift needs
 #pragma unroll
-        for (int i = 0; i < 9; i++) {
-            dy[i] = a * k1[i] + b * k2[i];
-            yt[i] = y[i] + dy[i];
-        }
+    for (int i = 3; i < 9; i++) {
+        d5[i] = y[i] + d5[i];
+        dw[i] = y[i] + dw[i];
     }
+#endif
     stage_trig<T, true>(tr0, dy, tr);
-    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(1408.0 / 2565.0), pacc, k3);
     {
-        const T a = h * T(1932.0 / 2197.0), b = h * T(-7200.0 / 2197.0), c = h * T(7296.0 / 2197.0);
+        T k4[9];
+        rhs9<T, VEH, true, SPM, CUR>(p, yt, tr, tau, nu_c, h * T(2197.0 / 4104.0), pacc, k4);
+        const T d = h * T(-845.0 / 4104.0), dwc = h * T(2197.0 / 4104.0);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            dy[i] = a * k1[i] + b * k2[i] + c * k3[i];
-            yt[i] = y[i] + dy[i];
+            d5[i] = d5[i] + d * k4[i];
+#ifdef DOCKAUV_RK_FOLD
+            yt[i] = i < 3 ? y[i] + d5[i] : d5[i];
+#else
+            yt[i] = y[i] + d5[i];
+#endif
+            dw[i] = dw[i] + dwc * k4[i];
         }
     }
-    stage_trig<T, true>(tr0, dy, tr);
-    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(2197.0 / 4104.0), pacc, k4);
+    stage_trig<T, true>(tr0, d5, tr);
     {
-        const T a = h * T(439.0 / 216.0), b = h * T(-8.0), c = h * T(3680.0 / 513.0), d = h * T(-845.0 / 4104.0);
+        T k5[9];
+        rhs9<T, VEH, true, SPM, CUR>(p, yt, tr, tau, nu_c, h * T(-1.0 / 5.0), pacc, k5);
+        const T e = h * T(-1.0 / 5.0);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            dy[i] = a * k1[i] + b * k2[i] + c * k3[i] + d * k4[i];
-            yt[i] = y[i] + dy[i];
+            dw[i] = dw[i] + e * k5[i];
+#ifdef DOCKAUV_RK_FOLD
+            y[i] = i < 3 ? y[i] + dw[i] : dw[i];
+#else
+            y[i] = y[i] + dw[i];
+#endif
         }
     }
-    stage_trig<T, true>(tr0, dy, tr);
-    rhs9<T, VEH, true>(p, yt, tr, tau, nu_c, h * T(-1.0 / 5.0), pacc, k5);
-    {
-        const T a = h * T(25.0 / 216.0), c = h * T(1408.0 / 2565.0), d = h * T(2197.0 / 4104.0), e = h * T(-1.0 / 5.0);
-#pragma unroll
-        for (int i = 0; i < 9; i++) {
-            dy[i] = a * k1[i] + c * k3[i] + d * k4[i] + e * k5[i];
-            y[i] = y[i] + dy[i];
-        }
-    }
-    stage_trig<T, true>(tr0, dy, tr1);
-#pragma unroll
-    for (int i = 0; i < 3; i++) pos[i] += pacc[i];
+    stage_trig<T, true>(tr0, dw, tr1);
 }
 
 // ------------------------------------------------------------------------------------------- radar geometry
@@ -528,38 +578,96 @@ __device__ __forceinline__ void obstacle_pair(const KParams<T> &p, const T pos[3
     in_view = !outside;
 }
 
-#ifndef DOCKAUV_CULL_CLIP
-#define DOCKAUV_CULL_CLIP 1
-#endif
-// The culls and the body-collision test of obstacle_pair in FLOAT, for the cull launch (FP64 runs at half rate and was
-// that launch's busiest pipe).  Differences of positions are formed in T and rounded once, everything after that is
-// float with explicit slack, so the result can only err on the safe side:
+// Just the ray-test record of obstacle_pair (same expressions, same bits): what the ray launch needs once the cull
+// launch has decided collision and visibility.
+template <typename T>
+__device__ __forceinline__ void obstacle_ray_record(const T pos[3], const T ob[7], bool is_cap, T *w) {
+    if (is_cap) {
+        const T bot[3] = {ob[0], ob[1], ob[2]}, top[3] = {ob[3], ob[4], ob[5]};
+        CapPre<T> q;
+        capsule_pre<T>(pos, bot, top, ob[6], q);
+        w[0] = q.ba[0]; w[1] = q.ba[1]; w[2] = q.ba[2];
+        w[3] = q.oa[0]; w[4] = q.oa[1]; w[5] = q.oa[2];
+        w[6] = q.baba; w[7] = q.baoa; w[8] = q.c; w[9] = q.c2a; w[10] = q.c2b;
+    } else {
+        T oc[3], d2 = T(0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            oc[c] = pos[c] - ob[c];
+            d2 += oc[c] * oc[c];
+        }
+        const T rad = ob[3];
+        w[0] = oc[0]; w[1] = oc[1]; w[2] = oc[2]; w[3] = d2 - rad * rad;
+    }
+}
+
+// Just the body-collision decision of obstacle_pair (same expressions, same bits): used by the cull launch for the
+// pairs its float pre-test leaves undecided.
+template <typename T>
+__device__ __forceinline__ bool obstacle_body_hit(const KParams<T> &p, const T pos[3], const T ob[7], bool is_cap) {
+    T rad, dist;
+    if (is_cap) {
+        const T bot[3] = {ob[0], ob[1], ob[2]}, top[3] = {ob[3], ob[4], ob[5]};
+        rad = ob[6];
+        CapPre<T> q;
+        capsule_pre<T>(pos, bot, top, rad, q);
+        const T inv_n = Mth<T>::rsqrt_pos(q.baba);
+        const T sp = -q.baoa * inv_n;
+        const T tp = (q.oc2[0] * q.ba[0] + q.oc2[1] * q.ba[1] + q.oc2[2] * q.ba[2]) * inv_n;
+        T hh = sp;
+        if (tp > hh || tp != tp) hh = tp;
+        if (T(0) > hh) hh = T(0);
+        T cr[3];
+        cross3(q.oa, q.ba, cr);
+        const T perp2 = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * (inv_n * inv_n);
+        const T dd = hh * hh + perp2;
+        dist = dd > T(0) ? Mth<T>::sqrt_pos(dd) : dd;
+    } else {
+        T d2 = T(0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const T oc = pos[c] - ob[c];
+            d2 += oc * oc;
+        }
+        rad = ob[3];
+        dist = d2 > T(0) ? Mth<T>::sqrt_pos(d2) : d2;
+    }
+    return dist <= rad + p.safety_radius;
+}
+
+// The culls and the body-collision pre-test of obstacle_pair in FLOAT, for the cull launch (FP64 runs at half rate and
+// the launch is bound by the bytes it reads).  Inputs are the float obstacle record (KParams::obsf, relative to the goal,
+// written by every reset) and the vehicle position relative to the goal (formed in T by the dynamics launch, rounded
+// once): every coordinate that matters is within max_dist_from_goal + max_dist of the origin, so the float rounding
+// error of a difference is a few 1e-6 m.  Everything after that carries explicit slack, so the result can only err on
+// the safe side:
 //   * in_view: every threshold is widened by far more than the float rounding error (lengths 2e-3 m, axis parameter
 //     1e-3, discriminant 1e-5 relative), so "culled" here implies "culled" in exact arithmetic;
 //   * hit: 0 = clear, 1 = collision, 2 = within 2e-3 m of the threshold -- the caller decides those in T.
+//   q0: capsule (bot - goal, radius) / sphere (centre - goal, radius);  q1: capsule (top - bot, 1 / |top - bot|)
+// The field-of-view test clips the reachable part of the axis against all five planes of the ray pyramid at once: an
+// axis point can carry a surface point inside the pyramid only if it is within r of the inner side of ALL five planes;
+// each signed distance is linear along the axis, so each plane keeps an interval of the segment parameter and the
+// obstacle is out of view when their intersection is empty (this also catches segments that leave the pyramid through
+// different planes).  Crossing parameters widened by 1e-3.
 template <typename T>
-__device__ __forceinline__ void cull_pair_f32(const KParams<T> &p, const T pos[3], const float Rm[9], const T ob[7],
-                                              bool is_cap, int &hit, bool &in_view) {
+__device__ __forceinline__ void cull_pair_rec(const KParams<T> &p, const float prel[3], const float Rm[9], float4 q0,
+                                              float4 q1, bool is_cap, int &hit, bool &in_view) {
     const float eps = 2e-3f;
     const float cull = (float)p.radar_max_dist * 1.0001f + eps;
-    float rad, dist;
-    float q0[3], q1[3];
+    const float rad = q0.w;
+    float dist;
+    float e0[3], e1[3];       // end points of the reachable part of the obstacle axis relative to the vehicle, NED
     bool axis_out = false;
+    const float oa[3] = {prel[0] - q0.x, prel[1] - q0.y, prel[2] - q0.z};
     if (is_cap) {
-        float ba[3], oa[3], oc2[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            ba[c] = (float)(ob[3 + c] - ob[c]);
-            oa[c] = (float)(pos[c] - ob[c]);
-            oc2[c] = (float)(pos[c] - ob[3 + c]);
-        }
-        rad = (float)ob[6];
+        const float ba[3] = {q1.x, q1.y, q1.z};
+        const float inv_n = q1.w;
         const float baba = ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2];
         const float baoa = oa[0] * ba[0] + oa[1] * ba[1] + oa[2] * ba[2];
         const float oaoa = oa[0] * oa[0] + oa[1] * oa[1] + oa[2] * oa[2];
-        const float inv_n = rsqrtf(baba);
-        const float sp = -baoa * inv_n;
-        const float tp = (oc2[0] * ba[0] + oc2[1] * ba[1] + oc2[2] * ba[2]) * inv_n;
+        const float sp = -baoa * inv_n;                   // (bot - pos) . d
+        const float tp = (baoa - baba) * inv_n;           // (pos - top) . d
         float hh = sp;
         if (tp > hh || tp != tp) hh = tp;
         if (0.0f > hh) hh = 0.0f;
@@ -579,40 +687,29 @@ __device__ __forceinline__ void cull_pair_f32(const KParams<T> &p, const T pos[3
         axis_out |= s_lo > s_hi;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            q0[c] = s_lo * ba[c] - oa[c];
-            q1[c] = s_hi * ba[c] - oa[c];
+            e0[c] = s_lo * ba[c] - oa[c];
+            e1[c] = s_hi * ba[c] - oa[c];
         }
     } else {
-        float d2 = 0.0f;
+        dist = sqrtf(oa[0] * oa[0] + oa[1] * oa[1] + oa[2] * oa[2]);
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const float oc = (float)(pos[c] - ob[c]);
-            d2 += oc * oc;
-            q0[c] = q1[c] = -oc;
-        }
-        rad = (float)ob[3];
-        dist = sqrtf(d2);
+        for (int c = 0; c < 3; c++) e0[c] = e1[c] = -oa[c];
     }
     const float thr = rad + (float)p.safety_radius;
     hit = (dist <= thr - eps) ? 1 : ((dist > thr + eps) ? 0 : 2);        // NaN -> 2
     bool outside = (dist - rad > cull) || axis_out;
     {
-        float a0[3], a1[3];
+        float a0[3], a1[3];    // body-frame coordinates R^T e
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            a0[c] = Rm[c] * q0[0] + Rm[3 + c] * q0[1] + Rm[6 + c] * q0[2];
-            a1[c] = Rm[c] * q1[0] + Rm[3 + c] * q1[1] + Rm[6 + c] * q1[2];
+            a0[c] = Rm[c] * e0[0] + Rm[3 + c] * e0[1] + Rm[6 + c] * e0[2];
+            a1[c] = Rm[c] * e1[0] + Rm[3 + c] * e1[1] + Rm[6 + c] * e1[2];
         }
-        // same half-space tests as obstacle_pair; the float error of a signed distance (~1e-6 * 60 m) and of the
-        // converted plane slopes (~6e-8 * 40 m) is far inside the eps added to the radius
+        // the float error of a signed distance (~1e-6 * 60 m) and of the converted plane slopes (~6e-8 * 40 m) is far
+        // inside the eps added to the radius
         const float rm = rad * 1.0001f + eps;
         const float ty = (float)p.fov_ty, tz = (float)p.fov_tz;
         const float ry = rm * (float)p.fov_ny, rz = rm * (float)p.fov_nz;
-#if DOCKAUV_CULL_CLIP
-        // an axis point can carry a surface point inside the pyramid only if it is within r of the inner side of ALL
-        // five planes; each signed distance is linear along the axis, so each plane keeps an interval of the segment
-        // parameter and the obstacle is out of view when their intersection is empty (this also catches segments that
-        // leave the pyramid through different planes).  Crossing parameters widened by 1e-3.
         float t_lo = 0.0f, t_hi = 1.0f;
         bool empty = false;
         auto clip = [&](float g0, float g1) {            // keep { t : g0 + t (g1 - g0) <= 0 }
@@ -631,15 +728,21 @@ __device__ __forceinline__ void cull_pair_f32(const KParams<T> &p, const T pos[3
         clip(a0[2] - tz * a0[0] - rz, a1[2] - tz * a1[0] - rz);
         clip(-a0[2] - tz * a0[0] - rz, -a1[2] - tz * a1[0] - rz);
         outside |= empty || (t_lo > t_hi);
-#else
-        outside |= (a0[0] < -rm) && (a1[0] < -rm);
-        outside |= (a0[1] - ty * a0[0] > ry) && (a1[1] - ty * a1[0] > ry);
-        outside |= (-a0[1] - ty * a0[0] > ry) && (-a1[1] - ty * a1[0] > ry);
-        outside |= (a0[2] - tz * a0[0] > rz) && (a1[2] - tz * a1[0] > rz);
-        outside |= (-a0[2] - tz * a0[0] > rz) && (-a1[2] - tz * a1[0] > rz);
-#endif
     }
     in_view = !outside;
+}
+
+// The float obstacle record of cull_pair_rec from an obstacle as stored (capsule: bot[3] top[3] r; sphere: c[3] r) and
+// the goal; differences are formed in double and rounded once.
+__device__ __forceinline__ void obstacle_record_f32(const double ob[7], const double goal[3], bool is_cap, float4 &q0,
+                                                    float4 &q1) {
+    q0 = make_float4((float)(ob[0] - goal[0]), (float)(ob[1] - goal[1]), (float)(ob[2] - goal[2]), (float)(is_cap ? ob[6] : ob[3]));
+    if (is_cap) {
+        const double b[3] = {ob[3] - ob[0], ob[4] - ob[1], ob[5] - ob[2]};
+        q1 = make_float4((float)b[0], (float)b[1], (float)b[2], (float)rsqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]));
+    } else {
+        q1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
 }
 
 // shape.py:341-390 for one ray: infinite-cylinder root, body hit if 0 < y < baba, else end-cap sphere.

@@ -6,6 +6,51 @@
 namespace dockauv {
 
 // ------------------------------------------------------------------------------------------- reset
+// Float obstacle records of env i for the cull launch (KParams::obsf, see cull_pair_rec), from the obstacles and the
+// goal as they are stored (T).  Capsule k -> slots 2k, 2k+1; sphere s -> slot 2 n_caps + s.
+template <typename T>
+__device__ __forceinline__ void store_capsule_record(const KParams<T> &p, int64_t i, int k, const T cap[7], const T goal[3]) {
+    if (p.obsf == nullptr) return;
+    const double ob[7] = {(double)cap[0], (double)cap[1], (double)cap[2], (double)cap[3], (double)cap[4], (double)cap[5], (double)cap[6]};
+    const double g[3] = {(double)goal[0], (double)goal[1], (double)goal[2]};
+    float4 q0, q1;
+    obstacle_record_f32(ob, g, true, q0, q1);
+    p.obsf[(int64_t)(2 * k) * p.n_envs + i] = q0;
+    p.obsf[(int64_t)(2 * k + 1) * p.n_envs + i] = q1;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_sphere_record(const KParams<T> &p, int64_t i, int s, const T sph[4], const T goal[3]) {
+    if (p.obsf == nullptr) return;
+    const double ob[7] = {(double)sph[0], (double)sph[1], (double)sph[2], (double)sph[3], 0.0, 0.0, 0.0};
+    const double g[3] = {(double)goal[0], (double)goal[1], (double)goal[2]};
+    float4 q0, q1;
+    obstacle_record_f32(ob, g, false, q0, q1);
+    p.obsf[(int64_t)(2 * p.n_caps + s) * p.n_envs + i] = q0;
+}
+
+// Rebuilds the float obstacle records of env i from the bound buffers (after the caller wrote obstacles or goals itself:
+// dockauv_refresh_obstacles).
+template <typename T>
+__global__ void refresh_obstacles_kernel(const __grid_constant__ KParams<T> p) {
+    const int64_t N = p.n_envs;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const T goal[3] = {p.goal[i], p.goal[N + i], p.goal[2 * N + i]};
+    for (int k = 0; k < p.n_caps; k++) {
+        T cap[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) cap[j] = p.capsules[(int64_t)(k * 7 + j) * N + i];
+        store_capsule_record<T>(p, i, k, cap, goal);
+    }
+    for (int s = 0; s < p.n_sph; s++) {
+        T sph[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) sph[j] = p.spheres[(int64_t)(s * 4 + j) * N + i];
+        store_sphere_record<T>(p, i, s, sph, goal);
+    }
+}
+
 // BaseDocking3d.reset (docking3d.py:222-322) + <Scenario>.generate_environment (:803-988) for env i.
 // Distributions are the reference's; the random stream is Philox4x32-10 keyed by (seed, global env id,
 // episode) instead of the reference's global MT19937 (DESIGN.md "reset").  Draw slots: 0 heading, 1-3
@@ -27,6 +72,27 @@ static __device__ __noinline__ void reset_env(const KParams<T> &p, int64_t i) {
     auto U = [&](uint32_t idx) { return uu[idx]; };
 
     double goal[3] = {0.0, 0.0, 0.0};
+    // obstacle rows (T) + their float records for the cull launch; the goal is final before the first obstacle is stored
+    auto put_capsule = [&](int k, const double cap[7]) {
+        T c[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            c[j] = (T)cap[j];
+            p.capsules[(int64_t)(k * 7 + j) * N + i] = c[j];
+        }
+        const T g[3] = {(T)goal[0], (T)goal[1], (T)goal[2]};
+        store_capsule_record<T>(p, i, k, c, g);
+    };
+    auto put_sphere = [&](int k, const double sph[4]) {
+        T c[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            c[j] = (T)sph[j];
+            p.spheres[(int64_t)(k * 4 + j) * N + i] = c[j];
+        }
+        const T g[3] = {(T)goal[0], (T)goal[1], (T)goal[2]};
+        store_sphere_record<T>(p, i, k, c, g);
+    };
     double heading = (U(0) - 0.5) * PI;                                   // :814
     double r[3] = {U(1) - 0.5, U(2) - 0.5, U(3) - 0.5};                   // :694-696
     {
@@ -52,8 +118,7 @@ static __device__ __noinline__ void reset_env(const KParams<T> &p, int64_t i) {
         heading = (double)ssa<double>(atan2(0.0 - goal[1], 0.0 - goal[0]));
         if (scn != DOCKAUV_SCN_OBSTACLES_NOCAP && kc < p.n_caps) {
             const double cap[7] = {0, 0, 2.0, 0, 0, -2.0, 1.0};          // bot = 2*position - top, shape.py:105-108
-#pragma unroll
-            for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+            put_capsule(kc, cap);
             kc++;
         }
     }
@@ -66,15 +131,13 @@ static __device__ __noinline__ void reset_env(const KParams<T> &p, int64_t i) {
             double x = c * 6, y = s * 6;
             theta += 2 * PI / 4;
             const double cap[7] = {x, y, half, x, y, -half, 1.0};
-#pragma unroll
-            for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+            put_capsule(kc, cap);
             kc++;
         }
     }
     for (; kc < p.n_caps; kc++) {   // unused capsule slots: park far away with zero radius (never hit, never collide)
         const double cap[7] = {1e6, 1e6, 1e6, 1e6, 1e6, 1e6 + 1.0, 0.0};
-#pragma unroll
-        for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+        put_capsule(kc, cap);
     }
     double cur[5] = {0, 0, 0, 0, 0};
     if (scn == DOCKAUV_SCN_SIMPLE_CURRENT || scn == DOCKAUV_SCN_CAPSULE_CURRENT || scn == DOCKAUV_SCN_OBSTACLES_CURRENT) {
@@ -91,16 +154,12 @@ static __device__ __noinline__ void reset_env(const KParams<T> &p, int64_t i) {
         double rr = 4.0 + 6.0 * U(15 + 3 * ks);
         double q = sqrt(1 - z * z), s, c;
         sincos(az, &s, &c);
-        p.spheres[(int64_t)(ks * 4 + 0) * N + i] = (T)(rr * q * c);
-        p.spheres[(int64_t)(ks * 4 + 1) * N + i] = (T)(rr * q * s);
-        p.spheres[(int64_t)(ks * 4 + 2) * N + i] = (T)(rr * z);
-        p.spheres[(int64_t)(ks * 4 + 3) * N + i] = (T)1.0;
+        const double sph[4] = {rr * q * c, rr * q * s, rr * z, 1.0};
+        put_sphere(ks, sph);
     }
     for (; ks < p.n_sph; ks++) {
-        p.spheres[(int64_t)(ks * 4 + 0) * N + i] = (T)1e6;
-        p.spheres[(int64_t)(ks * 4 + 1) * N + i] = (T)1e6;
-        p.spheres[(int64_t)(ks * 4 + 2) * N + i] = (T)1e6;
-        p.spheres[(int64_t)(ks * 4 + 3) * N + i] = (T)0.0;
+        const double sph[4] = {1e6, 1e6, 1e6, 0.0};
+        put_sphere(ks, sph);
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -148,13 +207,45 @@ __device__ __forceinline__ void reset_env_warp(const KParams<T> &p, int64_t i, i
         v[r] = (idx & 1) ? b : a;
     }
     const bool has_goal_ring = scn >= DOCKAUV_SCN_CAPSULE;
+    // the goal (draws 7 and 8) on every lane: the float obstacle records are relative to it
+    double goal[3] = {0.0, 0.0, 0.0};
+    {
+        const double u7 = __shfl_sync(0xffffffffu, u[1], 3), u8 = __shfl_sync(0xffffffffu, u[0], 4);
+        if (has_goal_ring) {                                                   // :860-886
+            double theta = u7 * 2 * PI;
+            double radius = 1.0 + (double)p.safety_radius;
+            double s, c;
+            sincos(theta, &s, &c);
+            goal[0] = c * radius;
+            goal[1] = s * radius;
+            goal[2] = (u8 - 0.5) * 4.0;
+        }
+    }
+    const T goal_t[3] = {(T)goal[0], (T)goal[1], (T)goal[2]};
+    auto put_capsule = [&](int k, const double cap[7]) {
+        T c[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            c[j] = (T)cap[j];
+            p.capsules[(int64_t)(k * 7 + j) * N + i] = c[j];
+        }
+        store_capsule_record<T>(p, i, k, c, goal_t);
+    };
+    auto put_sphere = [&](int k, const double sph[4]) {
+        T c[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            c[j] = (T)sph[j];
+            p.spheres[(int64_t)(k * 4 + j) * N + i] = c[j];
+        }
+        store_sphere_record<T>(p, i, k, c, goal_t);
+    };
     const bool has_dock = has_goal_ring && scn != DOCKAUV_SCN_OBSTACLES_NOCAP && p.n_caps > 0;
     const bool has_pillars = scn >= DOCKAUV_SCN_OBSTACLES;
     const int first_pillar = has_dock ? 1 : 0;
     const int n_pillars = has_pillars ? max(0, min(4, p.n_caps - first_pillar)) : 0;
     if (lane == 0) {
         p.episode[i] = (int32_t)(ep + 1);
-        double goal[3] = {0.0, 0.0, 0.0};
         double heading = (v[0] - 0.5) * PI;                                   // :814
         double r[3] = {v[1] - 0.5, v[2] - 0.5, v[3] - 0.5};                   // :694-696
         {
@@ -166,16 +257,7 @@ __device__ __forceinline__ void reset_env_warp(const KParams<T> &p, int64_t i, i
         double max_att = (double)p.max_attitude;
         double att[3] = {(v[4] - 0.5) * 2 * (max_att * 0.7), (v[5] - 0.5) * 2 * (max_att * 0.7),
                          (v[6] - 0.5) * 2 * PI};                               // :699-703
-        if (has_goal_ring) {                                                   // :860-886
-            double theta = v[7] * 2 * PI;
-            double radius = 1.0 + (double)p.safety_radius;
-            double s, c;
-            sincos(theta, &s, &c);
-            goal[0] = c * radius;
-            goal[1] = s * radius;
-            goal[2] = (v[8] - 0.5) * 4.0;
-            heading = (double)ssa<double>(atan2(0.0 - goal[1], 0.0 - goal[0]));
-        }
+        if (has_goal_ring) heading = (double)ssa<double>(atan2(0.0 - goal[1], 0.0 - goal[0]));
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             p.state[(int64_t)c * N + i] = (T)pos[c];
@@ -197,20 +279,16 @@ __device__ __forceinline__ void reset_env_warp(const KParams<T> &p, int64_t i, i
             sincos(theta, &s, &c);
             const double x = c * 6, y = s * 6;
             const double cap[7] = {x, y, half, x, y, -half, 1.0};
-            const int kc = first_pillar + k;
-#pragma unroll
-            for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+            put_capsule(first_pillar + k, cap);
         }
     } else if (lane == 5) {
         if (has_dock) {
             const double cap[7] = {0, 0, 2.0, 0, 0, -2.0, 1.0};              // bot = 2*position - top, shape.py:105-108
-#pragma unroll
-            for (int j = 0; j < 7; j++) p.capsules[(int64_t)j * N + i] = (T)cap[j];
+            put_capsule(0, cap);
         }
         for (int kc = first_pillar + n_pillars; kc < p.n_caps; kc++) {         // unused slots: far away, zero radius
             const double cap[7] = {1e6, 1e6, 1e6, 1e6, 1e6, 1e6 + 1.0, 0.0};
-#pragma unroll
-            for (int j = 0; j < 7; j++) p.capsules[(int64_t)(kc * 7 + j) * N + i] = (T)cap[j];
+            put_capsule(kc, cap);
         }
     } else if (lane <= 13) {
         const int ks = lane - 6;
@@ -220,15 +298,11 @@ __device__ __forceinline__ void reset_env_warp(const KParams<T> &p, int64_t i, i
             double rr = 4.0 + 6.0 * v[2];
             double q = sqrt(1 - z * z), s, c;
             sincos(az, &s, &c);
-            p.spheres[(int64_t)(ks * 4 + 0) * N + i] = (T)(rr * q * c);
-            p.spheres[(int64_t)(ks * 4 + 1) * N + i] = (T)(rr * q * s);
-            p.spheres[(int64_t)(ks * 4 + 2) * N + i] = (T)(rr * z);
-            p.spheres[(int64_t)(ks * 4 + 3) * N + i] = (T)1.0;
+            const double sph[4] = {rr * q * c, rr * q * s, rr * z, 1.0};
+            put_sphere(ks, sph);
         } else if (ks < p.n_sph) {
-            p.spheres[(int64_t)(ks * 4 + 0) * N + i] = (T)1e6;
-            p.spheres[(int64_t)(ks * 4 + 1) * N + i] = (T)1e6;
-            p.spheres[(int64_t)(ks * 4 + 2) * N + i] = (T)1e6;
-            p.spheres[(int64_t)(ks * 4 + 3) * N + i] = (T)0.0;
+            const double sph[4] = {1e6, 1e6, 1e6, 0.0};
+            put_sphere(ks, sph);
         }
     } else if (lane == 14) {
         double cur[5] = {0, 0, 0, 0, 0};

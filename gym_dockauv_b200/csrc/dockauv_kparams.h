@@ -3,6 +3,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <vector_types.h>
+
 #include "../../include/dockauv.h"
 
 namespace dockauv {
@@ -55,17 +57,27 @@ struct KParams {
     int32_t *ep_len_out;
     // debug outputs
     T *dbg_ray_dist, *dbg_reward_arr, *dbg_euler_dot, *dbg_nu_c, *dbg_nav, *dbg_obs, *dbg_state_dot;
-    // hand-off between the two launches of the split layout (library-owned): T[22][n_envs] + u32[n_envs]
-    T *handoff;
-    uint32_t *handoff_cond;
-    int64_t split_chunk;
-    // pipeline layout (library-owned): per-env view word (in-view mask | collision | listed), compact list of the envs
-    // the ray launch has to visit (local env index | mask << 32), its counter(s), obstacle-avoidance sums
-    uint32_t *view_info;
+    // pipeline layout (library-owned buffers):
+    //   rec      T[n_envs][16], one 16-word record per env written by the dynamics launch (AoS: the ray launch reads
+    //            it with one request per warp): 0..5 sin/cos of the post-step attitude (sphi cphi sth cth spsi cpsi),
+    //            6..8 post-step position relative to the goal, 9 (r0+r1)+(r2+r3), 10 r4+r5, 11 r7 (reward terms that
+    //            need no radar, already combined in numpy's summation order), 12 log_precision(delta_d), 13 delta_d,
+    //            14 done-condition bits 0..2 as a number, 15 NaN poison word (0 for a finite pose)
+    //   obsf     float4[n_obsf][n_envs]: float copy of the obstacles RELATIVE TO THE GOAL for the cull (written by every
+    //            reset and by dockauv_refresh_obstacles): capsule k -> slots 2k (bot - goal, radius), 2k+1 (top - bot,
+    //            1/|top - bot|); sphere s -> slot 2 n_caps + s (centre - goal, radius)
+    //   view_list / view_count: work lists of the ray launch, two counters per concurrently stepped range: envs with
+    //            something in view from the front (local env index | in-view mask << 32 | condition bits << 48), envs
+    //            whose episode ended in the cull launch from the back
+    int64_t chunk_envs;             // > 0: the launches of a step are issued per chunk of this many envs
+    T *rec;
+    float4 *obsf;
+    int32_t n_obsf, cull_exact;      // cull_exact: coordinates too large for the float cull -> decide everything in T
     unsigned long long *view_list;
     unsigned int *view_count;
-    T *oa_dot;
     int32_t sm_count;
+    int32_t sparse_minv;             // M_inv has only the z_G pattern (diagonal + [0,4] [4,0] [1,3] [3,1]) filled in
+    T *delta_d_out;
     // stats accumulator (double[DOCKAUV_N_STATS])
     double *stats;
     // ray table in global memory (handle-owned): rd_b[3][n_rays] then beta_oa[n_rays].  It is not part of this block:

@@ -17,4 +17,8 @@ cudaError_t launch_step(const KParams<T> &k, int vehicle, int layout, cudaStream
 template <typename T>
 cudaError_t launch_reset(const KParams<T> &k, const uint8_t *mask_dev, cudaStream_t st);
 
+// float obstacle records of the cull launch from the bound obstacle / goal buffers (no-op for handles without them)
+template <typename T>
+cudaError_t launch_refresh_obstacles(const KParams<T> &k, cudaStream_t st);
+
 }  // namespace dockauv

@@ -1,27 +1,37 @@
-// dockauv_step_pipe.cuh -- layout DOCKAUV_LAYOUT_PIPELINE: one batched step as four specialised launches.
+// dockauv_step_pipe.cuh -- layout DOCKAUV_LAYOUT_PIPELINE (default): one batched step as three specialised launches.
 //
-//   1. dynamics   step_warp_kernel<MODE 1> (dockauv_step_warp.cuh): thread per env, writes the post-step pose and the
-//                 radar-independent reward terms to the hand-off buffer.
-//   2. cull       cull_kernel: thread per env.  Walks over the env's obstacles (coalesced SoA loads), does the body
-//                 collision test and the range / field-of-view culls -- in float with conservative slack, the collision
-//                 re-decided in T when it is within 2 mm of the threshold (cull_pair_f32) -- and appends the envs that
-//                 have anything in view (28 % of them on the C4 workload) to a compact list.
-//   3. rays       rays_kernel: persistent grid, one warp per LISTED env (lanes = rays), data of the next list entry
-//                 prefetched while the current one is cast.  Writes the pooled ray cells of the observation row and the
-//                 obstacle-avoidance sum.
-//   4. finish     finish_kernel: thread per env: reward, done, counters, statistics, observation cells of envs with an
-//                 empty view; the ~1 % of envs whose episode ended are compacted per CTA and re-initialised by
-//                 neighbouring threads instead of one lane per warp.
+//   1. dynamics     dynamics_kernel: thread per env.  Current, command filter, RKF45, angle wrap, navigation errors,
+//                   obs[0:16], done conditions 0..2, the reward terms that need no radar.  Leaves one 16-word record
+//                   per env (KParams::rec): post-step attitude sines / cosines, position relative to the goal, the
+//                   reward terms already combined in numpy's summation order, delta_d, condition bits.
+//   2. cull+finish  cull_finish_kernel: thread per env.  Walks over the env's obstacles in FLOAT (float4 records
+//                   relative to the goal, written at reset; cull_pair_rec): body collision (re-decided in T when within
+//                   2 mm of the threshold) and the range / field-of-view culls.  Envs with something in view (24 % on
+//                   the C4 workload) are appended to a compact list.  Done flag, condition bits and counters are final
+//                   here for EVERY env (coalesced stores); an env with nothing in view is finished completely -- all ray
+//                   cells read max_dist, r_oa = 0: reward, running return, statistics -- and goes on a second list if
+//                   its episode ended.  No shared memory, no barrier.
+//   3. rays+finish  rays_finish_kernel: persistent grid, one warp per LISTED env (lanes = rays), data of the next list
+//                   entry in flight while the current one is cast (radar_env, dockauv_rays.cuh); the warp then writes the
+//                   reward with its obstacle-avoidance term and the running return.  Afterwards the warps of the grid
+//                   share the ended episodes of both lists: terminal-observation row, re-initialisation (one warp each).
 //
-// Each launch has its own register budget and occupancy (the fused / split kernels carry the radar's ~90 registers
-// through everything and run at 4 warps per scheduler), the ray warps never idle on envs with nothing in view, and the
-// three thread-per-env launches are plain data-parallel code.  Results are identical to the other layouts (same
-// device functions, same order of operations per env); debug outputs are served by the fused kernel.
+// Each launch has its own register budget and occupancy, the ray warps never idle on envs with nothing in view, and no
+// env is touched by a launch that has nothing to do for it (round 1 had a fourth launch that re-read every env's
+// hand-off just to finish it).  Results are identical to the other layouts (same device functions, same order of
+// operations per env); debug outputs are served by the fused kernel.
 #pragma once
 #include "dockauv_step_warp.cuh"
 
 namespace dockauv {
 
+#ifndef DOCKAUV_DYN_THREADS
+#define DOCKAUV_DYN_THREADS 128     // CTA size of the dynamics launch
+#endif
+#ifndef DOCKAUV_MINB_A
+#define DOCKAUV_MINB_A 4            // its min-CTAs hint: (128, 4) = 128 registers, 16 warps per SM
+#endif
+constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #ifndef DOCKAUV_MINB_CULL
 #define DOCKAUV_MINB_CULL 4
 #endif
@@ -32,32 +42,340 @@ namespace dockauv {
 #define DOCKAUV_MINB_RAYS 4
 #endif
 
-// ------------------------------------------------------------------------------------------------------- 2. cull
+constexpr int kListCounters = 2;    // work-list counters per stepped env range (see cull_finish_kernel)
+
+// ---- the per-env record written by the dynamics launch
+constexpr int kRecWords = 16;
+constexpr int REC_TRIG = 0, REC_PREL = 6, REC_A = 9, REC_B = 10, REC_R7 = 11, REC_LPD = 12, REC_DD = 13, REC_COND = 14,
+              REC_POISON = 15;
+
+// 16-byte vector access to a record: double -> 8 x double2, float -> 4 x float4
 template <typename T>
-__global__ void __launch_bounds__(256, DOCKAUV_MINB_CULL) cull_kernel(const __grid_constant__ KParams<T> p) {
-    const int64_t N = p.n_envs;
-    const int64_t i = p.env_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < p.env_end;
-    T pos[3] = {T(0), T(0), T(0)}, Rm[9] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)}, poison = T(0);
-    if (active) {
-        const T *hf = p.handoff + i;
+struct RecIO;
+template <>
+struct RecIO<double> {
+    static constexpr int kVecWords = 2;
+    static __device__ __forceinline__ void store(double *dst, const double w[kRecWords]) {
+        double2 *d = reinterpret_cast<double2 *>(dst);
 #pragma unroll
-        for (int c = 0; c < 3; c++) pos[c] = hf[(int64_t)c * N];
-#pragma unroll
-        for (int c = 0; c < 9; c++) Rm[c] = hf[(int64_t)(3 + c) * N];
-        poison = hf[(int64_t)12 * N];
+        for (int c = 0; c < 8; c++) d[c] = make_double2(w[2 * c], w[2 * c + 1]);
     }
-    cull_env<T>(p, i, active, pos, Rm, poison);
+    // words [2 * first_vec, 2 * (first_vec + n_vec))
+    template <int FIRST, int COUNT>
+    static __device__ __forceinline__ void load(const double *src, double *w) {
+        const double2 *s = reinterpret_cast<const double2 *>(src);
+#pragma unroll
+        for (int c = 0; c < COUNT; c++) {
+            const double2 v = s[FIRST + c];
+            w[2 * c] = v.x;
+            w[2 * c + 1] = v.y;
+        }
+    }
+};
+template <>
+struct RecIO<float> {
+    static constexpr int kVecWords = 4;
+    static __device__ __forceinline__ void store(float *dst, const float w[kRecWords]) {
+        float4 *d = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+        for (int c = 0; c < 4; c++) d[c] = make_float4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    }
+    // same word ranges as the double version: FIRST / COUNT are in units of two words
+    template <int FIRST, int COUNT>
+    static __device__ __forceinline__ void load(const float *src, float *w) {
+        const float2 *s = reinterpret_cast<const float2 *>(src);
+#pragma unroll
+        for (int c = 0; c < COUNT; c++) {
+            const float2 v = s[FIRST + c];
+            w[2 * c] = v.x;
+            w[2 * c + 1] = v.y;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------- 1. dynamics
+// CUR: the ocean current is evaluated (scenario with a current, injected current or noise); SPM: sparse M_inv.
+template <typename T, int VEH, int NU, bool CUR, bool SPM>
+__global__ void
+#ifdef DOCKAUV_DYN_MAXNREG
+__maxnreg__(DOCKAUV_DYN_MAXNREG)
+#else
+__launch_bounds__(kDynThreads, DOCKAUV_MINB_A)
+#endif
+dynamics_kernel(const __grid_constant__ KParams<T> p) {
+    const int64_t N = p.n_envs;
+    const int64_t i = p.env_begin + (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
+    // the cull launch appends to a list: this launch empties it
+    if (p.view_count != nullptr && blockIdx.x == 0 && threadIdx.x < kListCounters) p.view_count[threadIdx.x] = 0u;
+    prefetch_dynamics_inputs<T, NU>(p, i, threadIdx.x & 31, true);
+    if (i >= p.env_end) return;
+
+    T y[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
+    T tr0[6];
+    Mth<T>::sincos_(y[0], &tr0[0], &tr0[1]);
+    Mth<T>::sincos_(y[1], &tr0[2], &tr0[3]);
+    Mth<T>::sincos_(y[2], &tr0[4], &tr0[5]);
+    T nu_c[3] = {T(0), T(0), T(0)};
+    if (CUR) dyn_current<T>(p, i, tr0, nu_c);
+    T tau[6], penalty;
+    {
+        T u[NU];
+        penalty = command_and_penalty<T, NU>(p, i, u);
+#pragma unroll
+        for (int k = 0; k < NU; k++) p.u_prev[(int64_t)k * N + i] = u[k];
+        dyn_tau<T, VEH, NU>(p, u, tau);
+    }
+    T pacc[3], tr1[6];
+    rkf45_step<T, VEH, SPM, CUR>(p, y, tr0, tau, nu_c, pacc, tr1);
+#pragma unroll
+    for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
+    // position and goal are only needed from here on (their lines were prefetched into L2 by an earlier CTA): loading
+    // them now keeps twelve registers free during the integration
+    T pos[3], goal[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
+#pragma unroll
+    for (int c = 0; c < 3; c++) goal[c] = p.goal[(int64_t)c * N + i];
+#pragma unroll
+    for (int c = 0; c < 3; c++) pos[c] += pacc[c];
+#pragma unroll
+    for (int c = 0; c < 3; c++) p.state[(int64_t)c * N + i] = pos[c];
+#pragma unroll
+    for (int c = 0; c < 9; c++) p.state[(int64_t)(3 + c) * N + i] = y[c];
+
+    DynOut<T> q;
+    dyn_outputs<T>(p, pos, y, tr1, goal, nu_c, penalty, q);
+    // obs[0:16] goes straight to its HBM row (four 16-byte stores); a later launch zeroes the row if the env is reset
+    if ((p.n_obs & 3) == 0) {
+        float4 *orow4 = reinterpret_cast<float4 *>(p.obs + i * p.n_obs);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            orow4[c] = make_float4((float)q.o[4 * c], (float)q.o[4 * c + 1], (float)q.o[4 * c + 2], (float)q.o[4 * c + 3]);
+    } else {
+        float *orow = p.obs + i * p.n_obs;
+#pragma unroll
+        for (int c = 0; c < 16; c++) orow[c] = (float)q.o[c];
+    }
+    T w[kRecWords];
+#pragma unroll
+    for (int c = 0; c < 6; c++) w[REC_TRIG + c] = tr1[c];
+#pragma unroll
+    for (int c = 0; c < 3; c++) w[REC_PREL + c] = pos[c] - goal[c];
+    // np.sum of the 13 reward terms is ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) + r8 + .. + r12 (reward_sum13): the two
+    // sums that need no radar are formed here, in that order
+    w[REC_A] = (q.r[0] + q.r[1]) + (q.r[2] + q.r[3]);
+    w[REC_B] = q.r[4] + q.r[5];
+    w[REC_R7] = q.r[7];
+    w[REC_LPD] = q.r[6];
+    w[REC_DD] = q.delta_d;
+    w[REC_COND] = (T)q.cond;
+    // 0 for a finite pose, NaN otherwise: added to every ray distance so that a blown-up state poisons the radar
+    // outputs exactly like the reference's NaN propagation does
+    w[REC_POISON] = (((pos[0] + pos[1]) + (pos[2] + y[0])) + (y[1] + y[2])) * T(0);
+    RecIO<T>::store(p.rec + i * kRecWords, w);
 }
 
-// ------------------------------------------------------------------------------------------------------- 3. rays
+// ------------------------------------------------------------------------------------------------------- finish
+// is_done (docking3d.py:597-631): the five condition bits once the collision flag is known; t_steps is the counter before
+// its increment (:612 is evaluated pre-increment, so max_timesteps = 1000 ends an episode at step 1001)
+template <typename T>
+__device__ __forceinline__ uint32_t done_conditions(const KParams<T> &p, uint32_t cond012, int32_t t_steps, bool collision) {
+    return cond012 | ((t_steps >= p.max_timesteps) ? 8u : 0u) | (collision ? 16u : 0u);
+}
+
+// reward_step (docking3d.py:560-595) from the record words of the dynamics launch and the radar term r_oa
+// (Reward.obstacle_avoidance, :767-792).  np.sum's order for 13 terms: ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) + r8 .. r12.
+template <typename T>
+__device__ __forceinline__ T step_reward(const KParams<T> &p, T A, T B, T r7, T lp_d, T r_oa, uint32_t cond) {
+    T r6;
+    if (p.reward_set == 1) r6 = -p.w_oa * r_oa;
+    else r6 = -p.w_oa * cont_goal_constraints<T>(Mth<T>::abs_(r_oa), T(1), lp_d);
+    T reward = A + (B + (r6 + r7));
+#pragma unroll
+    for (int k = 0; k < 5; k++) reward += ((cond >> k) & 1u) ? p.w_done[k] : T(0);
+    return reward;
+}
+
+// One warp ends the episode of env ie: the last observation is kept as terminal_observation, the all-zero reset
+// observation is handed back (docking3d.py:269,322) and the env is re-initialised.  Called by all 32 lanes.
+template <typename T>
+__device__ __forceinline__ void end_episode_warp(const KParams<T> &p, int64_t ie, int lane) {
+    const int n_obs = p.n_obs;
+    float *row = p.obs + ie * n_obs;
+    float *trow = p.terminal_obs ? p.terminal_obs + ie * n_obs : nullptr;
+    for (int c = lane; c < n_obs; c += 32) {
+        if (trow) trow[c] = row[c];
+        if (p.auto_reset) row[c] = 0.0f;
+    }
+    if (p.auto_reset) reset_env_warp<T>(p, ie, lane);
+}
+
+// The two work lists of a stepped env range share one array of n entries (KParams::view_list): entries of envs with
+// something in view grow from the front (counter 0), envs whose episode ended in the cull launch from the back (counter 1).
+//   entry: bits 0..31 env index within the range, 32..47 in-view mask (capsules first), 48..52 done-condition bits
+// ------------------------------------------------------------------------------------------------------- 2. cull + finish
+constexpr int kCullThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_kernel(const __grid_constant__ KParams<T> p) {
+    const int64_t N = p.n_envs;
+    const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kCullThreads;
+    const int64_t i = i0 + threadIdx.x;
+    const bool active = i < p.env_end;
+    const int lane = threadIdx.x & 31;
+    WarpStats bs;
+    bool listed = false, ended = false;      // ended: episode over and nothing in view -> re-initialised by the ray launch's warps
+    uint32_t info = 0;                       // bits 0..15 in-view mask (capsules first), 16 collision
+    uint32_t cond = 0;
+    if (active) {
+        const T *rec = p.rec + i * kRecWords;
+        const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
+        // everything this thread reads besides the obstacle records, requested up front
+        T w[10], wc[2], wf[4];
+        RecIO<T>::template load<0, 5>(rec, w);       // trig, prel, A
+        RecIO<T>::template load<7, 1>(rec, wc);      // cond, poison
+        RecIO<T>::template load<5, 2>(rec, wf);      // B, r7, lp_d, delta_d
+        const int32_t t_steps = p.t_steps[i];
+        const T ep_return = p.ep_return[i];
+        const T A = w[REC_A], poison = wc[1];
+        if (n_obst > 0 && !p.cull_exact) {
+            // ---- float culls + collision pre-test (cull_pair_rec)
+            float Rf[9], prel[3];
+            rzyx<float>((float)w[0], (float)w[1], (float)w[2], (float)w[3], (float)w[4], (float)w[5], Rf);
+#pragma unroll
+            for (int c = 0; c < 3; c++) prel[c] = (float)w[REC_PREL + c];
+            // the next obstacle's record is requested before the current one is evaluated
+            const float4 *ob = p.obsf + i;
+            float4 q0 = ob[0], q1 = n_caps > 0 ? ob[N] : make_float4(0.f, 0.f, 0.f, 0.f);
+            int slot = n_caps > 0 ? 2 : 1;
+#pragma unroll 1
+            for (int k = 0; k < n_obst; k++) {
+                const bool is_cap = k < n_caps;
+                const float4 c0 = q0, c1 = q1;
+                if (k + 1 < n_obst) {
+                    q0 = ob[(int64_t)slot * N];
+                    if (k + 1 < n_caps) q1 = ob[(int64_t)(slot + 1) * N];
+                    slot += (k + 1 < n_caps) ? 2 : 1;
+                }
+                int hit3;
+                bool view;
+                cull_pair_rec<T>(p, prel, Rf, c0, c1, is_cap, hit3, view);
+                bool hit = hit3 == 1;
+                if (hit3 == 2) {      // within 2 mm of the collision threshold (or NaN): decided in T like the other layouts
+                    T pos[3], o7[7];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
+                    const T *g = is_cap ? p.capsules + (int64_t)(k * 7) * N + i : p.spheres + (int64_t)((k - n_caps) * 4) * N + i;
+                    const int n_words = is_cap ? 7 : 4;
+#pragma unroll
+                    for (int c = 0; c < 7; c++) o7[c] = c < n_words ? g[(int64_t)c * N] : T(0);
+                    hit = obstacle_body_hit<T>(p, pos, o7, is_cap);
+                }
+                info |= view ? (1u << k) : 0u;
+                info |= hit ? (1u << 16) : 0u;
+            }
+        } else if (n_obst > 0) {
+            // ---- coordinates too large for float records: everything in T (obstacle_pair)
+            T Rm[9], pos[3];
+            rzyx<T>(w[0], w[1], w[2], w[3], w[4], w[5], Rm);
+#pragma unroll
+            for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
+#pragma unroll 1
+            for (int k = 0; k < n_obst; k++) {
+                const bool is_cap = k < n_caps;
+                T o7[7];
+                const T *g = is_cap ? p.capsules + (int64_t)(k * 7) * N + i : p.spheres + (int64_t)((k - n_caps) * 4) * N + i;
+                const int n_words = is_cap ? 7 : 4;
+#pragma unroll
+                for (int c = 0; c < 7; c++) o7[c] = c < n_words ? g[(int64_t)c * N] : T(0);
+                bool hit, view;
+                obstacle_pair<T, false>(p, pos, Rm, o7, is_cap, nullptr, hit, view);
+                info |= view ? (1u << k) : 0u;
+                info |= hit ? (1u << 16) : 0u;
+            }
+        }
+        // a non-finite pose poisons the rays like the reference's NaN propagation: such envs go through the ray launch
+        // (without obstacles every ray reads max_dist whatever the pose, docking3d.py:441)
+        listed = (info & 0xffffu) != 0u || (n_obst > 0 && !(poison == T(0)));
+        // ---- everything that does not depend on the rays is final for EVERY env: done, condition bits, counters.
+        //      Stores of all lanes of the warp -> full sectors (a listed env only lacks its obstacle-avoidance term: its
+        //      reward word is provisional here and rewritten by the ray launch together with the running return)
+        cond = done_conditions<T>(p, (uint32_t)wc[0], t_steps, (info >> 16) != 0u);
+        const bool done = cond != 0;
+        const int32_t t_new = t_steps + 1;
+        const T r_oa = p.sum_beta_oa / p.sum_beta_oa - T(1);      // docking3d.py:792 with every ray at max_dist: exactly 0
+        const T reward = step_reward<T>(p, A, wf[0], wf[1], wf[2], r_oa, cond);
+        p.reward[i] = reward;
+        p.done[i] = done ? 1 : 0;
+        if (p.cond_bits) p.cond_bits[i] = (uint8_t)cond;
+        if (p.delta_d_out) p.delta_d_out[i] = wf[3];
+        if (done && p.ep_len_out) p.ep_len_out[i] = t_new;
+        if (listed) {
+            p.t_steps[i] = t_new;        // the ray launch reads it back (and zeroes it if it re-initialises the env)
+        } else {
+            // ---- nothing in view: every ray reads max_dist (sensor.py:113-117) -> pooled cells all ones, r_oa = 0
+            float *cells = p.obs + i * p.n_obs + 16;
+            if ((p.n_obs & 3) == 0 && (p.n_rr & 3) == 0) {
+                float4 *c4 = reinterpret_cast<float4 *>(cells);
+                for (int c = 0; c < (p.n_rr >> 2); c++) c4[c] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            } else {
+                for (int c = 0; c < p.n_rr; c++) cells[c] = 1.0f;
+            }
+            const T ep_ret = ep_return + reward;
+            if (done) {
+                if (p.ep_return_out) p.ep_return_out[i] = ep_ret;
+                bs.done = true;
+                bs.cond = cond;
+                bs.length = t_new;
+                bs.ep_return = (double)ep_ret;
+                bs.delta_d = (double)wf[3];
+                bs.nan = reward != reward;      // episodes that ended on a NaN reward
+                ended = true;
+            }
+            if (!(done && p.auto_reset)) {
+                p.ep_return[i] = ep_ret;
+                p.t_steps[i] = t_new;
+            }
+        }
+    }
+    // ---- warp-aggregated appends: envs with something in view from the front, ended episodes from the back
+    {
+        const unsigned lm = __ballot_sync(0xffffffffu, listed), em = __ballot_sync(0xffffffffu, ended);
+        const int64_t n_range = p.env_end - p.env_begin;
+        if (lm) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&p.view_count[0], (unsigned)__popc(lm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (listed) {
+                const unsigned k = base + __popc(lm & ((1u << lane) - 1u));
+                p.view_list[k] = (unsigned long long)(uint32_t)(i - p.env_begin) | ((unsigned long long)(info & 0xffffu) << 32) |
+                                 ((unsigned long long)cond << 48);
+            }
+        }
+        if (em) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&p.view_count[1], (unsigned)__popc(em));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (ended) {
+                const unsigned k = base + __popc(em & ((1u << lane) - 1u));
+                p.view_list[n_range - 1 - k] = (unsigned long long)(uint32_t)(i - p.env_begin);
+            }
+        }
+    }
+    bs.flush(p.stats, threadIdx.x == 0 ? (int)min((int64_t)kCullThreads, p.env_end - i0) : 0);
+}
+
+// ------------------------------------------------------------------------------------------------------- 3. rays + finish
+constexpr int kRayPoseWords = 24;    // shared words per warp for the staged entry: record[16] pos[3] ep_return pad
 template <typename T>
 struct RaysSmem {
-    int warp_words;      // T words per warp: pose[14] + rec[16][kPreStride] + rays[ray_stride]
+    int warp_words;      // T words per warp: entry[24] + rec[16][kPreStride] + rays[ray_stride]
     int ray_stride;
     __host__ __device__ RaysSmem(int n_rays) {
         ray_stride = (n_rays + 2) & ~1;
-        warp_words = kPoseStride + 16 * kPreStride + ray_stride;
+        warp_words = kRayPoseWords + 16 * kPreStride + ray_stride;
     }
 };
 
@@ -67,290 +385,138 @@ struct RaysSmem {
 constexpr int kRayWarps = DOCKAUV_RAY_WARPS;     // warps per CTA of the ray launch
 
 template <typename T, int RPL>
-__global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWarps) rays_kernel(const __grid_constant__ KParams<T> p) {
+__global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWarps) rays_finish_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using P2 = typename Pair<T>::type;
     const RaysSmem<T> L(p.n_rays);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T *s_pose = reinterpret_cast<T *>(smem_raw) + warp * L.warp_words;
-    T *s_pre = s_pose + kPoseStride;
+    T *s_ent = reinterpret_cast<T *>(smem_raw) + warp * L.warp_words;
+    T *s_pre = s_ent + kRayPoseWords;
     T *s_ray = s_pre + 16 * kPreStride;
     const int64_t N = p.n_envs;
-    const unsigned count = *p.view_count;
+    const unsigned count = p.view_count[0], n_ended = p.view_count[1];
     const unsigned n_warps = gridDim.x * kRayWarps;
-    unsigned idx = blockIdx.x * kRayWarps + warp;
-    if (idx >= count) return;
+    const unsigned w_global = blockIdx.x * kRayWarps + warp;
+    double stat_acc = 0.0;       // lane k < DOCKAUV_STAT_ENV_STEPS accumulates statistic k of the episodes this warp ended
 
-    const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph, n_r = p.n_rays;
-    const T dmax = p.radar_max_dist, inv_dmax = T(1) / dmax;
-    // this lane's rays: body-frame direction and obstacle-avoidance weight stay in registers
-    T rb[RPL][3], bw[RPL];
+    if (w_global < count) {
+        unsigned idx = w_global;
+        const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
+        RayLane<T, RPL> rl;
+        rl.init(p, lane, s_ray);
+
+        // software pipeline over the list: entry n + 2 and the data of entry n + 1 are in flight while entry n is cast.
+        // data of one entry: lane c < 14 holds record word c (one request), lanes 16..18 the post-step position, lane 19
+        // the running return, lane 20 the step counter; lane k < n_obst with bit k of the mask holds obstacle k.
+        const bool lane_is_cap = lane < n_caps;
+        const T *obst_row = lane_is_cap ? p.capsules + (int64_t)(lane * 7) * N : p.spheres + (int64_t)((lane - n_caps) * 4) * N;
+        auto fetch = [&](uint64_t entry, T &word, int32_t &tst, T ob[7]) {
+            const int64_t e = p.env_begin + (int64_t)(uint32_t)entry;
+            const unsigned mask = (unsigned)(entry >> 32) & 0xffffu;
+            if (lane < kRecWords) word = p.rec[e * kRecWords + lane];
+            else if (lane < 19) word = p.state[(int64_t)(lane - 16) * N + e];
+            else if (lane == 19) word = p.ep_return[e];
+            else if (lane == 20) tst = p.t_steps[e];
+            if (lane < n_obst && ((mask >> lane) & 1u)) {
+                const T *g = obst_row + e;
+                const int n_words = lane_is_cap ? 7 : 4;
 #pragma unroll
-    for (int j = 0; j < RPL; j++) {
-        const int ir = lane + 32 * j;
-        const bool ok = ir < n_r;
+                for (int c = 0; c < 7; c++)
+                    if (c < n_words) ob[c] = g[(int64_t)c * N];
+            }
+        };
+        uint64_t cur = p.view_list[idx];
+        uint64_t nxt = (idx + n_warps < count) ? p.view_list[idx + n_warps] : 0;
+        T word = T(0), ob[7];
+        int32_t tst = 0;
 #pragma unroll
-        for (int c = 0; c < 3; c++) rb[j][c] = ok ? p.ray_tab[c * n_r + ir] : T(0);
-        bw[j] = ok ? p.ray_tab[3 * n_r + ir] : T(0);
+        for (int c = 0; c < 7; c++) ob[c] = T(0);
+        fetch(cur, word, tst, ob);
+
+        for (; idx < count; idx += n_warps) {
+            const int64_t ie = p.env_begin + (int64_t)(uint32_t)cur;
+            const unsigned mask = (unsigned)(cur >> 32) & 0xffffu;
+            const uint32_t cond = (uint32_t)(cur >> 48) & 31u;
+            // ---- stage the prefetched data, start the next fetches
+            if (lane < 20) s_ent[lane] = word;
+            const int32_t t_new = __shfl_sync(0xffffffffu, tst, 20);     // already incremented by the cull launch
+            __syncwarp();
+            const T pos[3] = {s_ent[16], s_ent[17], s_ent[18]};
+            if (lane < n_obst && ((mask >> lane) & 1u)) obstacle_ray_record<T>(pos, ob, lane_is_cap, s_pre + lane * kPreStride);
+            const uint64_t nn = (idx + 2 * n_warps < count) ? p.view_list[idx + 2 * n_warps] : 0;
+            if (idx + n_warps < count) fetch(nxt, word, tst, ob);
+            T R[9];
+            rzyx<T>(s_ent[0], s_ent[1], s_ent[2], s_ent[3], s_ent[4], s_ent[5], R);
+            const T poison = s_ent[REC_POISON];
+            __syncwarp();
+
+            // ---- cast rays against the in-view obstacles, pooled cells to the observation row
+            const T oa_dot = radar_env<T, RPL, false>(p, rl, R, poison, mask, s_pre, s_ray, lane, ie);
+
+            // ---- what the cull launch left open: the reward with its obstacle-avoidance term and the running return
+            //      (every lane computes the same values from the staged record, lane 0 stores)
+            const T r_oa = p.sum_beta_oa / oa_dot - T(1);      // docking3d.py:792
+            const T reward = step_reward<T>(p, s_ent[REC_A], s_ent[REC_B], s_ent[REC_R7], s_ent[REC_LPD], r_oa, cond);
+            const T ep_ret = s_ent[19] + reward;
+            const bool done = cond != 0;
+            if (lane == 0) {
+                p.reward[ie] = reward;
+                if (done && p.ep_return_out) p.ep_return_out[ie] = ep_ret;
+                if (!(done && p.auto_reset)) p.ep_return[ie] = ep_ret;
+            }
+            if (done) {       // warp-uniform
+                double mine = 0.0;
+                if (lane == DOCKAUV_STAT_EPISODES) mine = 1.0;
+                else if (lane == DOCKAUV_STAT_SUM_RETURN) mine = (double)ep_ret;
+                else if (lane == DOCKAUV_STAT_SUM_LENGTH) mine = (double)t_new;
+                else if (lane >= DOCKAUV_STAT_COND0 && lane < DOCKAUV_STAT_COND0 + 5) mine = ((cond >> (lane - DOCKAUV_STAT_COND0)) & 1u) ? 1.0 : 0.0;
+                else if (lane == DOCKAUV_STAT_SUM_FINAL_DELTA_D) mine = (double)s_ent[REC_DD];
+                else if (lane == DOCKAUV_STAT_NAN_ENVS) mine = (reward != reward) ? 1.0 : 0.0;
+                stat_acc += mine;
+                __syncwarp();      // the pooled cells of the row are in place before it is moved
+                end_episode_warp<T>(p, ie, lane);
+            }
+            __syncwarp();
+            cur = nxt;
+            nxt = nn;
+        }
     }
-    // 2x2 pooling (at most one pooled cell per lane): the four source slots of this lane's cell; cells beyond the ray
-    // grid read the zero slot s_ray[n_r] (block_reduce pads with cval = 0, sensor.py:131-137)
-    const bool fast_pool = (p.block == 2) && (p.n_rr <= 32);
-    int pidx[4] = {n_r, n_r, n_r, n_r};
-    if (fast_pool && lane < p.n_rr) {
-        const int pr = lane / p.n_hr, pcol = lane - pr * p.n_hr;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int rv = 2 * pr + (q >> 1), rh = 2 * pcol + (q & 1);
-            if (rv < p.n_vert && rh < p.n_horiz) pidx[q] = rv * p.n_horiz + rh;
-        }
-    }
-    if (lane == 0) s_ray[n_r] = T(0);
-
-    // software pipeline over the list: entry n + 2 and the data of entry n + 1 are in flight while entry n is cast.
-    // data of one entry: lane c < 13 holds pose word c, lane k < n_obst with bit k of the mask holds obstacle k.
-    const bool lane_is_cap = lane < n_caps;
-    const T *obst_row = lane_is_cap ? p.capsules + (int64_t)(lane * 7) * N : p.spheres + (int64_t)((lane - n_caps) * 4) * N;
-    auto fetch = [&](uint64_t entry, T &pose_w, T ob[7]) {
-        const int64_t e = p.env_begin + (int64_t)(uint32_t)entry;
-        const unsigned mask = (unsigned)(entry >> 32);
-        if (lane < 13) pose_w = p.handoff[(int64_t)lane * N + e];
-        if (lane < n_obst && ((mask >> lane) & 1u)) {
-            const T *g = obst_row + e;
-            const int n_words = lane_is_cap ? 7 : 4;
-#pragma unroll
-            for (int c = 0; c < 7; c++)
-                if (c < n_words) ob[c] = g[(int64_t)c * N];
-        }
-    };
-    uint64_t cur = p.view_list[idx];
-    uint64_t nxt = (idx + n_warps < count) ? p.view_list[idx + n_warps] : 0;
-    T pose_w = T(0), ob[7];
-#pragma unroll
-    for (int c = 0; c < 7; c++) ob[c] = T(0);
-    fetch(cur, pose_w, ob);
-
-    for (; idx < count; idx += n_warps) {
-        const int64_t ie = p.env_begin + (int64_t)(uint32_t)cur;
-        const unsigned mask = (unsigned)(cur >> 32);
-        // ---- stage the prefetched data, start the next fetches
-        if (lane < 13) s_pose[lane] = pose_w;
-        __syncwarp();
-        if (lane < n_obst && ((mask >> lane) & 1u)) {
-            const T pos[3] = {s_pose[0], s_pose[1], s_pose[2]};
-            bool hit, view;
-            obstacle_pair<T, true>(p, pos, s_pose + 3, ob, lane_is_cap, s_pre + lane * kPreStride, hit, view);
-        }
-        const uint64_t nn = (idx + 2 * n_warps < count) ? p.view_list[idx + 2 * n_warps] : 0;
-        if (idx + n_warps < count) fetch(nxt, pose_w, ob);
-        __syncwarp();
-
-        // ---- cast rays against the in-view obstacles (uniform loop, broadcast shared reads)
-        T best[RPL];
-#pragma unroll
-        for (int j = 0; j < RPL; j++) best[j] = Mth<T>::inf();
-        if (mask) {
-            T rd[RPL][3];
-            {
-                T R[9];
-#pragma unroll
-                for (int c = 0; c < 9; c++) R[c] = s_pose[3 + c];
-#pragma unroll
-                for (int j = 0; j < RPL; j++) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++)
-                        rd[j][c] = R[3 * c] * rb[j][0] + R[3 * c + 1] * rb[j][1] + R[3 * c + 2] * rb[j][2];
-                }
-            }
-            unsigned cap_mask = mask & ((1u << n_caps) - 1u);
-            unsigned sph_mask = (mask >> n_caps) & ((1u << n_sph) - 1u);
-            while (cap_mask) {
-                const int k = __ffs(cap_mask) - 1;
-                cap_mask &= cap_mask - 1;
-                const P2 *w2 = reinterpret_cast<const P2 *>(s_pre + k * kPreStride);
-                const P2 v0 = w2[0], v1 = w2[1], v2 = w2[2], v3 = w2[3], v4 = w2[4], v5 = w2[5];
-                const T ba[3] = {v0.x, v0.y, v1.x}, oa[3] = {v1.y, v2.x, v2.y};
-                const T baba = v3.x, baoa = v3.y, cc = v4.x, c2a = v4.y, c2b = v5.x;
-#pragma unroll
-                for (int j = 0; j < RPL; j++) {
-                    // shape.py:341-390 for one ray: cylinder root, body hit if 0 < y < baba, else end cap
-                    const T bard = rd[j][0] * ba[0] + rd[j][1] * ba[1] + rd[j][2] * ba[2];
-                    const T rdoa = rd[j][0] * oa[0] + rd[j][1] * oa[1] + rd[j][2] * oa[2];
-                    const T a = baba - bard * bard;
-                    const T b = baba * rdoa - baoa * bard;
-                    const T h = b * b - a * cc;
-                    if (h > T(0)) {
-                        const T t = (-b - Mth<T>::sqrt_pos(h)) * Mth<T>::rcp_(a);
-                        const T y = baoa + t * bard;
-                        T v = t;
-                        if (!(y > T(0) && y < baba)) {
-                            const bool far_end = y >= T(0);
-                            const T b2 = far_end ? rdoa - bard : rdoa;     // rd . (pos - cap end)
-                            const T h2 = b2 * b2 - (far_end ? c2b : c2a);
-                            v = (h2 > T(0)) ? (-b2 - Mth<T>::sqrt_pos(h2 > T(0) ? h2 : T(1))) : T(-1);
-                        }
-                        if (v > T(0) && v < best[j]) best[j] = v;
-                    }
-                }
-            }
-            while (sph_mask) {
-                const int k = __ffs(sph_mask) - 1;
-                sph_mask &= sph_mask - 1;
-                const P2 *w2 = reinterpret_cast<const P2 *>(s_pre + (n_caps + k) * kPreStride);
-                const P2 v0 = w2[0], v1 = w2[1];
-#pragma unroll
-                for (int j = 0; j < RPL; j++) {
-                    // shape.py:252-263: nearest root of the ray / sphere quadratic
-                    const T b = v0.x * rd[j][0] + v0.y * rd[j][1] + v1.x * rd[j][2];
-                    const T h = b * b - v1.y;
-                    if (h >= T(0)) {
-                        const T v = -b - (h > T(0) ? Mth<T>::sqrt_pos(h) : T(0));
-                        if (v > T(0) && v < best[j]) best[j] = v;
-                    }
-                }
-            }
-        }
-        // ---- clamp (sensor.py:117), obstacle-avoidance sum (docking3d.py:767-792), stash for pooling
-        const T poison = s_pose[12];
-        T oa_part = T(0);
-#pragma unroll
-        for (int j = 0; j < RPL; j++) {
-            const int ir = lane + 32 * j;
-            if (ir < n_r) {
-                // min positive distance over obstacles (docking3d.py:438-439), max_dist if none or farther
-                const T d = (best[j] > dmax ? dmax : best[j]) + poison;
-                s_ray[ir] = d;
-                // (gamma_c (1 - c))^2 with c = clip(1 - d/d_max, 0, 1): 1 - c = d/d_max for d in [0, d_max]
-                const T x = d * inv_dmax;
-                const T qq = x * x;
-                const T mx = !(qq <= T(0.001)) ? qq : T(0.001);     // np.maximum, NaN propagates
-                oa_part += mx * bw[j];
-            }
-        }
-        const T oa_dot = warp_sum<T>(oa_part);
-        if (lane == 0) p.oa_dot[ie] = oa_dot;
-        __syncwarp();
-        // ---- 2x2 max-pool with zero padding (sensor.py:131-137) -> obs[16:]
-        float *orow = p.obs + ie * p.n_obs + 16;
-        if (fast_pool) {
-            if (lane < p.n_rr) {
-                T mx = s_ray[pidx[0]];
-#pragma unroll
-                for (int q = 1; q < 4; q++) {
-                    const T v = s_ray[pidx[q]];
-                    mx = !(v <= mx) ? v : mx;            // np.max, NaN propagates
-                }
-                T o = mx * inv_dmax;                     // clip(d / max_dist, 0, 1), docking3d.py:487
-                o = o > T(1) ? T(1) : o;
-                orow[lane] = (float)o;
-            }
-        } else {
-            for (int pc = lane; pc < p.n_rr; pc += 32) {
-                const int pr = pc / p.n_hr, pcol = pc - pr * p.n_hr;
-                T mx = T(0);
-                for (int dv = 0; dv < p.block; dv++)
-                    for (int dh = 0; dh < p.block; dh++) {
-                        const int rv = pr * p.block + dv, rh = pcol * p.block + dh;
-                        if (rv < p.n_vert && rh < p.n_horiz) {
-                            const T v = s_ray[rv * p.n_horiz + rh];
-                            mx = !(v <= mx) ? v : mx;
-                        }
-                    }
-                T o = mx * inv_dmax;
-                o = o > T(1) ? T(1) : o;
-                orow[pc] = (float)o;
-            }
-        }
-        __syncwarp();
-        cur = nxt;
-        nxt = nn;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------- 4. finish
-#ifndef DOCKAUV_MINB_FINISH
-#define DOCKAUV_MINB_FINISH 4      // 64 registers; 5 (48 registers, 40 B spills) measured the same
-#endif
-#ifndef DOCKAUV_FINISH_THREADS
-#define DOCKAUV_FINISH_THREADS 256
-#endif
-constexpr int kFinishThreads = DOCKAUV_FINISH_THREADS;
-
-template <typename T>
-__global__ void __launch_bounds__(kFinishThreads, DOCKAUV_MINB_FINISH) finish_kernel(const __grid_constant__ KParams<T> p) {
-    __shared__ int s_n_reset;
-    __shared__ int s_reset[kFinishThreads];
-    const int64_t N = p.n_envs;
-    const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kFinishThreads;
-    const int64_t i = i0 + threadIdx.x;
-    const bool active = i < p.env_end;
-    if (threadIdx.x == 0) s_n_reset = 0;
-    __syncthreads();
-    WarpStats bs;
-    if (active) {
-        const T *hf = p.handoff + i;
-        StepCarry<T> cy;
-#pragma unroll
-        for (int c = 0; c < 8; c++) cy.rarr[c] = hf[(int64_t)(13 + c) * N];
-        cy.delta_d = hf[(int64_t)21 * N];
-        cy.cond = p.handoff_cond[i];
-        cy.t_steps = p.t_steps[i];
-        cy.ep_return = p.ep_return[i];
-        const uint32_t info = p.view_info[i];
-        const bool listed = (info & kViewListed) != 0u;
-        // envs with an empty view: every ray reads max_dist (sensor.py:113-117) -> pooled cells all ones, r_oa = 0
-        T oa = p.sum_beta_oa;
-        float *row = p.obs + i * p.n_obs;
-        if (listed) {
-            oa = p.oa_dot[i];
-        } else {
-            float *cells = row + 16;
-            if ((p.n_obs & 3) == 0 && (p.n_rr & 3) == 0) {
-                float4 *c4 = reinterpret_cast<float4 *>(cells);
-                for (int c = 0; c < (p.n_rr >> 2); c++) c4[c] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-            } else {
-                for (int c = 0; c < p.n_rr; c++) cells[c] = 1.0f;
-            }
-        }
-        const T r_oa = p.sum_beta_oa / oa - T(1);      // docking3d.py:792
-        const bool done = step_finish<T, false, true>(p, i, cy, r_oa, (info & kViewCollision) != 0u, bs);
-        if (done) s_reset[atomicAdd(&s_n_reset, 1)] = threadIdx.x;     // ~1 % of the envs per step
-    }
-    bs.flush(p.stats, threadIdx.x == 0 ? (int)min((int64_t)kFinishThreads, p.env_end - i0) : 0);
-    // ---- finished envs of this CTA, compacted:
-    __syncthreads();
-    const int n_done = s_n_reset;
-    // one warp per finished env (lanes = columns / reset roles; a single thread walking its own row is a chain of 32
-    // dependent HBM round trips, a single-thread reset a ~3000-instruction chain, and the whole CTA would wait):
-    //  (a) the last observation is kept as terminal_observation and the all-zero reset observation is handed back
-    //      (docking3d.py:269,322);  (b) the env is re-initialised (reset_env_warp).
+    // ---- episodes that ended in the cull launch (nothing in view): one warp per env moves the terminal-observation row
+    //      and re-initialises the env.  A reset is a ~3000-instruction chain for one thread and the ~1 % of envs it hits
+    //      are scattered; here they are spread over all warps of this persistent grid.
     {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_obs = p.n_obs;
-        for (int e = warp; e < n_done; e += kFinishThreads / 32) {
-            const int64_t ie = i0 + s_reset[e];
-            float *row = p.obs + ie * n_obs;
-            float *trow = p.terminal_obs ? p.terminal_obs + ie * n_obs : nullptr;
-            for (int c = lane; c < n_obs; c += 32) {
-                if (trow) trow[c] = row[c];
-                if (p.auto_reset) row[c] = 0.0f;
-            }
-            if (p.auto_reset) reset_env_warp<T>(p, ie, lane);
+        const int64_t n_range = p.env_end - p.env_begin;
+        for (unsigned k = w_global; k < n_ended; k += n_warps) {
+            const int64_t ie = p.env_begin + (int64_t)(uint32_t)p.view_list[n_range - 1 - k];
+            end_episode_warp<T>(p, ie, lane);
         }
     }
+    if (lane < DOCKAUV_STAT_ENV_STEPS && stat_acc != 0.0)
+        atomicAdd(&p.stats[(blockIdx.x & (DOCKAUV_STAT_COPIES - 1)) * DOCKAUV_N_STATS + lane], stat_acc);
 }
 
 // ------------------------------------------------------------------------------------------------------- launcher
 template <typename T, int VEH, int NU>
+static cudaError_t launch_dynamics(const KParams<T> &k, unsigned blocks, cudaStream_t st) {
+    const bool cur = k.has_current != 0, spm = k.sparse_minv != 0;
+    if (cur && spm) dynamics_kernel<T, VEH, NU, true, true><<<blocks, kDynThreads, 0, st>>>(k);
+    else if (cur) dynamics_kernel<T, VEH, NU, true, false><<<blocks, kDynThreads, 0, st>>>(k);
+    else if (spm) dynamics_kernel<T, VEH, NU, false, true><<<blocks, kDynThreads, 0, st>>>(k);
+    else dynamics_kernel<T, VEH, NU, false, false><<<blocks, kDynThreads, 0, st>>>(k);
+    return cudaGetLastError();
+}
+
+template <typename T, int VEH, int NU>
 static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEvent_t *marks = nullptr, int *n_marks = nullptr) {
-    if (wants_debug(k) || k.handoff == nullptr) return launch_step_warp<T, VEH, NU>(k, st);   // debug outputs: fused kernel
-    if (k.split_chunk > 0 && k.split_chunk < k.env_end - k.env_begin && marks == nullptr) {
-        // chunked: the four launches per chunk of envs, so that a chunk's hand-off can still be in L2 when it is read
-        const int64_t chunk = ((k.split_chunk + kWarpEnvs - 1) / kWarpEnvs) * kWarpEnvs;
+    if (wants_debug(k) || k.rec == nullptr) return launch_step_warp<T, VEH, NU>(k, st);   // debug outputs: fused kernel
+    if (k.chunk_envs > 0 && k.chunk_envs < k.env_end - k.env_begin && marks == nullptr) {
+        // chunked: the launches per chunk of envs (measured slower than the whole batch: partial waves of short launches
+        // cost more than an L2-resident record saves; kept for experiments and as a test handle)
+        const int64_t chunk = ((k.chunk_envs + kWarpEnvs - 1) / kWarpEnvs) * kWarpEnvs;
         for (int64_t b = k.env_begin; b < k.env_end; b += chunk) {
             KParams<T> kb = k;
             kb.env_begin = b;
             kb.env_end = b + chunk < k.env_end ? b + chunk : k.env_end;
-            kb.split_chunk = 0;
+            kb.chunk_envs = 0;
             cudaError_t e = launch_step_pipe<T, VEH, NU>(kb, st);
             if (e != cudaSuccess) return e;
         }
@@ -358,41 +524,38 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     }
     const int64_t n = k.env_end - k.env_begin;
     KParams<T> kc = k;
-    kc.view_count = k.view_count + (k.env_begin / kWarpEnvs);   // one list counter per concurrently stepped env range
+    kc.view_count = k.view_count + kListCounters * (k.env_begin / kWarpEnvs);   // counters per concurrently stepped env range
     kc.view_list = k.view_list + k.env_begin;
     int n_mark = 0;
     auto mark = [&]() {
         if (marks) cudaEventRecord(marks[n_mark++], st);
     };
     mark();
-    // scenarios without obstacles: no cull, no rays (the view words stay at their initial 0 = nothing in view, no collision)
-    const bool has_obstacles = k.n_caps + k.n_sph > 0;
-    cudaError_t e = launch_step_warp_rpl<T, VEH, NU, 2, 1, false>(kc, st);
+    cudaError_t e = launch_dynamics<T, VEH, NU>(kc, (unsigned)((n + kDynThreads - 1) / kDynThreads), st);
     if (e != cudaSuccess) return e;
     mark();
-    if (has_obstacles) cull_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kc);
+    cull_finish_kernel<T><<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, 0, st>>>(kc);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     mark();
-    if (has_obstacles) {
+    // (scenarios without obstacles list nothing: the launch then only re-initialises the envs whose episode ended)
+    {
         const RaysSmem<T> L(k.n_rays);
         const int smem = kRayWarps * L.warp_words * (int)sizeof(T);
         int64_t blocks = (int64_t)(k.sm_count > 0 ? k.sm_count : 148) * (DOCKAUV_RAY_CTAS_PER_SM * 4 / kRayWarps);
         const int64_t most = (n + kRayWarps - 1) / kRayWarps;
         if (blocks > most) blocks = most;
         if (k.n_rays <= 64) {
-            auto kern = rays_kernel<T, 2>;
+            auto kern = rays_finish_kernel<T, 2>;
             if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
             kern<<<(unsigned)blocks, kRayWarps * 32, smem, st>>>(kc);
         } else {
-            auto kern = rays_kernel<T, 8>;
+            auto kern = rays_finish_kernel<T, 8>;
             if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
             kern<<<(unsigned)blocks, kRayWarps * 32, smem, st>>>(kc);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        mark();
     }
-    mark();
-    finish_kernel<T><<<(unsigned)((n + kFinishThreads - 1) / kFinishThreads), kFinishThreads, 0, st>>>(kc);
-    mark();
     if (n_marks) *n_marks = n_mark;
     return cudaGetLastError();
 }

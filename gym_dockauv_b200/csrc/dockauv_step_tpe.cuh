@@ -1,71 +1,47 @@
 // dockauv_step_tpe.cuh -- layout DOCKAUV_LAYOUT_THREAD_PER_ENV: one thread carries one env through the whole
 // step (docking3d.py:346-402).  Ray directions and every constant come from the constant bank (uniform
-// reads); per-env capsule pre-computations live in a small local array.  This is the simple layout used for
-// scenarios without obstacles (BASELINE config C2) and as the cross-check of the warp-cooperative radar layout.
+// reads); per-env capsule pre-computations live in a small local array.  6x slower than the pipeline on the C4
+// workload; kept as the independently written cross-check (the reference's per-ray bookkeeping, library hypot and
+// divisions, no culls).
 #pragma once
-#include "dockauv_cull.cuh"
+#include "dockauv_rays.cuh"
 
 namespace dockauv {
 
-// Dynamics + everything that does not need the radar.  Shared by both layouts.
-//   returns false for an env index beyond the batch.
-//   DBG: compile the optional debug outputs in (parity tests); the throughput kernels are built without them.
-template <typename T, int VEH, int NU, bool DBG>
-__device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T &spsi_out, T &cpsi_out,
-                                              float obs16[16], T att_out[3]) {
+// ---- pieces of the per-env step that do not need the radar; shared by every layout (same expressions, same bits)
+
+// Current.sim (current.py:78-96) then nu_c from the PRE-step attitude (docking3d.py:348-349).
+//   tr0: sin/cos of the pre-step attitude
+template <typename T>
+__device__ __forceinline__ void dyn_current(const KParams<T> &p, int64_t i, const T tr0[6], T nu_c[3]) {
     const int64_t N = p.n_envs;
-    T pos[3], y[9];
-#pragma unroll
-    for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
-#pragma unroll
-    for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
-    // everything else this step reads is requested up front so that one HBM round trip covers all of it
-    T goal[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) goal[c] = p.goal[(int64_t)c * N + i];
-    const int32_t t_steps = p.t_steps[i];
-    cy.t_steps = t_steps;
-    cy.ep_return = p.ep_return[i];
-
-    // ---- ocean current: Current.sim (current.py:78-96) then nu_c from the PRE-step attitude (docking3d.py:348-349)
-    // sin/cos of the pre-step attitude: the only library sincos calls of the step (every later attitude is a small
-    // shift of this one, sincos_shift); shared by the current rotation and the first Runge-Kutta stage
-    T tr0[6];
-    Mth<T>::sincos_(y[0], &tr0[0], &tr0[1]);
-    Mth<T>::sincos_(y[1], &tr0[2], &tr0[3]);
-    Mth<T>::sincos_(y[2], &tr0[4], &tr0[5]);
-    T nu_c[3] = {T(0), T(0), T(0)};
-    if (p.has_current) {
-        T Vc = p.current[i];
-        T alpha = p.current[N + i], beta = p.current[2 * N + i];
-        T vmin = p.current[3 * N + i], vmax = p.current[4 * N + i];
-        T w = T(0);
-        if (p.has_noise) {
-            w = (p.noise != nullptr) ? p.noise[i]
-                                     : (T)((double)p.cur_sigma *
-                                           philox_normal(p.seed, p.env_id0 + (uint64_t)i, (uint32_t)p.episode[i],
-                                                         (uint32_t)p.t_steps[i]));
-        }
-        T Vc_dot = -p.cur_mu * Vc + w;
-        Vc = Vc + Vc_dot * p.h;
-        Vc = clipv(Vc, vmin, vmax);
-        p.current[i] = Vc;
-        T sa, ca, sb, cb;
-        Mth<T>::sincos_(alpha, &sa, &ca);
-        Mth<T>::sincos_(beta, &sb, &cb);
-        T vn[3] = {Vc * ca * cb, Vc * sb, Vc * sa * cb};                 // current.py:71-73
-        T R[9];
-        rzyx(tr0[0], tr0[1], tr0[2], tr0[3], tr0[4], tr0[5], R);
-#pragma unroll
-        for (int c = 0; c < 3; c++) nu_c[c] = R[c] * vn[0] + R[3 + c] * vn[1] + R[6 + c] * vn[2];   // R^T v
+    T Vc = p.current[i];
+    T alpha = p.current[N + i], beta = p.current[2 * N + i];
+    T vmin = p.current[3 * N + i], vmax = p.current[4 * N + i];
+    T w = T(0);
+    if (p.has_noise) {
+        w = (p.noise != nullptr) ? p.noise[i]
+                                 : (T)((double)p.cur_sigma *
+                                       philox_normal(p.seed, p.env_id0 + (uint64_t)i, (uint32_t)p.episode[i],
+                                                     (uint32_t)p.t_steps[i]));
     }
-
-    // ---- command
-    T u[NU];
-    T penalty = command_and_penalty<T, NU>(p, i, u);
+    T Vc_dot = -p.cur_mu * Vc + w;
+    Vc = Vc + Vc_dot * p.h;
+    Vc = clipv(Vc, vmin, vmax);
+    p.current[i] = Vc;
+    T sa, ca, sb, cb;
+    Mth<T>::sincos_(alpha, &sa, &ca);
+    Mth<T>::sincos_(beta, &sb, &cb);
+    T vn[3] = {Vc * ca * cb, Vc * sb, Vc * sa * cb};                 // current.py:71-73
+    T R[9];
+    rzyx(tr0[0], tr0[1], tr0[2], tr0[3], tr0[4], tr0[5], R);
 #pragma unroll
-    for (int k = 0; k < NU; k++) p.u_prev[(int64_t)k * N + i] = u[k];
-    T tau[6];
+    for (int c = 0; c < 3; c++) nu_c[c] = R[c] * vn[0] + R[3 + c] * vn[1] + R[6 + c] * vn[2];   // R^T v
+}
+
+// generalised force of the low-passed command: BlueROV2 B u (B constant, BlueROV2.py:74-75); LAUV keeps u (B(nu) u per stage)
+template <typename T, int VEH, int NU>
+__device__ __forceinline__ void dyn_tau(const KParams<T> &p, const T u[NU], T tau[6]) {
     if (VEH == DOCKAUV_VEHICLE_BLUEROV2) {
 #pragma unroll
         for (int r = 0; r < 6; r++) {
@@ -77,36 +53,32 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     } else {
         tau[0] = u[0]; tau[1] = u[1]; tau[2] = u[2]; tau[3] = tau[4] = tau[5] = T(0);
     }
+}
 
-    // ---- integrate (auvsim.py:89-108)
-    T tr1[6];
-    rkf45_step<T, VEH>(p, pos, y, tr0, tau, nu_c, tr1);
-#pragma unroll
-    for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
-#pragma unroll
-    for (int c = 0; c < 3; c++) p.state[(int64_t)c * N + i] = pos[c];
-#pragma unroll
-    for (int c = 0; c < 9; c++) p.state[(int64_t)(3 + c) * N + i] = y[c];
+// Everything of update_navigation_errors / observe / is_done / reward_step (docking3d.py:404-631) that needs no radar,
+// no collision flag and no step counter.
+template <typename T>
+struct DynOut {
+    T o[16];            // observation entries 0..15 before the float32 cast
+    T r[8];             // reward terms 0..5 and 7; r[6] holds log_precision(delta_d) for reward_set 2
+    T ed[3];            // post-step Theta_dot (auvsim.py:108)
+    T delta_d, delta_theta, delta_psi;
+    uint32_t cond;      // done conditions 0..2
+};
 
-    // ---- post-step quantities: Theta_dot (auvsim.py:108, only euler_dot is consumed) and Rzyx for the radar
+//   pos, y: post-step position and (Theta after ssa, nu_r); tr1: sin/cos of the post-step attitude
+template <typename T>
+__device__ __forceinline__ void dyn_outputs(const KParams<T> &p, const T pos[3], const T y[9], const T tr1[6], const T goal[3],
+                                            const T nu_c[3], T penalty, DynOut<T> &q) {
     const T sphi = tr1[0], cphi = tr1[1], sth = tr1[2], cth = tr1[3], spsi = tr1[4], cpsi = tr1[5];
-    T ed[3];
+    const T *nu = y + 3;
     {
-        const T *nu = y + 3;
         T inv_cth = T(1) / cth, tth = sth * inv_cth;
         T qs = sphi * nu[4] + cphi * nu[5];
-        ed[0] = nu[3] + tth * qs;
-        ed[1] = cphi * nu[4] - sphi * nu[5];
-        ed[2] = qs * inv_cth;
+        q.ed[0] = nu[3] + tth * qs;
+        q.ed[1] = cphi * nu[4] - sphi * nu[5];
+        q.ed[2] = qs * inv_cth;
     }
-    rzyx(sphi, cphi, sth, cth, spsi, cpsi, cy.R);
-#pragma unroll
-    for (int c = 0; c < 3; c++) cy.pos[c] = pos[c];
-    spsi_out = spsi;
-    cpsi_out = cpsi;
-#pragma unroll
-    for (int c = 0; c < 3; c++) att_out[c] = y[c];
-
     // ---- navigation errors (docking3d.py:404-413)
     T diff[3];
 #pragma unroll
@@ -115,11 +87,12 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     T delta_d = Mth<T>::sqrt_(dxy2 + diff[2] * diff[2]);
     T delta_theta = y[1] + ssa<T>(Mth<T>::atan2_(diff[2], Mth<T>::sqrt_(dxy2)));
     T delta_psi = ssa<T>(Mth<T>::atan2_(diff[1], diff[0]) - y[2]);
-    cy.delta_d = delta_d;
+    q.delta_d = delta_d;
+    q.delta_theta = delta_theta;
+    q.delta_psi = delta_psi;
 
     // ---- observe (docking3d.py:462-488), entries 0..15
-    const T *nu = y + 3;
-    T o[16];
+    T *o = q.o;
     T lg = Mth<T>::log_(delta_d / p.max_dist_from_goal);
     o[0] = clipv(T(1) - lg / p.log_den_obs, T(0), T(1));
     o[1] = clipv(delta_theta * Mth<T>::inv_half_pi, T(-1), T(1));
@@ -137,19 +110,16 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
     o[13] = clipv(nu_c[0] / T(2), T(-1), T(1));
     o[14] = clipv(nu_c[1] / T(2), T(-1), T(1));
     o[15] = clipv(nu_c[2] / T(2), T(-1), T(1));
-#pragma unroll
-    for (int c = 0; c < 16; c++) obs16[c] = (float)o[c];
 
-    // ---- is_done conditions 0..3 (docking3d.py:606-615; t_steps is the value before the increment)
+    // ---- is_done conditions 0..2 (docking3d.py:606-611)
     uint32_t cond = 0;
     cond |= (delta_d < p.dist_goal_reached_tol) ? 1u : 0u;
     cond |= (delta_d > p.max_dist_from_goal) ? 2u : 0u;
     cond |= ((Mth<T>::abs_(y[0]) > p.max_attitude) || (Mth<T>::abs_(y[1]) > p.max_attitude)) ? 4u : 0u;
-    cond |= (t_steps >= p.max_timesteps) ? 8u : 0u;
-    cy.cond = cond;
+    q.cond = cond;
 
     // ---- reward terms that need no radar (docking3d.py:512-558, 584-588)
-    T *r = cy.rarr;
+    T *r = q.r;
     T lp_d;
     {
         // log_precision(delta_d, tol, max): shares the logarithm with obs[0] unless the epsilon guard bites
@@ -169,24 +139,92 @@ __device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, St
         T a = y[0] * Mth<T>::inv_half_pi, b = y[1] * Mth<T>::inv_half_pi;
         r[3] = -p.w_phi * (a * a);
         r[4] = -p.w_theta * (b * b);
-        T nrm = Mth<T>::sqrt_(ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]) * p.inv_p_max;
+        T nrm = Mth<T>::sqrt_(q.ed[0] * q.ed[0] + q.ed[1] * q.ed[1] + q.ed[2] * q.ed[2]) * p.inv_p_max;
         r[5] = -p.w_Thetadot * (nrm * nrm);
     }
-    r[6] = lp_d;   // parked here for reward_set 2 (overwritten by the obstacle-avoidance term)
+    r[6] = lp_d;   // parked here for reward_set 2 (replaced by the obstacle-avoidance term later)
     r[7] = penalty;
+}
+
+// Dynamics + everything that does not need the radar, for the single-launch layouts.
+//   DBG: compile the optional debug outputs in (parity tests); the throughput kernels are built without them.
+template <typename T, int VEH, int NU, bool DBG>
+__device__ __forceinline__ void step_dynamics(const KParams<T> &p, int64_t i, StepCarry<T> &cy, T &spsi_out, T &cpsi_out,
+                                              float obs16[16], T att_out[3]) {
+    const int64_t N = p.n_envs;
+    T pos[3], y[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
+#pragma unroll
+    for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
+    // everything else this step reads is requested up front so that one HBM round trip covers all of it
+    T goal[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) goal[c] = p.goal[(int64_t)c * N + i];
+    const int32_t t_steps = p.t_steps[i];
+    cy.t_steps = t_steps;
+    cy.ep_return = p.ep_return[i];
+
+    // sin/cos of the pre-step attitude: the only library sincos calls of the step (every later attitude is a small
+    // shift of this one, sincos_shift); shared by the current rotation and the first Runge-Kutta stage
+    T tr0[6];
+    Mth<T>::sincos_(y[0], &tr0[0], &tr0[1]);
+    Mth<T>::sincos_(y[1], &tr0[2], &tr0[3]);
+    Mth<T>::sincos_(y[2], &tr0[4], &tr0[5]);
+    T nu_c[3] = {T(0), T(0), T(0)};
+    if (p.has_current) dyn_current<T>(p, i, tr0, nu_c);
+
+    // ---- command
+    T u[NU];
+    T penalty = command_and_penalty<T, NU>(p, i, u);
+#pragma unroll
+    for (int k = 0; k < NU; k++) p.u_prev[(int64_t)k * N + i] = u[k];
+    T tau[6];
+    dyn_tau<T, VEH, NU>(p, u, tau);
+
+    // ---- integrate (auvsim.py:89-108)
+    T tr1[6];
+    {
+        T pacc[3];
+        rkf45_step<T, VEH>(p, y, tr0, tau, nu_c, pacc, tr1);
+#pragma unroll
+        for (int c = 0; c < 3; c++) pos[c] += pacc[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) p.state[(int64_t)c * N + i] = pos[c];
+#pragma unroll
+    for (int c = 0; c < 9; c++) p.state[(int64_t)(3 + c) * N + i] = y[c];
+
+    DynOut<T> q;
+    dyn_outputs<T>(p, pos, y, tr1, goal, nu_c, penalty, q);
+    rzyx(tr1[0], tr1[1], tr1[2], tr1[3], tr1[4], tr1[5], cy.R);
+#pragma unroll
+    for (int c = 0; c < 3; c++) cy.pos[c] = pos[c];
+    spsi_out = tr1[4];
+    cpsi_out = tr1[5];
+#pragma unroll
+    for (int c = 0; c < 3; c++) att_out[c] = y[c];
+    cy.delta_d = q.delta_d;
+#pragma unroll
+    for (int c = 0; c < 16; c++) obs16[c] = (float)q.o[c];
+    cy.cond = q.cond | ((t_steps >= p.max_timesteps) ? 8u : 0u);      // docking3d.py:612, pre-increment
+#pragma unroll
+    for (int c = 0; c < 8; c++) cy.rarr[c] = q.r[c];
 
     if (DBG) {
         if (p.dbg_euler_dot)
-            for (int c = 0; c < 3; c++) p.dbg_euler_dot[(int64_t)c * N + i] = ed[c];
+            for (int c = 0; c < 3; c++) p.dbg_euler_dot[(int64_t)c * N + i] = q.ed[c];
         if (p.dbg_nu_c)
             for (int c = 0; c < 3; c++) p.dbg_nu_c[(int64_t)c * N + i] = nu_c[c];
         if (p.dbg_nav) {
-            p.dbg_nav[i] = delta_d;
-            p.dbg_nav[N + i] = delta_theta;
-            p.dbg_nav[2 * N + i] = delta_psi;
+            p.dbg_nav[i] = q.delta_d;
+            p.dbg_nav[N + i] = q.delta_theta;
+            p.dbg_nav[2 * N + i] = q.delta_psi;
         }
         if (p.dbg_obs)
-            for (int c = 0; c < 16; c++) p.dbg_obs[(int64_t)c * N + i] = o[c];
+            for (int c = 0; c < 16; c++) p.dbg_obs[(int64_t)c * N + i] = q.o[c];
         if (p.dbg_state_dot) {
             // the full auv._state_dot (auvsim.py:108): right-hand side at the post-step state with the pre-step nu_c
             T sd_pos[3] = {T(0), T(0), T(0)}, sd[9];
@@ -217,6 +255,7 @@ __device__ __forceinline__ bool step_finish(const KParams<T> &p, int64_t i, Step
     p.reward[i] = reward;
     p.done[i] = done ? 1 : 0;
     if (p.cond_bits) p.cond_bits[i] = (uint8_t)cond;
+    if (p.delta_d_out) p.delta_d_out[i] = cy.delta_d;
     T ep_ret = cy.ep_return + reward;
     int32_t t_new = cy.t_steps + 1;
     if (DBG && p.dbg_reward_arr)

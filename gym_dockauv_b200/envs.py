@@ -71,6 +71,8 @@ class BaseDocking3d:
             raise _capi.DockauvError("gym_dockauv_b200 runs on CUDA devices only (no CPU fallback)")
         if not torch.cuda.is_available():
             raise _capi.DockauvError("no CUDA device available; gym_dockauv_b200 has no CPU fallback")
+        if self.device.index is None:      # "cuda" -> the current device, so that tensors, handle and checks agree
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.precision = precision
         self.dtype = torch.float64 if precision == "f64" else torch.float32
         self.auto_reset = bool(auto_reset)
@@ -117,6 +119,7 @@ class BaseDocking3d:
         self.cond_bits = z(N, dtype=torch.uint8)
         self.ep_return_out = z(N)
         self.ep_len_out = z(N, dtype=torch.int32)
+        self.delta_d = z(N)           # info["delta_d"] of the reference (docking3d.py:400)
         self.debug = None
         if debug_outputs:
             self.debug = dict(ray_dist=z(self.n_rays, N), reward_arr=z(13, N), euler_dot=z(3, N), nu_c=z(3, N),
@@ -124,14 +127,14 @@ class BaseDocking3d:
 
         self._handle = C.c_void_p()
         with torch.cuda.device(self.device):
-            _capi.check(self._lib.dockauv_create(C.byref(self._params), N, self.device.index or 0,
-                                                 C.byref(self._handle)))
+            _capi.check(self._lib.dockauv_create(C.byref(self._params), N, self.device.index, C.byref(self._handle)))
         bufs = DockauvBuffers(*[_ptr(t) for t in (self.state, self.u_prev, self.goal, self.heading_goal,
                                                   self.current, self.capsules, self.spheres, self.ep_return,
                                                   self.t_steps, self.episode)])
         _capi.check(self._lib.dockauv_bind(self._handle, C.byref(bufs)))
         self._out = DockauvStepOut(*[_ptr(t) for t in (self.obs, self.reward, self.done, self.cond_bits,
-                                                       self.terminal_obs, self.ep_return_out, self.ep_len_out)])
+                                                       self.terminal_obs, self.ep_return_out, self.ep_len_out,
+                                                       self.delta_d)])
         self._dbg = None
         if self.debug is not None:
             self._dbg = DockauvDebugOut(*[_ptr(self.debug[k]) for k in ("ray_dist", "reward_arr", "euler_dot", "nu_c",
@@ -197,7 +200,7 @@ class BaseDocking3d:
                                            int(self.auto_reset), self._stream()))
         self.t_total_steps += 1
         info = {"cond_bits": self.cond_bits, "terminal_observation": self.terminal_obs,
-                "episode_return": self.ep_return_out, "episode_length": self.ep_len_out}
+                "episode_return": self.ep_return_out, "episode_length": self.ep_len_out, "delta_d": self.delta_d}
         return self.obs, self.reward, self.done, info
 
     def _action_dtype(self, actions, shape):
@@ -211,8 +214,15 @@ class BaseDocking3d:
             return ACT_F64
         raise TypeError("actions must be float32 or float64")
 
+    def _check_rows(self, *rows):
+        """Observation rows are written with 128-bit stores when n_obs is a multiple of 4 (include/dockauv.h)."""
+        if self.n_observations % 4 == 0:
+            for t in rows:
+                if t is not None and t.data_ptr() % 16 != 0:
+                    raise ValueError("obs / terminal_obs tensors must start at a 16-byte aligned address")
+
     def step_into(self, actions, obs, reward, done, cond_bits=None, terminal_obs=None, ep_return_out=None,
-                  ep_len_out=None):
+                  ep_len_out=None, delta_d_out=None):
         """``step`` with caller-chosen output tensors (e.g. row t of a device-resident rollout buffer): the kernel
         writes the observation / reward / done of this step straight into them, nothing is copied afterwards.
         ``obs`` f32 [N, n_obs], ``reward`` env dtype [N], ``done`` uint8 [N]; all contiguous, on the env's device."""
@@ -221,15 +231,16 @@ class BaseDocking3d:
                              (reward, (self.num_envs,), self.dtype), (done, (self.num_envs,), torch.uint8)):
             if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != self.device:
                 raise ValueError(f"output tensor must be contiguous {dt} {shape} on {self.device}")
+        self._check_rows(obs, terminal_obs)
         out = DockauvStepOut(*[_ptr(t) for t in (obs, reward, done, cond_bits, terminal_obs, ep_return_out,
-                                                 ep_len_out)])
+                                                 ep_len_out, delta_d_out)])
         actions = actions.contiguous()
         _capi.check(self._lib.dockauv_step(self._handle, _ptr(actions), adt, None, C.byref(out), None,
                                            int(self.auto_reset), self._stream()))
         self.t_total_steps += 1
 
     def rollout(self, actions, obs, reward, done, cond_bits=None, terminal_obs=None, ep_return_out=None,
-                ep_len_out=None, use_graph=True):
+                ep_len_out=None, use_graph=True, delta_d_out=None):
         """T steps with actions known up front (``actions`` [T, N, n_u] on the device; random-action rollouts,
         replayed logs) in ONE library call: row t of ``obs`` [T, N, n_obs] / ``reward`` [T, N] / ``done`` [T, N]
         receives the outputs of step t.  With ``use_graph`` the launch sequence is captured into a CUDA graph the
@@ -242,8 +253,9 @@ class BaseDocking3d:
                 raise ValueError(f"output tensor must be contiguous {dt} {shape} on {self.device}")
         if not actions.is_contiguous():
             raise ValueError("actions must be contiguous")
+        self._check_rows(obs, terminal_obs)
         out = DockauvRolloutOut(*[_ptr(t) for t in (obs, reward, done, cond_bits, terminal_obs, ep_return_out,
-                                                    ep_len_out)])
+                                                    ep_len_out, delta_d_out)])
         _capi.check(self._lib.dockauv_rollout(self._handle, _ptr(actions), adt, T, C.byref(out), int(self.auto_reset),
                                               int(bool(use_graph)), self._stream()))
         self.t_total_steps += T
@@ -327,6 +339,14 @@ class BaseDocking3d:
             put(self.spheres, np.asarray(spheres).reshape(len(spheres), -1), self.n_spheres * 4)
         put(self.t_steps, None if t_steps is None else np.asarray(t_steps).reshape(-1, 1), None)
         put(self.ep_return, None if ep_return is None else np.asarray(ep_return).reshape(-1, 1), None)
+        if goal is not None or capsules is not None or spheres is not None:
+            self.refresh_obstacles()
+
+    def refresh_obstacles(self):
+        """Call after writing ``self.capsules``, ``self.spheres`` or ``self.goal`` directly: the cull launch reads a
+        float copy of the obstacles relative to the goal that the library keeps (dockauv_refresh_obstacles);
+        ``reset`` and ``set_state`` do it themselves."""
+        _capi.check(self._lib.dockauv_refresh_obstacles(self._handle, self._stream()))
 
     # ------------------------------------------------------------------ statistics (FullDataStorage bookkeeping)
     def stats_tensor(self):
@@ -363,6 +383,21 @@ class BaseDocking3d:
         _capi.check(self._lib.dockauv_launch_count(self._handle, C.byref(n)))
         return n.value
 
+    def enable_step_graph(self, enabled=True):
+        """``step`` / ``step_into`` replay a cached CUDA graph of their launch sequence (default); False = plain launches."""
+        _capi.check(self._lib.dockauv_enable_step_graph(self._handle, int(bool(enabled))))
+
+    def step_graph_captures(self):
+        n = C.c_int64()
+        _capi.check(self._lib.dockauv_step_graph_captures(self._handle, C.byref(n)))
+        return n.value
+
+    def rollout_captures(self):
+        """How many times ``rollout(use_graph=True)`` had to capture its launch sequence (replays do not)."""
+        n = C.c_int64()
+        _capi.check(self._lib.dockauv_rollout_captures(self._handle, C.byref(n)))
+        return n.value
+
     # ------------------------------------------------------------------ conveniences mirroring the reference's info dict
     def info_dict(self, i):
         """The reference's per-step info dict (docking3d.py:388-400) for env i (device -> host read; small N only)."""
@@ -372,7 +407,8 @@ class BaseDocking3d:
                 "t_total_steps": self.t_total_steps, "cumulative_reward": float(self.ep_return[i].item()),
                 "last_reward": float(self.reward[i].item()), "done": bool(self.done[i].item()),
                 "conditions_true": idx, "conditions_true_info": [DONE_NAMES[k] for k in idx],
-                "collision": bool(bits >> 4 & 1), "goal_reached": bool(bits & 1)}
+                "collision": bool(bits >> 4 & 1), "goal_reached": bool(bits & 1),
+                "simulation_time": self.t_total_steps * float(self._params.h), "delta_d": float(self.delta_d[i].item())}
 
 
 class _DevView:

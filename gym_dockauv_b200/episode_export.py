@@ -54,14 +54,6 @@ class VehicleRecord:
         self.name, self.step_size, self.u_bound = name, float(step_size), np.asarray(u_bound)
 
 
-def _reference_shapes():
-    try:
-        from gym_dockauv.objects import shape   # only if the user has the reference installed
-        return shape
-    except Exception:   # noqa: BLE001
-        return None
-
-
 def _rzyx(phi, theta, psi):
     cphi, sphi, cth, sth, cpsi, spsi = np.cos(phi), np.sin(phi), np.cos(theta), np.sin(theta), np.cos(psi), np.sin(psi)
     return np.array([[cpsi * cth, -spsi * cphi + cpsi * sth * sphi, spsi * sphi + cpsi * cphi * sth],
@@ -79,9 +71,14 @@ class EpisodeRecorder:
     in ``env_ids``; every finished episode is written to ``path_folder`` as
     ``<utc>__<title>__EPISODE_<k>_DATA_STORAGE.pkl`` and all finished envs are reset (``env.reset(mask=done)``)."""
 
-    def __init__(self, env, env_ids, path_folder, title="", save=True):
+    def __init__(self, env, env_ids, path_folder, title="", save=True, shape_module=None):
+        """``shape_module``: optionally the reference's own ``gym_dockauv.objects.shape`` module, passed in by a caller
+        that has the reference installed and wants its ``Capsule`` / ``Sphere`` classes inside the pickles (what
+        ``plot_*`` of the reference draws); by default the files hold ``ShapeRecord`` stand-ins with the same
+        attributes.  This package never imports the reference on its own."""
         if env.auto_reset or env.debug is None:
             raise ValueError("create the env with auto_reset=False and debug_outputs=True")
+        self.shape_module = shape_module
         self.env, self.ids = env, [int(i) for i in env_ids]
         self.path_folder, self.title, self.save = path_folder, title, save
         self._sel = torch.as_tensor(self.ids, device=env.device)
@@ -169,7 +166,7 @@ class EpisodeRecorder:
         for key in ("states", "states_dot", "u", "nu_c", "radar"):
             r[key].append(r[key][-1])
         r["rewards"].append(r["_last_r"]); r["cum_rewards"].append(r["_cum"]); r["observation"].append(r["_last_obs"])
-        shape = _reference_shapes()
+        shape = self.shape_module
         if shape is not None:
             shapes = [shape.Capsule(position=(c[0:3] + c[3:6]) / 2, radius=c[6], vec_top=c[3:6]) for c in r["capsules"]]
             shapes += [shape.Sphere(position=s[0:3], radius=s[3]) for s in r["spheres"]]

@@ -12,11 +12,11 @@ import numpy as np
 from . import vehicles as _veh
 from .config import validate
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_U, MAX_CAPSULES, MAX_SPHERES, MAX_RAYS, N_REWARDS, N_STATS = 8, 8, 8, 256, 13, 16
 F64, F32 = 0, 1
 ACT_F64, ACT_F32 = 0, 1
-LAYOUTS = {"auto": 0, "thread_per_env": 1, "warp_rays": 2, "split": 3, "pipeline": 4}
+LAYOUTS = {"auto": 0, "thread_per_env": 1, "warp_rays": 2, "pipeline": 4}
 VEHICLE_IDS = {"BlueROV2": 0, "LAUV": 1}
 SCENARIO_IDS = {"SimpleDocking3d": 0, "SimpleCurrentDocking3d": 1, "CapsuleDocking3d": 2,
                 "CapsuleCurrentDocking3d": 3, "ObstaclesDocking3d": 4, "ObstaclesCurrentDocking3d": 5,
@@ -57,7 +57,7 @@ class DockauvBuffers(C.Structure):
 
 class DockauvStepOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("obs", "reward", "done", "cond_bits", "terminal_obs", "ep_return_out",
-                                          "ep_len_out")]
+                                          "ep_len_out", "delta_d_out")]
 
 
 class DockauvDebugOut(C.Structure):
@@ -66,7 +66,7 @@ class DockauvDebugOut(C.Structure):
 
 class DockauvRolloutOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("obs", "reward", "done", "cond_bits", "terminal_obs", "ep_return_out",
-                                          "ep_len_out")]
+                                          "ep_len_out", "delta_d_out")]
 
 
 def skew(a):

@@ -19,15 +19,20 @@ def shard_env_range(n_total, rank, world_size):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def reduce_stats(stats_tensor, group=None, async_op=False):
-    """Sum the statistics vectors of all ranks in place (torch.distributed all-reduce).  Works on the device
-    tensor returned by env.stats_tensor() (NCCL) or on a CPU tensor (gloo).  Returns the work handle if async."""
+def reduce_stats(stats_tensor, group=None):
+    """Sum of the statistics vectors of all ranks (torch.distributed all-reduce; NCCL for the device tensor returned by
+    ``env.stats_tensor()``, gloo for a CPU tensor).  The input is NOT modified: ``env.stats_tensor()`` is the library's
+    live accumulator, and reducing it in place would make every rank keep accumulating on top of the global sum (the
+    next reduce would then count earlier episodes world_size times).  A copy is reduced and returned; with one process
+    (or without an initialised process group) the copy is returned as is.  Call ``env.clear_stats()`` after the reduce
+    for per-rollout statistics, or keep accumulating for running totals -- both are consistent."""
     import torch.distributed as dist
     if stats_tensor.numel() != N_STATS:
         raise ValueError(f"statistics vector must have {N_STATS} entries")
-    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return None
-    return dist.all_reduce(stats_tensor, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    out = stats_tensor.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
 
 
 def summarize(stats):

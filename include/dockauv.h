@@ -28,8 +28,9 @@
  *   - plain C types only; no torch / C++ types cross this boundary.
  *   - all `*_dev` pointers are device pointers on the handle's device.  The library never allocates, frees
  *     or keeps caller buffers beyond what dockauv_bind() registered; the caller (PyTorch) owns them.  The
- *     handle owns its ray table, the statistics vector, the hand-off buffers between the launches of a step
- *     (~210 bytes per env) and, lazily, device staging for dockauv_step_host.
+ *     handle owns its ray table, the statistics vector, the buffers between the launches of a step
+ *     (a 16-word record, the ray list entry and a float copy of the obstacles: ~350 bytes per env) and, lazily, device
+ *     staging for dockauv_step_host.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are asynchronous and
  *     stream-ordered; one handle must not be used from two threads at once.  Large batches (>= 131,072 envs)
  *     are stepped as two halves on two handle-owned streams that are forked from / joined to `stream` by
@@ -51,7 +52,7 @@
 extern "C" {
 #endif
 
-#define DOCKAUV_ABI_VERSION 2
+#define DOCKAUV_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DOCKAUV_API __attribute__((visibility("default")))
@@ -97,10 +98,10 @@ extern "C" {
 /* kernel layouts */
 #define DOCKAUV_LAYOUT_AUTO 0
 #define DOCKAUV_LAYOUT_THREAD_PER_ENV 1   /* one thread does everything for one env */
-#define DOCKAUV_LAYOUT_WARP_RAYS 2        /* dynamics thread-per-env, radar one warp per env (lanes = rays) */
-#define DOCKAUV_LAYOUT_SPLIT 3            /* the same two phases as two launches per chunk, hand-off through L2 */
-#define DOCKAUV_LAYOUT_PIPELINE 4         /* four launches: dynamics, cull (thread per env), rays (one warp per env that
-                                             has an obstacle in view, from a compact list), finish (thread per env) */
+#define DOCKAUV_LAYOUT_WARP_RAYS 2        /* one launch: dynamics thread-per-env, radar one warp per env (lanes = rays) */
+#define DOCKAUV_LAYOUT_PIPELINE 4         /* three launches: dynamics (thread per env), cull + finish of the envs with nothing in
+                                             view (thread per env), rays + finish (one warp per env that has an obstacle in
+                                             view, from a compact list) */
 
 /* indices into the stats vector (sums since the last clear; reduce over ranks with one all-reduce) */
 #define DOCKAUV_STAT_EPISODES 0
@@ -128,7 +129,8 @@ typedef struct DockauvParams {
     int32_t action_factor_is_scalar;   /* config "action_reward_factors" was a python scalar */
     int32_t layout;              /* DOCKAUV_LAYOUT_* */
     int32_t force_current;       /* evaluate the ocean current even if the scenario spawns none (injected currents) */
-    int32_t split_chunk_envs;    /* DOCKAUV_LAYOUT_SPLIT: envs per launch pair (0 = library default) */
+    int32_t split_chunk_envs;    /* DOCKAUV_LAYOUT_PIPELINE: envs per launch group (0 = library default: the whole batch, in two
+                                    halves on two streams from 131,072 envs on) */
     /* rigid body + hydrodynamics (statespace.py) */
     double m;
     double r_G[3];
@@ -177,7 +179,9 @@ typedef struct DockauvBuffers {
     int32_t *episode;     /* int32[N]: episodes started so far (Philox counter) */
 } DockauvBuffers;
 
-/* Per-step outputs (device pointers; nullable ones are skipped). */
+/* Per-step outputs (device pointers; nullable ones are skipped).  When n_obs is a multiple of 4 (every stock radar
+ * geometry) observation rows are written with 128-bit stores: obs and terminal_obs must then be 16-byte aligned
+ * (DOCKAUV_EINVAL otherwise). */
 typedef struct DockauvStepOut {
     float *obs;            /* f32[N][n_obs] row-major; all-zero row when the env was auto-reset (docking3d.py:269,322) */
     void *reward;          /* real[N] */
@@ -187,6 +191,7 @@ typedef struct DockauvStepOut {
                               (rows of envs that are not done are left untouched) */
     void *ep_return_out;   /* real[N], nullable: return of the episode that ended this step (Monitor 'r') */
     int32_t *ep_len_out;   /* int32[N], nullable: length of the episode that ended this step (Monitor 'l') */
+    void *delta_d_out;     /* real[N], nullable: distance to the goal after the step = info["delta_d"] (docking3d.py:400) */
 } DockauvStepOut;
 
 /* Optional per-step intermediate values for the parity tests (device pointers, all nullable). */
@@ -211,6 +216,7 @@ typedef struct DockauvRolloutOut {
     float *terminal_obs;   /* f32[T][N][n_obs], nullable: rows of episodes that ended at step t (others untouched) */
     void *ep_return_out;   /* real[T][N], nullable: only entries of episodes that ended at step t are written */
     int32_t *ep_len_out;   /* int32[T][N], nullable: same; the call zero-fills it first, so length > 0 marks an end */
+    void *delta_d_out;     /* real[T][N], nullable */
 } DockauvRolloutOut;
 
 typedef struct DockauvHandle DockauvHandle;
@@ -232,11 +238,23 @@ DOCKAUV_API int dockauv_set_seed(DockauvHandle *h, uint64_t seed);
 /* Re-initialise envs whose mask byte is non-zero (all envs if mask_dev == NULL). */
 DOCKAUV_API int dockauv_reset(DockauvHandle *h, const uint8_t *mask_dev, void *stream);
 
+/* The cull launch reads a float copy of the obstacles relative to the goal, which the library keeps next to the bound
+ * buffers: dockauv_bind and every reset (dockauv_reset, auto-reset inside a step) write it.  A caller that writes the
+ * bound `capsules`, `spheres` or `goal` buffers ITSELF (exact-state injection: the reference's env.capsules = [...] /
+ * env.goal_location = ..., docking3d.py:860-946) calls this afterwards, on the stream that did the writes. */
+DOCKAUV_API int dockauv_refresh_obstacles(DockauvHandle *h, void *stream);
+
 /* One batched env.step().  actions_dev: [N][n_u] row-major, float or double per action_dtype.
  * noise_dev (nullable): real[N] N(0, sigma) draws for Current.sim; when NULL and cur_sigma > 0 the draw
  * comes from the handle's Philox stream.  auto_reset != 0 re-initialises finished envs in the same launch. */
 DOCKAUV_API int dockauv_step(DockauvHandle *h, const void *actions_dev, int action_dtype, const void *noise_dev,
                  const DockauvStepOut *out, const DockauvDebugOut *debug_or_null, int auto_reset, void *stream);
+
+/* dockauv_step replays a CUDA graph of its launch sequence, captured once per set of pointers (actions, noise, outputs) and
+ * cached per handle (96 sets; calls with debug outputs, with timing enabled, or on a stream that is itself being captured
+ * issue plain launches).  On by default; dockauv_enable_step_graph(h, 0) switches to plain launches. */
+DOCKAUV_API int dockauv_enable_step_graph(DockauvHandle *h, int enabled);
+DOCKAUV_API int dockauv_step_graph_captures(DockauvHandle *h, int64_t *n_captures);
 
 /* Same step with HOST buffers (pinned memory recommended): actions are copied in, obs/reward/done (and
  * cond_bits if non-NULL) are copied out, pipelined in chunks over the handle's internal streams; returns
@@ -285,10 +303,13 @@ DOCKAUV_API int dockauv_measure_peaks(int device, double *fp64_tflops, double *f
 /* Kernel-level accounting for bench.py: number of kernels launched by this handle so far, and CUDA-event
  * time (ms) of the most recent dockauv_step launch when timing is enabled. */
 DOCKAUV_API int dockauv_launch_count(DockauvHandle *h, int64_t *n_launches);
+/* how many times dockauv_rollout(use_graph) had to capture its launch sequence (a replay with the same pointers does not) */
+DOCKAUV_API int dockauv_rollout_captures(DockauvHandle *h, int64_t *n_captures);
 DOCKAUV_API int dockauv_enable_timing(DockauvHandle *h, int enabled);
 DOCKAUV_API int dockauv_last_step_ms(DockauvHandle *h, float *ms);
 /* Per-launch CUDA-event times (ms) of the most recent timed dockauv_step of a multi-launch layout, in launch order
- * (DOCKAUV_LAYOUT_PIPELINE: dynamics, cull, rays, finish); *n_launches = 0 for the single-launch layouts. */
+ * (DOCKAUV_LAYOUT_PIPELINE: dynamics, cull + finish, rays + finish; the last one only with obstacles); *n_launches = 0 for
+ * the single-launch layouts. */
 DOCKAUV_API int dockauv_last_step_launch_ms(DockauvHandle *h, float *ms, int capacity, int *n_launches);
 
 #ifdef __cplusplus

@@ -684,9 +684,12 @@ void orc_reset_env(const OrcParams *p, OrcEnv *e, int scenario, uint64_t seed, u
     }
 }
 
-int64_t orc_step_batch(const OrcParams *p, OrcEnv *envs, int64_t n, const void *actions, int action_is_f32,
-                       int scenario, uint64_t seed, uint64_t env_id0, float *obs, double *reward, uint8_t *done,
-                       int n_threads) {
+/* env_ids == NULL: env i has the global id env_id0 + i (a contiguous shard); else env i has the id env_ids[i] (an
+ * arbitrary sample of a larger batch: the Philox reset stream is keyed by the global id, so any subset can be
+ * followed on its own). */
+int64_t orc_step_batch_ids(const OrcParams *p, OrcEnv *envs, int64_t n, const void *actions, int action_is_f32,
+                           int scenario, uint64_t seed, uint64_t env_id0, const uint64_t *env_ids, float *obs,
+                           double *reward, uint8_t *done, uint8_t *cond_bits, int n_threads) {
     int64_t finished = 0;
     size_t astride = (size_t)p->n_u * (action_is_f32 ? 4 : 8);
 #ifdef _OPENMP
@@ -702,12 +705,24 @@ int64_t orc_step_batch(const OrcParams *p, OrcEnv *envs, int64_t n, const void *
         }
         if (reward) reward[i] = o.reward;
         if (done) done[i] = o.done;
+        if (cond_bits) {   /* bit k = done condition k, docking3d.py:606-617 */
+            uint8_t b = 0;
+            for (int k = 0; k < 5; k++) b |= (uint8_t)((o.cond[k] ? 1 : 0) << k);
+            cond_bits[i] = b;
+        }
         if (o.done) {
             finished++;
-            orc_reset_env(p, &envs[i], scenario, seed, env_id0 + (uint64_t)i);
+            orc_reset_env(p, &envs[i], scenario, seed, env_ids ? env_ids[i] : env_id0 + (uint64_t)i);
         }
     }
     return finished;
+}
+
+int64_t orc_step_batch(const OrcParams *p, OrcEnv *envs, int64_t n, const void *actions, int action_is_f32,
+                       int scenario, uint64_t seed, uint64_t env_id0, float *obs, double *reward, uint8_t *done,
+                       int n_threads) {
+    return orc_step_batch_ids(p, envs, n, actions, action_is_f32, scenario, seed, env_id0, NULL, obs, reward, done,
+                              NULL, n_threads);
 }
 
 int orc_sizeof_params(void) { return (int)sizeof(OrcParams); }

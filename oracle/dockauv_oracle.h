@@ -138,6 +138,12 @@ int64_t orc_step_batch(const OrcParams *p, OrcEnv *envs, int64_t n, const void *
                        int scenario, uint64_t seed, uint64_t env_id0, float *obs, double *reward, uint8_t *done,
                        int n_threads);
 
+/* The same for an arbitrary sample of a larger batch: env i has the global id env_ids[i] (NULL: env_id0 + i);
+ * cond_bits (nullable): bit k = done condition k of the step. */
+int64_t orc_step_batch_ids(const OrcParams *p, OrcEnv *envs, int64_t n, const void *actions, int action_is_f32,
+                           int scenario, uint64_t seed, uint64_t env_id0, const uint64_t *env_ids, float *obs,
+                           double *reward, uint8_t *done, uint8_t *cond_bits, int n_threads);
+
 int orc_sizeof_params(void);
 int orc_sizeof_env(void);
 int orc_sizeof_stepout(void);

@@ -105,6 +105,10 @@ def lib():
     L.orc_step_batch.restype = C.c_int64
     L.orc_step_batch.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                  C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_step_batch_ids.restype = C.c_int64
+    L.orc_step_batch_ids.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int]
     assert L.orc_sizeof_params() == C.sizeof(OrcParams), (L.orc_sizeof_params(), C.sizeof(OrcParams))
     assert L.orc_sizeof_env() == C.sizeof(OrcEnv)
     assert L.orc_sizeof_stepout() == C.sizeof(OrcStepOut)
@@ -273,33 +277,58 @@ def step(P, E, action, noise_w=0.0):
 
 
 class BatchOracle:
-    """N independent envs stepped by orc_step_batch (OpenMP) -- the CPU baseline of bench.py."""
+    """N independent envs stepped by orc_step_batch (OpenMP) -- the CPU baseline of bench.py.  ``env_ids`` (optional,
+    uint64 array of length n_envs) makes env i the env with that GLOBAL id of a larger batch: the reset stream is
+    keyed by the global id, so an arbitrary sample of a 1M-env GPU batch can be followed on its own."""
 
-    def __init__(self, config, scenario, n_envs, seed=0, n_extra_spheres=0, n_threads=0, env_id0=0):
-        self.P = make_params(config)
+    def __init__(self, config, scenario, n_envs, seed=0, n_extra_spheres=0, n_threads=0, env_id0=0, env_ids=None,
+                 vehicle_key=None):
+        self.P = make_params(config, vehicle_key=vehicle_key)
         self.n = int(n_envs)
         self.scenario = SCENARIOS[scenario] | (int(n_extra_spheres) << 8)
         self.seed, self.n_threads, self.env_id0 = int(seed), int(n_threads), int(env_id0)
+        self.env_ids = None
+        if env_ids is not None:
+            self.env_ids = np.ascontiguousarray(env_ids, dtype=np.uint64)
+            assert self.env_ids.shape == (self.n,)
         self.envs = (OrcEnv * self.n)()
         L = lib()
         for i in range(self.n):
-            L.orc_reset_env(C.byref(self.P), C.byref(self.envs[i]), self.scenario, self.seed, self.env_id0 + i)
+            gid = int(self.env_ids[i]) if self.env_ids is not None else self.env_id0 + i
+            L.orc_reset_env(C.byref(self.P), C.byref(self.envs[i]), self.scenario, self.seed, gid)
         self.obs = np.zeros((self.n, self.P.n_obs), dtype=np.float32)
         self.reward = np.zeros(self.n)
         self.done = np.zeros(self.n, dtype=np.uint8)
+        self.cond_bits = np.zeros(self.n, dtype=np.uint8)      # bit k = done condition k of the last step
+        # zero-copy numpy view of the env array (AoS) for field()
+        self._raw = np.ctypeslib.as_array(C.cast(self.envs, C.POINTER(C.c_uint8)), shape=(self.n * C.sizeof(OrcEnv),))
+        self._raw = self._raw.reshape(self.n, C.sizeof(OrcEnv))
 
     def step(self, actions):
         a = np.ascontiguousarray(actions)
         is_f32 = a.dtype == np.float32
         if not is_f32:
             a = a.astype(np.float64)
-        fin = lib().orc_step_batch(C.byref(self.P), C.cast(self.envs, C.c_void_p), self.n,
-                                   a.ctypes.data_as(C.c_void_p), int(is_f32), self.scenario, self.seed,
-                                   self.env_id0, self.obs.ctypes.data_as(C.c_void_p),
-                                   self.reward.ctypes.data_as(C.c_void_p), self.done.ctypes.data_as(C.c_void_p),
-                                   self.n_threads)
+        ids = self.env_ids.ctypes.data_as(C.c_void_p) if self.env_ids is not None else None
+        fin = lib().orc_step_batch_ids(C.byref(self.P), C.cast(self.envs, C.c_void_p), self.n,
+                                       a.ctypes.data_as(C.c_void_p), int(is_f32), self.scenario, self.seed,
+                                       self.env_id0, ids, self.obs.ctypes.data_as(C.c_void_p),
+                                       self.reward.ctypes.data_as(C.c_void_p), self.done.ctypes.data_as(C.c_void_p),
+                                       self.cond_bits.ctypes.data_as(C.c_void_p), self.n_threads)
         return self.obs, self.reward, self.done, fin
 
     def field(self, name):
-        return np.array([np.ctypeslib.as_array(getattr(e, name)) if hasattr(getattr(e, name), "__len__")
-                         else getattr(e, name) for e in self.envs])
+        """Copy of one OrcEnv field over all envs ([n] or [n, k...]), read through a strided view of the AoS block."""
+        f = getattr(OrcEnv, name)
+        ctype = dict(OrcEnv._fields_)[name]
+        base = ctype
+        shape = []
+        while hasattr(base, "_length_"):
+            shape.append(base._length_)
+            base = base._type_
+        dt = np.dtype(base)
+        count = int(np.prod(shape)) if shape else 1
+        out = np.empty((self.n, count), dtype=dt)
+        rows = self._raw[:, f.offset:f.offset + count * dt.itemsize]
+        out.view(np.uint8).reshape(self.n, -1)[:] = rows
+        return out.reshape([self.n] + shape) if shape else out[:, 0].copy()

@@ -10,6 +10,7 @@ cfg = dict(BASE_CONFIG); cfg["radar"] = dict(RADAR_64)
 N = 1 << 20
 env = envs.SCENARIOS[name](cfg, num_envs=N, seed=0, layout=layout, n_synthetic_spheres=nsph, split_chunk_envs=chunk)
 env.reset()
+env.enable_step_graph(False)      # plain launches: ncu's --launch-skip counts kernels
 gen = torch.Generator(device="cuda").manual_seed(1)
 pool = [torch.rand(N, 6, device="cuda", generator=gen) * 2 - 1 for _ in range(8)]
 for k in range(steps):

@@ -10,7 +10,7 @@ N = 1000          # not a multiple of any CTA size
 gen = torch.Generator(device="cuda").manual_seed(0)
 for name, kw in [("ObstaclesDocking3d", dict(n_synthetic_spheres=3)), ("ObstaclesCurrentDocking3d", dict(n_synthetic_spheres=8)),
                  ("SimpleDocking3d", {}), ("CapsuleCurrentDocking3d", {})]:
-    for layout in ("pipeline", "split", "warp_rays", "thread_per_env"):
+    for layout in ("pipeline", "warp_rays", "thread_per_env"):
         env = envs.SCENARIOS[name](cfg, num_envs=N, seed=1, layout=layout, **kw)
         env.reset()
         # short episodes so that resets happen inside the run

@@ -12,10 +12,8 @@ for name, kw in [("SimpleDocking3d", dict(layout="thread_per_env")), ("SimpleDoc
                  ("CapsuleDocking3d", dict(layout="warp_rays")), ("ObstaclesDocking3d", dict(layout="warp_rays")),
                  ("ObstaclesDocking3d", dict(layout="warp_rays", n_synthetic_spheres=3)),
                  ("ObstaclesCurrentDocking3d", dict(layout="warp_rays", n_synthetic_spheres=3)),
-                 ("ObstaclesDocking3d", dict(layout="split", n_synthetic_spheres=3)),
-                 ("ObstaclesDocking3d", dict(layout="split", n_synthetic_spheres=3, split_chunk_envs=1 << 20)),
-                 ("ObstaclesDocking3d", dict(layout="split", n_synthetic_spheres=3, split_chunk_envs=131072)),
-                 ("SimpleDocking3d", dict(layout="split")),
+                 ("ObstaclesDocking3d", dict(layout="pipeline", n_synthetic_spheres=3)),
+                 ("SimpleDocking3d", dict(layout="pipeline")),
                  ("ObstaclesDocking3d", dict(layout="thread_per_env", n_synthetic_spheres=3))][:(int(os.environ.get("N_CASES", "99")))]:
     env = envs.SCENARIOS[name](cfg, num_envs=N, seed=0, **kw)
     env.reset()

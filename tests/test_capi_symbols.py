@@ -42,10 +42,21 @@ def test_argument_validation_without_gpu():
     h = C.c_void_p()
     p.abi_version = 99
     assert lib.dockauv_create(C.byref(p), 16, 0, C.byref(h)) == -1 and b"ABI" in lib.dockauv_last_error()
-    p.abi_version = 2
+    from gym_dockauv_b200.params import ABI_VERSION
+    p.abi_version = ABI_VERSION
     assert lib.dockauv_create(C.byref(p), 0, 0, C.byref(h)) == -1
     p.n_rays = 62
     assert lib.dockauv_create(C.byref(p), 16, 0, C.byref(h)) == -1 and b"radar" in lib.dockauv_last_error()
+    # every value that would silently produce inf / NaN observations or read uninitialised reset draws is refused
+    for field, bad, word in (("n_synthetic_spheres", -1, b"n_synthetic_spheres"), ("n_synthetic_spheres", 1, b"n_synthetic_spheres"),
+                             ("h", 0.0, b"t_step_size"), ("max_timesteps", 0, b"max_timesteps"), ("u_max", 0.0, b"u_max"),
+                             ("r_max", -1.0, b"u_max"), ("max_attitude", 0.0, b"max_attitude"),
+                             ("max_dist_from_goal", 0.0, b"max_dist_from_goal"), ("dist_goal_reached_tol", 0.0, b"dist_goal_reached_tol"),
+                             ("radar_max_dist", 0.0, b"max_dist"), ("layout", 3, b"layout"), ("reward_set", 3, b"reward_set")):
+        q, _ = pack_params(BASE_CONFIG, "ObstaclesDocking3d")
+        setattr(q, field, bad)
+        assert lib.dockauv_create(C.byref(q), 16, 0, C.byref(h)) == -1, field
+        assert word in lib.dockauv_last_error(), (field, lib.dockauv_last_error())
     assert lib.dockauv_step(None, None, 0, None, None, None, 0, None) == -1
     assert lib.dockauv_destroy(None) == 0
     # the caller-side entry points validate their arguments before touching the device
@@ -56,6 +67,8 @@ def test_argument_validation_without_gpu():
     ms = (C.c_float * 4)()
     assert lib.dockauv_last_step_launch_ms(None, ms, 4, C.byref(n)) == -1
     assert lib.dockauv_step_host(None, None, 0, None, None, None, None, 1, None) == -1
+    assert lib.dockauv_refresh_obstacles(None, None) == -1
+    assert lib.dockauv_rollout_captures(None, None) == -1
 
 
 def test_no_cpu_fallback():

@@ -39,7 +39,7 @@ def _env_for_case(g, layout, precision="f64", debug=True):
     return env
 
 
-@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split", "pipeline"])
+@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "pipeline"])
 @pytest.mark.parametrize("name", case_names())
 def test_cuda_matches_reference_trace(name, layout):
     import torch
@@ -53,7 +53,7 @@ def test_cuda_matches_reference_trace(name, layout):
     f32 = meta["action_dtype"] == "f32"
     unstable = meta["vehicle"] == "LAUV" and meta["config"]["t_step_size"] > 0.05
     alive = np.ones(E, dtype=bool)           # still inside the recorded episode and not blown up
-    worst = dict(state=0.0, u=0.0, ray=0.0, reward=0.0, rarr=0.0, nav=0.0, edot=0.0, nu_c=0.0, ret=0.0)
+    worst = dict(state=0.0, u=0.0, ray=0.0, reward=0.0, rarr=0.0, nav=0.0, edot=0.0, nu_c=0.0, ret=0.0, delta_d=0.0)
     obs_mismatch, compared = 0, 0
     for t in range(T):
         alive &= t < g["ep_len"]
@@ -79,6 +79,7 @@ def test_cuda_matches_reference_trace(name, layout):
         worst["state"] = max(worst["state"], rel_err(st[m], g["state"][m, t]))
         worst["u"] = max(worst["u"], rel_err(env.u_prev.t().cpu().numpy()[m, :meta["n_u"]], g["u"][m, t]))
         worst["reward"] = max(worst["reward"], rel_err(reward.cpu().numpy()[m], g["reward"][m, t]))
+        worst["delta_d"] = max(worst["delta_d"], rel_err(info["delta_d"].cpu().numpy()[m], g["delta_d"][m, t]))   # info["delta_d"]
         if dbg:
             worst["ray"] = max(worst["ray"], rel_err(env.debug["ray_dist"].t().cpu().numpy()[m], g["ray_dist"][m, t]))
             worst["rarr"] = max(worst["rarr"], rel_err(env.debug["reward_arr"].t().cpu().numpy()[m], g["reward_arr"][m, t]))
@@ -134,7 +135,7 @@ def _oracle_rollout(config, scenario, n, steps, seed, n_synth, dtype, layout, pr
     return out
 
 
-@pytest.mark.parametrize("layout", ["warp_rays", "split", "pipeline"])
+@pytest.mark.parametrize("layout", ["warp_rays", "pipeline"])
 @pytest.mark.parametrize("radar,n_synth", [
     (dict(alpha=60, beta=80, ray_per_deg=5, blocksize_reduce=2), 3),     # 13 x 17 = 221 rays (8 per lane), 63 pooled cells
     (dict(alpha=70, beta=70, ray_per_deg=10, blocksize_reduce=3), 8),    # 3 x 3 pooling blocks; 13 obstacles (16-slot path)
@@ -153,7 +154,7 @@ def test_radar_extremes_vs_oracle(layout, radar, n_synth):
     assert r["worst_state"] < TOL and r["worst_reward"] < TOL and r["obs_worst"] < 2e-7, r
 
 
-@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "split", "pipeline"])
+@pytest.mark.parametrize("layout", ["thread_per_env", "warp_rays", "pipeline"])
 def test_random_rollout_with_autoreset_vs_oracle(layout):
     """256 envs x 300 steps of the BASELINE C4 workload (64 rays, 5 capsules + 3 spheres), auto-reset on."""
     from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
@@ -213,9 +214,10 @@ def test_fp32_variant():
         d, rd = done.cpu().numpy().astype(bool), rdone.astype(bool)
         mismatches += int(((d != rd) & alive).sum())
         m = alive & ~d & ~rd
-        worst["state"] = max(worst["state"], rel_err(env.state.t().cpu().numpy().astype(np.float64)[m], bo.field("state")[m]))
-        worst["reward"] = max(worst["reward"], rel_err(rew.cpu().numpy().astype(np.float64)[alive], rrew[alive]))
-        worst["obs"] = max(worst["obs"], rel_err(obs.cpu().numpy()[m], robs[m]))
+        # the FP32 bound is stated with a floor of 1.0 (absolute below 1): float32 carries 7 digits of O(10) positions
+        worst["state"] = max(worst["state"], rel_err(env.state.t().cpu().numpy().astype(np.float64)[m], bo.field("state")[m], floor=1.0))
+        worst["reward"] = max(worst["reward"], rel_err(rew.cpu().numpy().astype(np.float64)[alive], rrew[alive], floor=1.0))
+        worst["obs"] = max(worst["obs"], rel_err(obs.cpu().numpy()[m], robs[m], floor=1.0))
         alive &= ~(d | rd)
     assert alive.sum() > n // 3
     assert worst["state"] < 2e-5 and worst["reward"] < 5e-5 and worst["obs"] < 5e-4, worst
@@ -286,6 +288,61 @@ def test_step_host_matches_device_step():
     e2.close()
 
 
+def test_device_without_index_and_misaligned_rows():
+    """device="cuda" means the current device (handle, tensors and the device checks agree); observation rows that do not
+    start at a 16-byte boundary are refused instead of faulting in a 128-bit store."""
+    import torch
+    from gym_dockauv_b200 import _capi, envs
+    from gym_dockauv_b200.config import BASE_CONFIG
+    env = envs.ObstaclesDocking3d(dict(BASE_CONFIG), num_envs=300, device="cuda")
+    assert env.device == torch.device("cuda", torch.cuda.current_device())
+    env.reset()
+    a = torch.zeros(300, 6, device="cuda")
+    obs, reward, done, info = env.step(a)
+    assert torch.isfinite(obs).all() and info["delta_d"].shape == (300,) and (info["delta_d"] > 0).all()
+    d = env.info_dict(0)
+    assert d["delta_d"] == float(info["delta_d"][0]) and abs(d["simulation_time"] - 0.1) < 1e-15
+    # a view whose storage offset is one float: misaligned rows
+    big = torch.zeros(300 * env.n_observations + 4, dtype=torch.float32, device="cuda")
+    bad = big[1:1 + 300 * env.n_observations].view(300, env.n_observations)
+    with pytest.raises(ValueError):
+        env.step_into(a, bad, env.reward, env.done)
+    out = envs.DockauvStepOut(*[C.c_void_p(t.data_ptr()) for t in (bad, env.reward, env.done)], None, None, None, None, None)
+    rc = env._lib.dockauv_step(env._handle, C.c_void_p(a.data_ptr()), 1, None, C.byref(out), None, 1, None)
+    assert rc == -1 and b"16-byte" in env._lib.dockauv_last_error()
+    env.close()
+
+
+def test_rollout_graph_is_replayed_not_recaptured():
+    """dockauv_rollout(use_graph): the same pointers replay the captured launch sequence; other pointers re-capture."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.config import BASE_CONFIG
+    n, T = 4096, 6
+    env = envs.ObstaclesDocking3d(dict(BASE_CONFIG), num_envs=n, seed=3)
+    ref = envs.ObstaclesDocking3d(dict(BASE_CONFIG), num_envs=n, seed=3)
+    env.reset()
+    ref.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    acts = torch.rand(T, n, 6, device="cuda", generator=gen) * 2 - 1
+    obs = torch.zeros(T, n, env.n_observations, device="cuda")
+    rew = torch.zeros(T, n, dtype=torch.float64, device="cuda")
+    done = torch.zeros(T, n, dtype=torch.uint8, device="cuda")
+    dd = torch.zeros(T, n, dtype=torch.float64, device="cuda")
+    for rep in range(4):
+        env.rollout(acts, obs, rew, done, delta_d_out=dd)
+        for t in range(T):
+            o, r, d, info = ref.step(acts[t])
+            assert torch.equal(o, obs[t]) and torch.equal(r, rew[t]) and torch.equal(d, done[t])
+            assert torch.equal(info["delta_d"], dd[t])
+        assert env.rollout_captures() == 1, rep
+    obs2 = torch.zeros_like(obs)
+    env.rollout(acts, obs2, rew, done)
+    assert env.rollout_captures() == 2
+    env.close()
+    ref.close()
+
+
 def test_layouts_agree_bitwise_on_flags_large_batch():
     """65,536 envs, 40 steps: all kernel layouts give identical done flags / observations and rewards within 1e-12."""
     import torch
@@ -293,7 +350,7 @@ def test_layouts_agree_bitwise_on_flags_large_batch():
     from gym_dockauv_b200.config import BASE_CONFIG
     n = 65536
     es = [envs.ObstaclesCurrentDocking3d(dict(BASE_CONFIG), num_envs=n, seed=4, layout=l)
-          for l in ("thread_per_env", "warp_rays", "split", "pipeline")]
+          for l in ("thread_per_env", "warp_rays", "pipeline")]
     for e in es:
         e.reset()
     gen = torch.Generator(device="cuda").manual_seed(0)
@@ -331,7 +388,7 @@ def test_step_in_parts_equals_one_launch_group():
     assert torch.equal(es[0].state, es[1].state) and torch.equal(es[0].episode, es[1].episode)
     s0, s1 = es[0].get_stats(), es[1].get_stats()
     assert s0["env_steps"] == s1["env_steps"] == 12 * n and s0["episodes"] == s1["episodes"]
-    assert es[0].launch_count() - es[1].launch_count() == 12 * 4      # 8 launches per step against 4
+    assert es[0].launch_count() - es[1].launch_count() == 12 * 3      # 6 launches per step against 3
     for e in es:
         e.close()
 

@@ -22,7 +22,7 @@ def test_all_layouts_agree_on_odd_batch(name, kw):
     cfg = dict(BASE_CONFIG)
     cfg["radar"] = dict(RADAR_64)
     N = 1000
-    layouts = ("thread_per_env", "warp_rays", "split", "pipeline")
+    layouts = ("thread_per_env", "warp_rays", "pipeline")
     es = [envs.SCENARIOS[name](cfg, num_envs=N, seed=11, layout=l, **kw) for l in layouts]
     for e in es:
         e.reset()
@@ -56,8 +56,8 @@ def test_all_layouts_agree_on_odd_batch(name, kw):
         assert rel_err(s["sum_return"], s0["sum_return"]) < 1e-10
     # host-buffer entry point on the default layout vs the device one
     a = np.random.default_rng(1).uniform(-1, 1, (N, es[0].n_actions)).astype(np.float32)
-    oh, rh, dh, _ = es[3].step_host(a)
-    od, rd, dd, _ = es[2].step(torch.as_tensor(a, device="cuda"))
+    oh, rh, dh, _ = es[2].step_host(a)
+    od, rd, dd, _ = es[1].step(torch.as_tensor(a, device="cuda"))
     assert np.array_equal(dh, dd.cpu().numpy().astype(bool)) and np.array_equal(oh, od.cpu().numpy())
     assert rel_err(rh, rd.cpu().numpy()) < 1e-12
     for e in es:

@@ -20,8 +20,11 @@ def _worker(rank, world, port, out):
     local[2] = 500.0 * (rank + 1)       # sum_length
     local[7] = rank                     # collisions
     local[10] = float(e - b)            # env_steps
-    reduce_stats(local)
-    s = summarize(local)
+    before = local.clone()
+    red = reduce_stats(local)
+    assert torch.equal(local, before)       # the live accumulator is left alone; a second reduce counts nothing twice
+    assert torch.equal(reduce_stats(local), red)
+    s = summarize(red)
     out[rank] = (b, e, s["episodes"], s["mean_return"], s["mean_length"], s["env_steps"], s["collision_rate"])
     dist.destroy_process_group()
 
