@@ -11,8 +11,8 @@ NCCL all-reduce of the episode statistics per rollout).  `--scaling strong` shar
 (config C4 as BASELINE.json words it); a run with more than one rank also measures that strong-scaling point in a second
 pass and reports it as `strong` next to the weak-scaling `value`.
 
-One "step" = one batched env.step() over every env of the rank (three launches -- dynamics, cull + finish, rays +
-finish -- for each half of the batch, the halves on two streams).  Rank 0 prints ONE JSON line.
+One "step" = one batched env.step() over every env of the rank (four launches -- dynamics, cull + finish, rays +
+finish, episode end -- for each half of the batch, the halves on two streams).  Rank 0 prints ONE JSON line.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The per-step
 working set (~0.9 GB at 1M envs) is far larger than L2 (126 MB), so no explicit L2 flush is needed at the default size
 (stated in config.l2; smaller configs rotate through a pool of action tensors and say so).  Actions are synthetic
@@ -44,23 +44,25 @@ N_SYNTH_SPHERES = 3
 # 5 capsules x 33 + 3 spheres x 10 + pool / OA 8).  Bytes: every persistent item read once and written once.
 CONFIGS = {
     "C2": dict(scenario="SimpleDocking3d", vehicle="BlueROV2", envs=65536, radar64=False, n_synth=0, h=0.1,
-               bytes=538, flops=2900, launch_flops=dict(dynamics=2900, cull_finish=0, rays_finish=0),
-               launch_bytes=dict(dynamics=458, cull_finish=80, rays_finish=0),
+               bytes=538, flops=2900, launch_flops=dict(dynamics=2900, cull_finish=0, rays_finish=0, episode_end=0),
+               launch_bytes=dict(dynamics=458, cull_finish=80, rays_finish=0, episode_end=0),
                workload="C2: SimpleDocking3d, BlueROV2, 65,536 envs, dynamics + reward only (no obstacles: every ray "
                         "reads max_dist), random actions U(-1,1) f32, auto-reset"),
     "C3": dict(scenario="CapsuleCurrentDocking3d", vehicle="LAUV", envs=262144, radar64=False, n_synth=0, h=0.02,
-               bytes=534, flops=7250, launch_flops=dict(dynamics=3050, cull_finish=35, rays_finish=4165),
-               launch_bytes=dict(dynamics=398, cull_finish=136, rays_finish=0),
+               bytes=534, flops=7250, launch_flops=dict(dynamics=3050, cull_finish=35, rays_finish=4165, episode_end=0),
+               launch_bytes=dict(dynamics=398, cull_finish=136, rays_finish=0, episode_end=0),
                workload="C3: CapsuleCurrentDocking3d, LAUV with ocean current, 262,144 envs, docking-capsule collision "
                         "checks, t_step_size 0.02 (the reference's integrator diverges at its stock 0.1 for this "
                         "vehicle, SURVEY.md 8c), random actions U(-1,1) f32, auto-reset"),
     "C4": dict(scenario="ObstaclesDocking3d", vehicle="BlueROV2", envs=1 << 20, radar64=True, n_synth=N_SYNTH_SPHERES, h=0.1,
-               bytes=898, flops=17700, launch_flops=dict(dynamics=2900, cull_finish=205, rays_finish=14592),
-               launch_bytes=dict(dynamics=458, cull_finish=440, rays_finish=0),
+               bytes=898, flops=17700, launch_flops=dict(dynamics=2900, cull_finish=205, rays_finish=14592, episode_end=0),
+               launch_bytes=dict(dynamics=458, cull_finish=440, rays_finish=0, episode_end=0),
                workload="C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions "
                         "U(-1,1) f32, auto-reset of finished envs"),
 }
-LAUNCH_NAMES = ("dynamics", "cull_finish", "rays_finish")
+def launch_names(c):
+    return ("dynamics", "cull_finish", "rays_finish", "episode_end") if c["scenario"] != "SimpleDocking3d" else \
+        ("dynamics", "episode_end")
 
 
 def workload_config(c):
@@ -456,7 +458,7 @@ def run_ours(args, rank, world, local_rank):
             print(f"peak measurement failed: {ex}", file=sys.stderr)
         pipe_name = "fp64" if args.precision == "f64" else "fp32"
         pipe_peak = fp64_peak if args.precision == "f64" else fp32_peak
-        names = LAUNCH_NAMES[:len(launch_ms)]
+        names = launch_names(c)[:len(launch_ms)]
         launches_ms = {n: float(v) for n, v in zip(names, launch_ms)}
         dominant = names[int(np.argmax(launch_ms))] if len(launch_ms) else None
         ncu, ncu_src = ncu_figures(args.config)

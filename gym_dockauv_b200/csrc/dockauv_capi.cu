@@ -328,7 +328,7 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         const size_t n = (size_t)n_envs;
         const int n_obsf = 2 * p->n_capsules + p->n_spheres;
         const size_t off_rec = 0, off_obsf = off_rec + 16 * esz * n, off_list = off_obsf + 16 * (size_t)n_obsf * n;
-        const size_t off_cnt = off_list + 8 * n;
+        const size_t off_end = off_list + 8 * n, off_cnt = off_end + 4 * ((n + 1) & ~(size_t)1);
         const size_t n_cnt = 2 * (n / 128 + 2);      // two list counters per concurrently stepped env range
         cudaError_t e5 = cudaMalloc(&h->pipe_buf, off_cnt + 4 * n_cnt);
         if (e5 == cudaSuccess) e5 = cudaMemset(h->pipe_buf, 0, off_cnt + 4 * n_cnt);
@@ -345,6 +345,7 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         h->kd.obsf = h->kf.obsf = n_obsf > 0 ? (float4 *)(base + off_obsf) : nullptr;
         h->kd.n_obsf = h->kf.n_obsf = n_obsf;
         h->kd.view_list = h->kf.view_list = (unsigned long long *)(base + off_list);
+        h->kd.ended_list = h->kf.ended_list = (uint32_t *)(base + off_end);
         h->kd.view_count = h->kf.view_count = (unsigned int *)(base + off_cnt);
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -482,7 +483,7 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
     const bool staged = dbg == nullptr;   // else: the fused kernel
     if (layout == DOCKAUV_LAYOUT_PIPELINE && staged) {
         const int64_t chunk = h->kd.chunk_envs > 0 ? h->kd.chunk_envs : (end - begin);
-        h->launches += 3 * ((end - begin + chunk - 1) / chunk);
+        h->launches += ((h->params.n_capsules + h->params.n_spheres) > 0 ? 4 : 2) * ((end - begin + chunk - 1) / chunk);
     } else {
         h->launches += 1;
     }

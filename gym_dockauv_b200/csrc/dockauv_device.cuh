@@ -39,6 +39,8 @@ struct Mth<double> {
         *s = r.x;
         *c = r.y;
     }
+    static __device__ __forceinline__ double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }   // never contracted
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
@@ -88,6 +90,8 @@ struct Mth<float> {
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
     static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
     static __device__ __forceinline__ void sincos_(float x, float *s, float *c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
     static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
@@ -301,12 +305,14 @@ __device__ __forceinline__ void nu_dot(const KParams<T> &p, const T nu[6], const
         // diagonal and [0,4] [4,0] [1,3] [3,1].  The dense product adds exact zeros for the other 26 entries -- unless
         // a component of f is inf / NaN, in which case 0 * f poisons EVERY row; `z` keeps that behaviour.
         const T z = (((f[0] + f[1]) + (f[2] + f[3])) + (f[4] + f[5])) * T(0);
-        out[0] = p.M_inv[0] * f[0] + (p.M_inv[4] * f[4] + z);
-        out[1] = p.M_inv[7] * f[1] + (p.M_inv[9] * f[3] + z);
-        out[2] = p.M_inv[14] * f[2] + z;
-        out[3] = p.M_inv[19] * f[1] + (p.M_inv[21] * f[3] + z);
-        out[4] = p.M_inv[24] * f[0] + (p.M_inv[28] * f[4] + z);
-        out[5] = p.M_inv[35] * f[5] + z;
+        // same operation order as the dense loop below (first product rounded, the second one fused into it), so the two
+        // forms give identical bits for finite f
+        out[0] = Mth<T>::fma_(p.M_inv[4], f[4], Mth<T>::mul_(p.M_inv[0], f[0])) + z;
+        out[1] = Mth<T>::fma_(p.M_inv[9], f[3], Mth<T>::mul_(p.M_inv[7], f[1])) + z;
+        out[2] = Mth<T>::mul_(p.M_inv[14], f[2]) + z;
+        out[3] = Mth<T>::fma_(p.M_inv[21], f[3], Mth<T>::mul_(p.M_inv[19], f[1])) + z;
+        out[4] = Mth<T>::fma_(p.M_inv[28], f[4], Mth<T>::mul_(p.M_inv[24], f[0])) + z;
+        out[5] = Mth<T>::mul_(p.M_inv[35], f[5]) + z;
     } else {
 #pragma unroll
         for (int i = 0; i < 6; i++) {
@@ -326,13 +332,24 @@ __device__ __forceinline__ void rzyx(T sphi, T cphi, T sth, T cth, T spsi, T cps
     R[6] = -sth;       R[7] = cth * sphi;                       R[8] = cth * cphi;
 }
 
+// parked values (shared memory, stride ST != 1) are read through volatile: ptxas otherwise hoists the loads to the top
+// of the integration and spills exactly as before
+template <int ST, typename T>
+__device__ __forceinline__ T parked(const T *q, int i) {
+    if (ST == 1) return q[i];
+    return reinterpret_cast<const volatile T *>(q)[i * ST];
+}
+
 // One evaluation of the reduced right-hand side (auvsim.py:110-160) at y = (Theta, nu_r).
 //   tr = sin/cos of (phi, theta, psi) at y: {sphi, cphi, sth, cth, spsi, cpsi} (psi only read if WPOS)
 //   k[0:3] = T(phi, theta) nu2 (geomutils.py:72-75), k[3:9] = nu_dot;  if WPOS, pacc += wpos * R(Theta) (nu1 + nu_c).
 //   CUR = false: no ocean current (nu_c is not read).
-template <typename T, int VEH, bool WPOS, bool SPM = false, bool CUR = true>
-__device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T tr[6], const T tau[6], const T nu_c[3],
+template <typename T, int VEH, bool WPOS, bool SPM = false, bool CUR = true, int ST = 1>
+__device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T tr[6], const T *tau_s, const T nu_c[3],
                                      T wpos, T pacc[3], T k[9]) {
+    T tau[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) tau[i] = parked<ST>(tau_s, i);
     const T sphi = tr[0], cphi = tr[1], sth = tr[2], cth = tr[3];
     const T *nu = y + 3;
     T inv_cth = T(1) / cth;
@@ -357,11 +374,11 @@ __device__ __forceinline__ void rhs9(const KParams<T> &p, const T y[9], const T 
 }
 
 // sin/cos of the stage attitude Theta0 + d from the pre-step values tr0 (psi skipped when the stage has no position weight)
-template <typename T, bool WPSI>
-__device__ __forceinline__ void stage_trig(const T tr0[6], const T d[3], T tr[6]) {
-    sincos_shift<T>(tr0[0], tr0[1], d[0], &tr[0], &tr[1]);
-    sincos_shift<T>(tr0[2], tr0[3], d[1], &tr[2], &tr[3]);
-    if (WPSI) sincos_shift<T>(tr0[4], tr0[5], d[2], &tr[4], &tr[5]);
+template <typename T, bool WPSI, int ST = 1>
+__device__ __forceinline__ void stage_trig(const T *tr0, const T d[3], T tr[6]) {
+    sincos_shift<T>(parked<ST>(tr0, 0), parked<ST>(tr0, 1), d[0], &tr[0], &tr[1]);
+    sincos_shift<T>(parked<ST>(tr0, 2), parked<ST>(tr0, 3), d[1], &tr[2], &tr[3]);
+    if (WPSI) sincos_shift<T>(parked<ST>(tr0, 4), parked<ST>(tr0, 5), d[2], &tr[4], &tr[5]);
 }
 
 // utils/odesolver45.py:18-26 on the reduced state y = (Theta, nu_r); the 4th-order result is written back to y and the
@@ -372,8 +389,9 @@ __device__ __forceinline__ void stage_trig(const T tr0[6], const T d[3], T tr[6]
 // the stage derivatives are not kept until they are last used: as soon as k3 exists, the partial sums of the two
 // combinations that still need k1..k3 (the stage-5 input and the result) are formed and k1..k3 die; the sums are
 // continued with k4 / k5 in the same left-to-right order as written in the tableau, so nothing changes numerically.
-template <typename T, int VEH, bool SPM = false, bool CUR = true>
-__device__ __forceinline__ void rkf45_step(const KParams<T> &p, T y[9], const T tr0[6], const T tau[6], const T nu_c[3],
+//   ST: stride of y / tr0 / tau (1 = plain arrays; the dynamics launch can park them in shared memory, [word][thread])
+template <typename T, int VEH, bool SPM = false, bool CUR = true, int ST = 1>
+__device__ __forceinline__ void rkf45_step(const KParams<T> &p, T *y, const T *tr0, const T *tau, const T nu_c[3],
                                            T pacc[3], T tr1[6]) {
     const T h = p.h;
     T yt[9], dy[9], tr[6];
@@ -381,27 +399,32 @@ __device__ __forceinline__ void rkf45_step(const KParams<T> &p, T y[9], const T 
     pacc[0] = pacc[1] = pacc[2] = T(0);
     {
         T k1[9], k2[9], k3[9];
-        rhs9<T, VEH, true, SPM, CUR>(p, y, tr0, tau, nu_c, h * T(25.0 / 216.0), pacc, k1);
+        T y0[9], tr0r[6];
+#pragma unroll
+        for (int i = 0; i < 9; i++) y0[i] = parked<ST>(y, i);
+#pragma unroll
+        for (int i = 0; i < 6; i++) tr0r[i] = parked<ST>(tr0, i);
+        rhs9<T, VEH, true, SPM, CUR, ST>(p, y0, tr0r, tau, nu_c, h * T(25.0 / 216.0), pacc, k1);
         {
             const T a = h * T(0.25);
 #pragma unroll
             for (int i = 0; i < 9; i++) {
                 dy[i] = a * k1[i];
-                yt[i] = y[i] + dy[i];
+                yt[i] = parked<ST>(y, i) + dy[i];
             }
         }
-        stage_trig<T, false>(tr0, dy, tr);
-        rhs9<T, VEH, false, SPM, CUR>(p, yt, tr, tau, nu_c, T(0), pacc, k2);   // b2 = 0: no position contribution
+        stage_trig<T, false, ST>(tr0, dy, tr);
+        rhs9<T, VEH, false, SPM, CUR, ST>(p, yt, tr, tau, nu_c, T(0), pacc, k2);   // b2 = 0: no position contribution
         {
             const T a = h * T(3.0 / 32.0), b = h * T(9.0 / 32.0);
 #pragma unroll
             for (int i = 0; i < 9; i++) {
                 dy[i] = a * k1[i] + b * k2[i];
-                yt[i] = y[i] + dy[i];
+                yt[i] = parked<ST>(y, i) + dy[i];
             }
         }
-        stage_trig<T, true>(tr0, dy, tr);
-        rhs9<T, VEH, true, SPM, CUR>(p, yt, tr, tau, nu_c, h * T(1408.0 / 2565.0), pacc, k3);
+        stage_trig<T, true, ST>(tr0, dy, tr);
+        rhs9<T, VEH, true, SPM, CUR, ST>(p, yt, tr, tau, nu_c, h * T(1408.0 / 2565.0), pacc, k3);
         {
             const T a = h * T(1932.0 / 2197.0), b = h * T(-7200.0 / 2197.0), c = h * T(7296.0 / 2197.0);
             const T a5 = h * T(439.0 / 216.0), b5 = h * T(-8.0), c5 = h * T(3680.0 / 513.0);
@@ -409,7 +432,7 @@ __device__ __forceinline__ void rkf45_step(const KParams<T> &p, T y[9], const T 
 #pragma unroll
             for (int i = 0; i < 9; i++) {
                 dy[i] = a * k1[i] + b * k2[i] + c * k3[i];
-                yt[i] = y[i] + dy[i];
+                yt[i] = parked<ST>(y, i) + dy[i];
                 d5[i] = a5 * k1[i] + b5 * k2[i] + c5 * k3[i];
                 dw[i] = aw * k1[i] + cw * k3[i];
             }
@@ -420,42 +443,42 @@ __device__ __forceinline__ void rkf45_step(const KParams<T> &p, T y[9], const T 
     // earlier); the attitude components keep their increments, which sincos_shift needs
 #pragma unroll
     for (int i = 3; i < 9; i++) {
-        d5[i] = y[i] + d5[i];
-        dw[i] = y[i] + dw[i];
+        d5[i] = parked<ST>(y, i) + d5[i];
+        dw[i] = parked<ST>(y, i) + dw[i];
     }
 #endif
-    stage_trig<T, true>(tr0, dy, tr);
+    stage_trig<T, true, ST>(tr0, dy, tr);
     {
         T k4[9];
-        rhs9<T, VEH, true, SPM, CUR>(p, yt, tr, tau, nu_c, h * T(2197.0 / 4104.0), pacc, k4);
+        rhs9<T, VEH, true, SPM, CUR, ST>(p, yt, tr, tau, nu_c, h * T(2197.0 / 4104.0), pacc, k4);
         const T d = h * T(-845.0 / 4104.0), dwc = h * T(2197.0 / 4104.0);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             d5[i] = d5[i] + d * k4[i];
 #ifdef DOCKAUV_RK_FOLD
-            yt[i] = i < 3 ? y[i] + d5[i] : d5[i];
+            yt[i] = i < 3 ? parked<ST>(y, i) + d5[i] : d5[i];
 #else
-            yt[i] = y[i] + d5[i];
+            yt[i] = parked<ST>(y, i) + d5[i];
 #endif
             dw[i] = dw[i] + dwc * k4[i];
         }
     }
-    stage_trig<T, true>(tr0, d5, tr);
+    stage_trig<T, true, ST>(tr0, d5, tr);
     {
         T k5[9];
-        rhs9<T, VEH, true, SPM, CUR>(p, yt, tr, tau, nu_c, h * T(-1.0 / 5.0), pacc, k5);
+        rhs9<T, VEH, true, SPM, CUR, ST>(p, yt, tr, tau, nu_c, h * T(-1.0 / 5.0), pacc, k5);
         const T e = h * T(-1.0 / 5.0);
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             dw[i] = dw[i] + e * k5[i];
 #ifdef DOCKAUV_RK_FOLD
-            y[i] = i < 3 ? y[i] + dw[i] : dw[i];
+            y[i * ST] = i < 3 ? parked<ST>(y, i) + dw[i] : dw[i];
 #else
-            y[i] = y[i] + dw[i];
+            y[i * ST] = parked<ST>(y, i) + dw[i];
 #endif
         }
     }
-    stage_trig<T, true>(tr0, dw, tr1);
+    stage_trig<T, true, ST>(tr0, dw, tr1);
 }
 
 // ------------------------------------------------------------------------------------------- radar geometry
@@ -635,100 +658,81 @@ __device__ __forceinline__ bool obstacle_body_hit(const KParams<T> &p, const T p
     return dist <= rad + p.safety_radius;
 }
 
-// The culls and the body-collision pre-test of obstacle_pair in FLOAT, for the cull launch (FP64 runs at half rate and
-// the launch is bound by the bytes it reads).  Inputs are the float obstacle record (KParams::obsf, relative to the goal,
-// written by every reset) and the vehicle position relative to the goal (formed in T by the dynamics launch, rounded
-// once): every coordinate that matters is within max_dist_from_goal + max_dist of the origin, so the float rounding
-// error of a difference is a few 1e-6 m.  Everything after that carries explicit slack, so the result can only err on
-// the safe side:
-//   * in_view: every threshold is widened by far more than the float rounding error (lengths 2e-3 m, axis parameter
-//     1e-3, discriminant 1e-5 relative), so "culled" here implies "culled" in exact arithmetic;
-//   * hit: 0 = clear, 1 = collision, 2 = within 2e-3 m of the threshold -- the caller decides those in T.
-//   q0: capsule (bot - goal, radius) / sphere (centre - goal, radius);  q1: capsule (top - bot, 1 / |top - bot|)
-// The field-of-view test clips the reachable part of the axis against all five planes of the ray pyramid at once: an
-// axis point can carry a surface point inside the pyramid only if it is within r of the inner side of ALL five planes;
-// each signed distance is linear along the axis, so each plane keeps an interval of the segment parameter and the
-// obstacle is out of view when their intersection is empty (this also catches segments that leave the pyramid through
-// different planes).  Crossing parameters widened by 1e-3.
+// The culls and the body-collision pre-test of obstacle_pair in FLOAT, for the cull launch (FP64 runs at half rate, and
+// the launch is bound by the instructions it issues: this function is written for instruction count).  Inputs are the
+// float obstacle record (KParams::obsf, relative to the goal, written by every reset) and the vehicle position relative to
+// the goal (formed in T by the dynamics launch, rounded once): every coordinate that matters is within
+// max_dist_from_goal + max_dist of the origin, so the float rounding error of a position difference is a few 1e-6 m and
+// that of a squared length below ~5e-4 m^2.  Every decision carries explicit slack far beyond that, so the result can
+// only err on the safe side:
+//   * in_view = false implies "culled" in exact arithmetic: lengths are widened by eps = 2e-3 m (+1e-4 relative),
+//     discriminants by 1e-5 relative, clipped axis parameters by 1e-3 m;
+//   * hit: 0 = clear, 1 = collision, 2 = within eps of the threshold (or NaN) -- the caller decides those in T.
+//   q0: capsule (bot - goal, radius) / sphere (centre - goal, radius);  q1: capsule (unit axis d = (top - bot) / L, L)
+// Geometry (capsule): with s = (pos - bot) . d the foot point, perp^2 = |pos - bot|^2 - s^2, the distance to the segment
+// is hypot(max(-s, s - L, 0), perp); only axis points within Rr = max_dist + r of the vehicle can carry a surface point a
+// ray reaches: t in [s - sqrt(Rr^2 - perp^2), s + sqrt(..)] clipped to [0, L] (a 40 m pillar seen under roll / pitch
+// otherwise has its far ends on both sides of every plane).  Field of view: a surface point hit by a ray lies inside the
+// ray pyramid {x >= 0, |y| <= ty x, |z| <= tz x} (body frame), so some axis point of that range lies within r of the
+// inner side of ALL five planes; each signed distance g_k(t) = alpha_k t - beta_k is linear along the axis, each plane
+// keeps an interval {t : alpha_k t <= beta_k}, and the obstacle is out of view when the intersection is empty (this also
+// catches segments that leave the pyramid through different planes).
 template <typename T>
 __device__ __forceinline__ void cull_pair_rec(const KParams<T> &p, const float prel[3], const float Rm[9], float4 q0,
                                               float4 q1, bool is_cap, int &hit, bool &in_view) {
     const float eps = 2e-3f;
     const float cull = (float)p.radar_max_dist * 1.0001f + eps;
     const float rad = q0.w;
-    float dist;
-    float e0[3], e1[3];       // end points of the reachable part of the obstacle axis relative to the vehicle, NED
-    bool axis_out = false;
     const float oa[3] = {prel[0] - q0.x, prel[1] - q0.y, prel[2] - q0.z};
+    const float oaoa = oa[0] * oa[0] + oa[1] * oa[1] + oa[2] * oa[2];
+    const float Rr = cull + rad;
+    // body-frame coordinates R^T v of the vehicle-to-obstacle offset
+    float ob_[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) ob_[c] = Rm[c] * oa[0] + Rm[3 + c] * oa[1] + Rm[6 + c] * oa[2];
+    const float rm = rad * 1.0001f + eps;
+    const float ty = (float)p.fov_ty, tz = (float)p.fov_tz;
+    const float ry = rm * (float)p.fov_ny, rz = rm * (float)p.fov_nz;
+    const float vy = ty * ob_[0], vz = tz * ob_[0];
+    // beta_k: the five plane offsets at t = 0 (the point bot, or the sphere centre): inside plane k iff beta_k >= 0
+    const float b1 = rm - ob_[0], b2 = ry + ob_[1] - vy, b3 = ry - ob_[1] - vy, b4 = rz + ob_[2] - vz, b5 = rz - ob_[2] - vz;
+    float dist2;
+    bool outside;
     if (is_cap) {
-        const float ba[3] = {q1.x, q1.y, q1.z};
-        const float inv_n = q1.w;
-        const float baba = ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2];
-        const float baoa = oa[0] * ba[0] + oa[1] * ba[1] + oa[2] * ba[2];
-        const float oaoa = oa[0] * oa[0] + oa[1] * oa[1] + oa[2] * oa[2];
-        const float sp = -baoa * inv_n;                   // (bot - pos) . d
-        const float tp = (baoa - baba) * inv_n;           // (pos - top) . d
-        float hh = sp;
-        if (tp > hh || tp != tp) hh = tp;
-        if (0.0f > hh) hh = 0.0f;
-        float cr[3];
-        cross3(oa, ba, cr);
-        const float inv_baba = inv_n * inv_n;
-        const float perp2 = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) * inv_baba;
-        dist = sqrtf(hh * hh + perp2);
-        const float Rr = cull + rad;
-        const float t1 = baoa * baoa, t2 = baba * (oaoa - Rr * Rr);
-        const float D = t1 - t2, tolD = 1e-5f * (t1 + fabsf(t2));
-        axis_out = D < -tolD;
+        const float d[3] = {q1.x, q1.y, q1.z}, L = q1.w;
+        const float s = oa[0] * d[0] + oa[1] * d[1] + oa[2] * d[2];
+        float perp2 = oaoa - s * s;
+        perp2 = perp2 < 0.0f ? 0.0f : perp2;           // NaN stays NaN (fmaxf would drop it)
+        const float hh = fmaxf(fmaxf(-s, s - L), 0.0f);
+        dist2 = hh * hh + perp2;                       // a NaN pose gives NaN here: hit = 2, not culled
+        const float D = Rr * Rr - perp2, tolD = 1e-5f * (oaoa + s * s);
         const float sq = sqrtf(fmaxf(D, 0.0f) + tolD);
-        float s_lo = (baoa - sq) * inv_baba - 1e-3f, s_hi = (baoa + sq) * inv_baba + 1e-3f;
-        s_lo = s_lo > 0.0f ? s_lo : 0.0f;
-        s_hi = s_hi < 1.0f ? s_hi : 1.0f;
-        axis_out |= s_lo > s_hi;
+        float t_lo = fmaxf(s - sq - 1e-3f, 0.0f), t_hi = fminf(s + sq + 1e-3f, L);
+        bool empty = D < -tolD;
+        float db[3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            e0[c] = s_lo * ba[c] - oa[c];
-            e1[c] = s_hi * ba[c] - oa[c];
-        }
+        for (int c = 0; c < 3; c++) db[c] = Rm[c] * d[0] + Rm[3 + c] * d[1] + Rm[6 + c] * d[2];
+        const float uy = ty * db[0], uz = tz * db[0];
+        auto clip = [&](float alpha, float beta) {        // keep { t : alpha t <= beta }
+            const float q = __fdividef(beta, alpha);
+            t_hi = fminf(t_hi, alpha > 0.0f ? q + 1e-3f : 3.0e38f);
+            t_lo = fmaxf(t_lo, alpha < 0.0f ? q - 1e-3f : -3.0e38f);
+            empty |= (alpha == 0.0f) && (beta < 0.0f);
+        };
+        clip(-db[0], b1);
+        clip(db[1] - uy, b2);
+        clip(-db[1] - uy, b3);
+        clip(db[2] - uz, b4);
+        clip(-db[2] - uz, b5);
+        outside = empty || (t_lo > t_hi);
     } else {
-        dist = sqrtf(oa[0] * oa[0] + oa[1] * oa[1] + oa[2] * oa[2]);
-#pragma unroll
-        for (int c = 0; c < 3; c++) e0[c] = e1[c] = -oa[c];
+        dist2 = oaoa;
+        outside = (b1 < 0.0f) || (b2 < 0.0f) || (b3 < 0.0f) || (b4 < 0.0f) || (b5 < 0.0f);
     }
     const float thr = rad + (float)p.safety_radius;
-    hit = (dist <= thr - eps) ? 1 : ((dist > thr + eps) ? 0 : 2);        // NaN -> 2
-    bool outside = (dist - rad > cull) || axis_out;
-    {
-        float a0[3], a1[3];    // body-frame coordinates R^T e
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            a0[c] = Rm[c] * e0[0] + Rm[3 + c] * e0[1] + Rm[6 + c] * e0[2];
-            a1[c] = Rm[c] * e1[0] + Rm[3 + c] * e1[1] + Rm[6 + c] * e1[2];
-        }
-        // the float error of a signed distance (~1e-6 * 60 m) and of the converted plane slopes (~6e-8 * 40 m) is far
-        // inside the eps added to the radius
-        const float rm = rad * 1.0001f + eps;
-        const float ty = (float)p.fov_ty, tz = (float)p.fov_tz;
-        const float ry = rm * (float)p.fov_ny, rz = rm * (float)p.fov_nz;
-        float t_lo = 0.0f, t_hi = 1.0f;
-        bool empty = false;
-        auto clip = [&](float g0, float g1) {            // keep { t : g0 + t (g1 - g0) <= 0 }
-            const bool o0 = g0 > 0.0f, o1 = g1 > 0.0f;
-            empty |= o0 && o1;
-            if (o0 != o1) {
-                float ts = __fdividef(g0, g0 - g1);
-                ts = fminf(fmaxf(ts, 0.0f), 1.0f);       // NaN -> 0
-                if (o0) t_lo = fmaxf(t_lo, ts - 1e-3f);
-                else t_hi = fminf(t_hi, ts + 1e-3f);
-            }
-        };
-        clip(-a0[0] - rm, -a1[0] - rm);
-        clip(a0[1] - ty * a0[0] - ry, a1[1] - ty * a1[0] - ry);
-        clip(-a0[1] - ty * a0[0] - ry, -a1[1] - ty * a1[0] - ry);
-        clip(a0[2] - tz * a0[0] - rz, a1[2] - tz * a1[0] - rz);
-        clip(-a0[2] - tz * a0[0] - rz, -a1[2] - tz * a1[0] - rz);
-        outside |= empty || (t_lo > t_hi);
-    }
+    const float lo = thr - eps, hi = thr + eps;
+    hit = (dist2 <= lo * lo) ? 1 : ((dist2 > hi * hi) ? 0 : 2);        // NaN -> 2
+    outside |= dist2 > Rr * Rr;                                         // range: nearest surface point beyond max_dist
     in_view = !outside;
 }
 
@@ -739,7 +743,8 @@ __device__ __forceinline__ void obstacle_record_f32(const double ob[7], const do
     q0 = make_float4((float)(ob[0] - goal[0]), (float)(ob[1] - goal[1]), (float)(ob[2] - goal[2]), (float)(is_cap ? ob[6] : ob[3]));
     if (is_cap) {
         const double b[3] = {ob[3] - ob[0], ob[4] - ob[1], ob[5] - ob[2]};
-        q1 = make_float4((float)b[0], (float)b[1], (float)b[2], (float)rsqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]));
+        const double L = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+        q1 = make_float4((float)(b[0] / L), (float)(b[1] / L), (float)(b[2] / L), (float)L);
     } else {
         q1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }

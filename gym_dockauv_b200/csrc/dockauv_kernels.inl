@@ -39,9 +39,7 @@ template <>
 cudaError_t launch_reset<DOCKAUV_REAL>(const KParams<DOCKAUV_REAL> &k, const uint8_t *mask_dev, cudaStream_t st) {
     const int64_t n = k.env_end - k.env_begin;
     if (n <= 0) return cudaSuccess;
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    reset_kernel<DOCKAUV_REAL><<<blocks, threads, 0, st>>>(k, mask_dev);
+    reset_kernel<DOCKAUV_REAL><<<(unsigned)((n + 31) / 32), kResetCta, 0, st>>>(k, mask_dev);
     return cudaGetLastError();
 }
 

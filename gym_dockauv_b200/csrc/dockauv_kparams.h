@@ -64,16 +64,17 @@ struct KParams {
     //            need no radar, already combined in numpy's summation order), 12 log_precision(delta_d), 13 delta_d,
     //            14 done-condition bits 0..2 as a number, 15 NaN poison word (0 for a finite pose)
     //   obsf     float4[n_obsf][n_envs]: float copy of the obstacles RELATIVE TO THE GOAL for the cull (written by every
-    //            reset and by dockauv_refresh_obstacles): capsule k -> slots 2k (bot - goal, radius), 2k+1 (top - bot,
-    //            1/|top - bot|); sphere s -> slot 2 n_caps + s (centre - goal, radius)
-    //   view_list / view_count: work lists of the ray launch, two counters per concurrently stepped range: envs with
-    //            something in view from the front (local env index | in-view mask << 32 | condition bits << 48), envs
-    //            whose episode ended in the cull launch from the back
+    //            reset and by dockauv_refresh_obstacles): capsule k -> slots 2k (bot - goal, radius), 2k+1 (unit axis
+    //            (top - bot) / L, L); sphere s -> slot 2 n_caps + s (centre - goal, radius)
+    //   view_list / ended_list / view_count: work lists, two counters per concurrently stepped range: envs with
+    //            something in view (local env index | in-view mask << 32 | condition bits << 48) for the ray launch, envs
+    //            whose episode ended (local env index) for the episode-end launch
     int64_t chunk_envs;             // > 0: the launches of a step are issued per chunk of this many envs
     T *rec;
     float4 *obsf;
     int32_t n_obsf, cull_exact;      // cull_exact: coordinates too large for the float cull -> decide everything in T
     unsigned long long *view_list;
+    uint32_t *ended_list;
     unsigned int *view_count;
     int32_t sm_count;
     int32_t sparse_minv;             // M_inv has only the z_G pattern (diagonal + [0,4] [4,0] [1,3] [3,1]) filled in

@@ -29,13 +29,19 @@ struct Pair<float> {
     using type = float2;
 };
 
-// What a lane keeps in registers for the whole kernel: its rays (ray = lane + 32 j) and its pooled cell.
+// What a lane needs for the whole kernel: its rays (ray = lane + 32 j) and its pooled cell.  Two homes: registers
+// (RayLane, fused warp kernel) or the warp's shared memory (RayLaneShared, ray launch of the pipeline: 24 registers less
+// per thread decide whether five or six CTAs fit an SM there).
 template <typename T, int RPL>
 struct RayLane {
-    T rb[RPL][3], bw[RPL];   // body-frame direction (sensor.py:63-71), obstacle-avoidance weight (docking3d.py:789-790)
-    int pidx[4];             // 2x2 pooling fast path: the four source slots of this lane's cell
-    bool fast_pool;          // 2x2 blocks and at most one pooled cell per lane
+    T rb_[RPL][3], bw_[RPL];   // body-frame direction (sensor.py:63-71), obstacle-avoidance weight (docking3d.py:789-790)
+    int pidx_[4];              // 2x2 pooling fast path: the four source slots of this lane's cell
+    bool fast_pool;            // 2x2 blocks and at most one pooled cell per lane
     T dmax, inv_dmax;
+
+    __device__ __forceinline__ T rb(int j, int c) const { return rb_[j][c]; }
+    __device__ __forceinline__ T bw(int j) const { return bw_[j]; }
+    __device__ __forceinline__ int pidx(int q) const { return pidx_[q]; }
 
     // s_ray: the warp's ray-distance scratch (n_rays + 2 words; slot n_rays holds the zero that block_reduce pads with)
     __device__ __forceinline__ void init(const KParams<T> &p, int lane, T *s_ray) {
@@ -45,18 +51,18 @@ struct RayLane {
             const int ir = lane + 32 * j;
             const bool ok = ir < n_r;
 #pragma unroll
-            for (int c = 0; c < 3; c++) rb[j][c] = ok ? p.ray_tab[c * n_r + ir] : T(0);
-            bw[j] = ok ? p.ray_tab[3 * n_r + ir] : T(0);
+            for (int c = 0; c < 3; c++) rb_[j][c] = ok ? p.ray_tab[c * n_r + ir] : T(0);
+            bw_[j] = ok ? p.ray_tab[3 * n_r + ir] : T(0);
         }
         fast_pool = (p.block == 2) && (p.n_rr <= 32);
 #pragma unroll
-        for (int q = 0; q < 4; q++) pidx[q] = n_r;
+        for (int q = 0; q < 4; q++) pidx_[q] = n_r;
         if (fast_pool && lane < p.n_rr) {
             const int pr = lane / p.n_hr, pcol = lane - pr * p.n_hr;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int rv = 2 * pr + (q >> 1), rh = 2 * pcol + (q & 1);
-                if (rv < p.n_vert && rh < p.n_horiz) pidx[q] = rv * p.n_horiz + rh;
+                if (rv < p.n_vert && rh < p.n_horiz) pidx_[q] = rv * p.n_horiz + rh;
             }
         }
         if (lane == 0) s_ray[n_r] = T(0);
@@ -65,13 +71,49 @@ struct RayLane {
     }
 };
 
+// the same constants in shared memory: words [4 RPL][32] of T (rb, bw) followed by int [4][32] (pidx), this lane's column;
+// read through volatile so that the compiler does not pull them back into registers for the whole loop
+template <typename T, int RPL>
+struct RayLaneShared {
+    const T *w;        // + lane
+    const int *pi;     // + lane
+    bool fast_pool;
+    T dmax, inv_dmax;
+
+    static __host__ __device__ constexpr int words() { return 4 * RPL * 32 + 4 * 32 * (int)sizeof(int) / (int)sizeof(T); }
+    __device__ __forceinline__ T rb(int j, int c) const { return reinterpret_cast<const volatile T *>(w)[(4 * j + c) * 32]; }
+    __device__ __forceinline__ T bw(int j) const { return reinterpret_cast<const volatile T *>(w)[(4 * j + 3) * 32]; }
+    __device__ __forceinline__ int pidx(int q) const { return reinterpret_cast<const volatile int *>(pi)[q * 32]; }
+
+    __device__ __forceinline__ void init(const KParams<T> &p, int lane, T *s_ray, T *s_lane) {
+        RayLane<T, RPL> r;
+        r.init(p, lane, s_ray);
+        T *wl = s_lane + lane;
+        int *pl = reinterpret_cast<int *>(s_lane + 4 * RPL * 32) + lane;
+#pragma unroll
+        for (int j = 0; j < RPL; j++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) wl[(4 * j + c) * 32] = r.rb_[j][c];
+            wl[(4 * j + 3) * 32] = r.bw_[j];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) pl[q * 32] = r.pidx_[q];
+        w = wl;
+        pi = pl;
+        fast_pool = r.fast_pool;
+        dmax = r.dmax;
+        inv_dmax = r.inv_dmax;
+        __syncwarp();
+    }
+};
+
 // Casts this lane's rays against the obstacles of `mask` (bit k = obstacle k, capsules first; records in shared memory
 // at pre_env + k * kPreStride), clamps (sensor.py:117), writes the 2x2 zero-padded max-pool of the distances straight into
 // the env's observation row (obs[16:], docking3d.py:487) and returns sum(max((d/d_max)^2, eps_c) * beta) on every lane.
 //   R: post-step Rzyx (row-major); poison: 0, or NaN for a non-finite pose (added to every distance so that a blown-up
 //   state poisons the radar outputs like the reference's NaN propagation does).  Must be called by all 32 lanes.
-template <typename T, int RPL, bool DBG>
-__device__ __forceinline__ T radar_env(const KParams<T> &p, const RayLane<T, RPL> &rl, const T R[9], T poison, unsigned mask,
+template <typename T, int RPL, bool DBG, typename LANE>
+__device__ __forceinline__ T radar_env(const KParams<T> &p, const LANE &rl, const T R[9], T poison, unsigned mask,
                                        const T *pre_env, T *s_ray, int lane, int64_t ie) {
     using P2 = typename Pair<T>::type;
     const int n_caps = p.n_caps, n_sph = p.n_sph, n_r = p.n_rays;
@@ -83,8 +125,9 @@ __device__ __forceinline__ T radar_env(const KParams<T> &p, const RayLane<T, RPL
         T rd[RPL][3];
 #pragma unroll
         for (int j = 0; j < RPL; j++) {
+            const T b0 = rl.rb(j, 0), b1 = rl.rb(j, 1), b2 = rl.rb(j, 2);
 #pragma unroll
-            for (int c = 0; c < 3; c++) rd[j][c] = R[3 * c] * rl.rb[j][0] + R[3 * c + 1] * rl.rb[j][1] + R[3 * c + 2] * rl.rb[j][2];
+            for (int c = 0; c < 3; c++) rd[j][c] = R[3 * c] * b0 + R[3 * c + 1] * b1 + R[3 * c + 2] * b2;
         }
         unsigned cap_mask = mask & ((1u << n_caps) - 1u);
         unsigned sph_mask = (mask >> n_caps) & ((1u << n_sph) - 1u);
@@ -148,7 +191,7 @@ __device__ __forceinline__ T radar_env(const KParams<T> &p, const RayLane<T, RPL
             const T x = d * inv_dmax;
             const T qq = x * x;
             const T mx = !(qq <= T(0.001)) ? qq : T(0.001);     // np.maximum, NaN propagates
-            oa_part += mx * rl.bw[j];
+            oa_part += mx * rl.bw(j);
         }
     }
     const T oa_dot = warp_sum<T>(oa_part);
@@ -157,10 +200,10 @@ __device__ __forceinline__ T radar_env(const KParams<T> &p, const RayLane<T, RPL
     float *orow = p.obs + ie * p.n_obs + 16;
     if (rl.fast_pool) {
         if (lane < p.n_rr) {
-            T mx = s_ray[rl.pidx[0]];
+            T mx = s_ray[rl.pidx(0)];
 #pragma unroll
             for (int q = 1; q < 4; q++) {
-                const T v = s_ray[rl.pidx[q]];
+                const T v = s_ray[rl.pidx(q)];
                 mx = !(v <= mx) ? v : mx;            // np.max, NaN propagates
             }
             T o = mx * inv_dmax;                     // clip(d / max_dist, 0, 1), docking3d.py:487

@@ -1,4 +1,4 @@
-// dockauv_step_pipe.cuh -- layout DOCKAUV_LAYOUT_PIPELINE (default): one batched step as three specialised launches.
+// dockauv_step_pipe.cuh -- layout DOCKAUV_LAYOUT_PIPELINE (default): one batched step as specialised launches.
 //
 //   1. dynamics     dynamics_kernel: thread per env.  Current, command filter, RKF45, angle wrap, navigation errors,
 //                   obs[0:16], done conditions 0..2, the reward terms that need no radar.  Leaves one 16-word record
@@ -13,8 +13,9 @@
 //                   its episode ended.  No shared memory, no barrier.
 //   3. rays+finish  rays_finish_kernel: persistent grid, one warp per LISTED env (lanes = rays), data of the next list
 //                   entry in flight while the current one is cast (radar_env, dockauv_rays.cuh); the warp then writes the
-//                   reward with its obstacle-avoidance term and the running return.  Afterwards the warps of the grid
-//                   share the ended episodes of both lists: terminal-observation row, re-initialisation (one warp each).
+//                   reward with its obstacle-avoidance term and the running return (skipped for obstacle-free scenarios).
+//   4. episode end  episode_end_kernel: thread per ENDED env (~1 % of the batch, compacted by launches 2 and 3):
+//                   terminal-observation row, zero row, re-initialisation.  Tiny; overlaps the other half's launches.
 //
 // Each launch has its own register budget and occupancy, the ray warps never idle on envs with nothing in view, and no
 // env is touched by a launch that has nothing to do for it (round 1 had a fourth launch that re-read every env's
@@ -35,11 +36,14 @@ constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #ifndef DOCKAUV_MINB_CULL
 #define DOCKAUV_MINB_CULL 4
 #endif
-#ifndef DOCKAUV_RAY_CTAS_PER_SM
-#define DOCKAUV_RAY_CTAS_PER_SM 4   // persistent grid of the ray launch, in 4-warp CTAs per SM (= what is resident; 8: +0.7 %, 16: +2 % time)
+#ifndef DOCKAUV_CULL_PREFETCH
+#define DOCKAUV_CULL_PREFETCH 1
 #endif
 #ifndef DOCKAUV_MINB_RAYS
-#define DOCKAUV_MINB_RAYS 4
+#define DOCKAUV_MINB_RAYS 6         // ray launch: (128, 6) = 80 registers, 24 warps per SM
+#endif
+#ifndef DOCKAUV_RAY_CTAS_PER_SM
+#define DOCKAUV_RAY_CTAS_PER_SM DOCKAUV_MINB_RAYS   // persistent grid of the ray launch, in 4-warp CTAs per SM (= what is resident)
 #endif
 
 constexpr int kListCounters = 2;    // work-list counters per stepped env range (see cull_finish_kernel)
@@ -93,9 +97,34 @@ struct RecIO<float> {
     }
 };
 
+// ------------------------------------------------------------------------------------------------------- finish helpers
+// is_done (docking3d.py:597-631): the five condition bits once the collision flag is known; t_steps is the counter before
+// its increment (:612 is evaluated pre-increment, so max_timesteps = 1000 ends an episode at step 1001)
+template <typename T>
+__device__ __forceinline__ uint32_t done_conditions(const KParams<T> &p, uint32_t cond012, int32_t t_steps, bool collision) {
+    return cond012 | ((t_steps >= p.max_timesteps) ? 8u : 0u) | (collision ? 16u : 0u);
+}
+
+// reward_step (docking3d.py:560-595) from the record words of the dynamics launch and the radar term r_oa
+// (Reward.obstacle_avoidance, :767-792).  np.sum's order for 13 terms: ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) + r8 .. r12.
+template <typename T>
+__device__ __forceinline__ T step_reward(const KParams<T> &p, T A, T B, T r7, T lp_d, T r_oa, uint32_t cond) {
+    T r6;
+    if (p.reward_set == 1) r6 = -p.w_oa * r_oa;
+    else r6 = -p.w_oa * cont_goal_constraints<T>(Mth<T>::abs_(r_oa), T(1), lp_d);
+    T reward = A + (B + (r6 + r7));
+    if (cond != 0u) {      // ~1 % of the env-steps; the other terms are exact zeros
+#pragma unroll
+        for (int k = 0; k < 5; k++) reward += ((cond >> k) & 1u) ? p.w_done[k] : T(0);
+    }
+    return reward;
+}
+
 // ------------------------------------------------------------------------------------------------------- 1. dynamics
-// CUR: the ocean current is evaluated (scenario with a current, injected current or noise); SPM: sparse M_inv.
-template <typename T, int VEH, int NU, bool CUR, bool SPM>
+// CUR: the ocean current is evaluated (scenario with a current, injected current or noise); SPM: sparse M_inv;
+// FIN: the scenario has no obstacles -- every ray reads max_dist and nothing can collide, so the env is finished right
+// here (reward, done, counters, statistics, all-ones ray cells; no record, no cull / ray launch).
+template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN>
 __global__ void
 #ifdef DOCKAUV_DYN_MAXNREG
 __maxnreg__(DOCKAUV_DYN_MAXNREG)
@@ -128,7 +157,25 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
         dyn_tau<T, VEH, NU>(p, u, tau);
     }
     T pacc[3], tr1[6];
+#ifdef DOCKAUV_DYN_SMEM
+    // tuning variant: the values that live through the whole integration but are read once per stage (pre-step state,
+    // its sines / cosines, the generalised force) parked in shared memory, [word][thread]
+    {
+        __shared__ T s_park[21 * kDynThreads];
+        T *sp = s_park + threadIdx.x;
+#pragma unroll
+        for (int c = 0; c < 9; c++) sp[c * kDynThreads] = y[c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) sp[(9 + c) * kDynThreads] = tr0[c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) sp[(15 + c) * kDynThreads] = tau[c];
+        rkf45_step<T, VEH, SPM, CUR, kDynThreads>(p, sp, sp + 9 * kDynThreads, sp + 15 * kDynThreads, nu_c, pacc, tr1);
+#pragma unroll
+        for (int c = 0; c < 9; c++) y[c] = sp[c * kDynThreads];
+    }
+#else
     rkf45_step<T, VEH, SPM, CUR>(p, y, tr0, tau, nu_c, pacc, tr1);
+#endif
 #pragma unroll
     for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
     // position and goal are only needed from here on (their lines were prefetched into L2 by an earlier CTA): loading
@@ -158,15 +205,66 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
 #pragma unroll
         for (int c = 0; c < 16; c++) orow[c] = (float)q.o[c];
     }
+    // np.sum of the 13 reward terms is ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) + r8 + .. + r12 (reward_sum13): the two
+    // sums that need no radar are formed here, in that order
+    const T A = (q.r[0] + q.r[1]) + (q.r[2] + q.r[3]), B = q.r[4] + q.r[5];
+    if (FIN) {
+        // ---- every ray reads max_dist (docking3d.py:441, sensor.py:113-117) -> pooled cells all ones, r_oa = 0
+        float *cells = p.obs + i * p.n_obs + 16;
+        if ((p.n_obs & 3) == 0 && (p.n_rr & 3) == 0) {
+            float4 *c4 = reinterpret_cast<float4 *>(cells);
+            for (int c = 0; c < (p.n_rr >> 2); c++) c4[c] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+        } else {
+            for (int c = 0; c < p.n_rr; c++) cells[c] = 1.0f;
+        }
+        const int32_t t_steps = p.t_steps[i];
+        const uint32_t cond = done_conditions<T>(p, q.cond, t_steps, false);
+        const bool done = cond != 0;
+        const int32_t t_new = t_steps + 1;
+        const T r_oa = p.sum_beta_oa / p.sum_beta_oa - T(1);
+        const T reward = step_reward<T>(p, A, B, q.r[7], q.r[6], r_oa, cond);
+        const T ep_ret = p.ep_return[i] + reward;
+        p.reward[i] = reward;
+        p.done[i] = done ? 1 : 0;
+        if (p.cond_bits) p.cond_bits[i] = (uint8_t)cond;
+        if (p.delta_d_out) p.delta_d_out[i] = q.delta_d;
+        WarpStats bs;
+        if (done) {
+            if (p.ep_len_out) p.ep_len_out[i] = t_new;
+            if (p.ep_return_out) p.ep_return_out[i] = ep_ret;
+            bs.done = true;
+            bs.cond = cond;
+            bs.length = t_new;
+            bs.ep_return = (double)ep_ret;
+            bs.delta_d = (double)q.delta_d;
+            bs.nan = reward != reward;
+        }
+        if (!(done && p.auto_reset)) {
+            p.ep_return[i] = ep_ret;
+            p.t_steps[i] = t_new;
+        }
+        {   // ended episodes -> the list of the episode-end launch (aggregated over the lanes that are still here)
+            const unsigned am = __activemask();
+            const unsigned em = __ballot_sync(am, done);
+            if (em) {
+                const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(&p.view_count[1], (unsigned)__popc(em));
+                base = __shfl_sync(am, base, leader);
+                if (done) p.ended_list[base + __popc(em & ((1u << lane) - 1u))] = (uint32_t)(i - p.env_begin);
+            }
+        }
+        const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kDynThreads;
+        bs.flush_direct(p.stats, threadIdx.x == 0 ? (int)min((int64_t)kDynThreads, p.env_end - i0) : 0);
+        return;
+    }
     T w[kRecWords];
 #pragma unroll
     for (int c = 0; c < 6; c++) w[REC_TRIG + c] = tr1[c];
 #pragma unroll
     for (int c = 0; c < 3; c++) w[REC_PREL + c] = pos[c] - goal[c];
-    // np.sum of the 13 reward terms is ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) + r8 + .. + r12 (reward_sum13): the two
-    // sums that need no radar are formed here, in that order
-    w[REC_A] = (q.r[0] + q.r[1]) + (q.r[2] + q.r[3]);
-    w[REC_B] = q.r[4] + q.r[5];
+    w[REC_A] = A;
+    w[REC_B] = B;
     w[REC_R7] = q.r[7];
     w[REC_LPD] = q.r[6];
     w[REC_DD] = q.delta_d;
@@ -177,44 +275,6 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
     RecIO<T>::store(p.rec + i * kRecWords, w);
 }
 
-// ------------------------------------------------------------------------------------------------------- finish
-// is_done (docking3d.py:597-631): the five condition bits once the collision flag is known; t_steps is the counter before
-// its increment (:612 is evaluated pre-increment, so max_timesteps = 1000 ends an episode at step 1001)
-template <typename T>
-__device__ __forceinline__ uint32_t done_conditions(const KParams<T> &p, uint32_t cond012, int32_t t_steps, bool collision) {
-    return cond012 | ((t_steps >= p.max_timesteps) ? 8u : 0u) | (collision ? 16u : 0u);
-}
-
-// reward_step (docking3d.py:560-595) from the record words of the dynamics launch and the radar term r_oa
-// (Reward.obstacle_avoidance, :767-792).  np.sum's order for 13 terms: ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) + r8 .. r12.
-template <typename T>
-__device__ __forceinline__ T step_reward(const KParams<T> &p, T A, T B, T r7, T lp_d, T r_oa, uint32_t cond) {
-    T r6;
-    if (p.reward_set == 1) r6 = -p.w_oa * r_oa;
-    else r6 = -p.w_oa * cont_goal_constraints<T>(Mth<T>::abs_(r_oa), T(1), lp_d);
-    T reward = A + (B + (r6 + r7));
-#pragma unroll
-    for (int k = 0; k < 5; k++) reward += ((cond >> k) & 1u) ? p.w_done[k] : T(0);
-    return reward;
-}
-
-// One warp ends the episode of env ie: the last observation is kept as terminal_observation, the all-zero reset
-// observation is handed back (docking3d.py:269,322) and the env is re-initialised.  Called by all 32 lanes.
-template <typename T>
-__device__ __forceinline__ void end_episode_warp(const KParams<T> &p, int64_t ie, int lane) {
-    const int n_obs = p.n_obs;
-    float *row = p.obs + ie * n_obs;
-    float *trow = p.terminal_obs ? p.terminal_obs + ie * n_obs : nullptr;
-    for (int c = lane; c < n_obs; c += 32) {
-        if (trow) trow[c] = row[c];
-        if (p.auto_reset) row[c] = 0.0f;
-    }
-    if (p.auto_reset) reset_env_warp<T>(p, ie, lane);
-}
-
-// The two work lists of a stepped env range share one array of n entries (KParams::view_list): entries of envs with
-// something in view grow from the front (counter 0), envs whose episode ended in the cull launch from the back (counter 1).
-//   entry: bits 0..31 env index within the range, 32..47 in-view mask (capsules first), 48..52 done-condition bits
 // ------------------------------------------------------------------------------------------------------- 2. cull + finish
 constexpr int kCullThreads = 256;
 
@@ -226,12 +286,18 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
     const bool active = i < p.env_end;
     const int lane = threadIdx.x & 31;
     WarpStats bs;
-    bool listed = false, ended = false;      // ended: episode over and nothing in view -> re-initialised by the ray launch's warps
+    bool listed = false, ended = false;      // ended: episode over and nothing in view -> on the list of the episode-end launch
     uint32_t info = 0;                       // bits 0..15 in-view mask (capsules first), 16 collision
     uint32_t cond = 0;
     if (active) {
         const T *rec = p.rec + i * kRecWords;
         const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
+        // the obstacle records are walked one after the other (one register pair of float4 in flight): pulling all of
+        // them into L2 now turns the loop's round trips into L2 hits (it was 64 % of this launch's stall samples)
+#if DOCKAUV_CULL_PREFETCH
+        if (!p.cull_exact)
+            for (int sl = 0; sl < p.n_obsf; sl++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obsf + (int64_t)sl * N + i));
+#endif
         // everything this thread reads besides the obstacle records, requested up front
         T w[10], wc[2], wf[4];
         RecIO<T>::template load<0, 5>(rec, w);       // trig, prel, A
@@ -340,10 +406,9 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
             }
         }
     }
-    // ---- warp-aggregated appends: envs with something in view from the front, ended episodes from the back
+    // ---- warp-aggregated appends to the two work lists
     {
         const unsigned lm = __ballot_sync(0xffffffffu, listed), em = __ballot_sync(0xffffffffu, ended);
-        const int64_t n_range = p.env_end - p.env_begin;
         if (lm) {
             unsigned base = 0;
             if (lane == 0) base = atomicAdd(&p.view_count[0], (unsigned)__popc(lm));
@@ -360,22 +425,33 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
             base = __shfl_sync(0xffffffffu, base, 0);
             if (ended) {
                 const unsigned k = base + __popc(em & ((1u << lane) - 1u));
-                p.view_list[n_range - 1 - k] = (unsigned long long)(uint32_t)(i - p.env_begin);
+                p.ended_list[k] = (uint32_t)(i - p.env_begin);
             }
         }
     }
-    bs.flush(p.stats, threadIdx.x == 0 ? (int)min((int64_t)kCullThreads, p.env_end - i0) : 0);
+    bs.flush_direct(p.stats, threadIdx.x == 0 ? (int)min((int64_t)kCullThreads, p.env_end - i0) : 0);
 }
 
 // ------------------------------------------------------------------------------------------------------- 3. rays + finish
-constexpr int kRayPoseWords = 24;    // shared words per warp for the staged entry: record[16] pos[3] ep_return pad
-template <typename T>
+// Shared memory of one warp of the ray launch (T words):
+//   stage[2][kStageWords]   the data of two list entries (double buffer, filled by cp.async one entry ahead):
+//                           0..15 the env's record, 16..18 post-step position, 19 running return, 20 step counter (int),
+//                           24 + 8 k .. obstacle k as stored (7 or 4 words), k < 16
+//   pre[16][kPreStride]     ray-test records of the in-view obstacles
+//   ray[ray_stride]         clamped ray distances (pooling scratch)
+//   lane[RayLaneShared]     per-lane ray constants
+// Nothing of the software pipeline lives in registers (round 1 kept the next entry's 24 words there), and neither do the
+// per-lane ray constants: 118 -> 80 registers, six CTAs of four warps per SM instead of four.
+constexpr int kStageObst = 24, kStageWords = kStageObst + 16 * 8;
+template <typename T, int RPL>
 struct RaysSmem {
-    int warp_words;      // T words per warp: entry[24] + rec[16][kPreStride] + rays[ray_stride]
-    int ray_stride;
+    int warp_words, ray_stride, pre_off, ray_off, lane_off;
     __host__ __device__ RaysSmem(int n_rays) {
         ray_stride = (n_rays + 2) & ~1;
-        warp_words = kRayPoseWords + 16 * kPreStride + ray_stride;
+        pre_off = 2 * kStageWords;
+        ray_off = pre_off + 16 * kPreStride;
+        lane_off = ray_off + ray_stride;
+        warp_words = (lane_off + RayLaneShared<T, RPL>::words() + 1) & ~1;
     }
 };
 
@@ -384,124 +460,171 @@ struct RaysSmem {
 #endif
 constexpr int kRayWarps = DOCKAUV_RAY_WARPS;     // warps per CTA of the ray launch
 
+// one word global -> shared without a register in between (completion: cp_async_wait_all); dst = shared-window address
+template <typename T>
+__device__ __forceinline__ void cp_async_word(unsigned dst_shared, const T *src) {
+    if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_shared), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <typename T, int RPL>
 __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWarps) rays_finish_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const RaysSmem<T> L(p.n_rays);
+    const RaysSmem<T, RPL> L(p.n_rays);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    T *s_ent = reinterpret_cast<T *>(smem_raw) + warp * L.warp_words;
-    T *s_pre = s_ent + kRayPoseWords;
-    T *s_ray = s_pre + 16 * kPreStride;
+    T *s_warp = reinterpret_cast<T *>(smem_raw) + warp * L.warp_words;
+    T *s_pre = s_warp + L.pre_off;
+    T *s_ray = s_warp + L.ray_off;
     const int64_t N = p.n_envs;
-    const unsigned count = p.view_count[0], n_ended = p.view_count[1];
+    const unsigned count = p.view_count[0];
     const unsigned n_warps = gridDim.x * kRayWarps;
-    const unsigned w_global = blockIdx.x * kRayWarps + warp;
-    double stat_acc = 0.0;       // lane k < DOCKAUV_STAT_ENV_STEPS accumulates statistic k of the episodes this warp ended
+    unsigned idx = blockIdx.x * kRayWarps + warp;
+    if (idx >= count) return;
 
-    if (w_global < count) {
-        unsigned idx = w_global;
-        const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
-        RayLane<T, RPL> rl;
-        rl.init(p, lane, s_ray);
+    const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
+    RayLaneShared<T, RPL> rl;
+    rl.init(p, lane, s_ray, s_warp + L.lane_off);
 
-        // software pipeline over the list: entry n + 2 and the data of entry n + 1 are in flight while entry n is cast.
-        // data of one entry: lane c < 14 holds record word c (one request), lanes 16..18 the post-step position, lane 19
-        // the running return, lane 20 the step counter; lane k < n_obst with bit k of the mask holds obstacle k.
-        const bool lane_is_cap = lane < n_caps;
-        const T *obst_row = lane_is_cap ? p.capsules + (int64_t)(lane * 7) * N : p.spheres + (int64_t)((lane - n_caps) * 4) * N;
-        auto fetch = [&](uint64_t entry, T &word, int32_t &tst, T ob[7]) {
-            const int64_t e = p.env_begin + (int64_t)(uint32_t)entry;
-            const unsigned mask = (unsigned)(entry >> 32) & 0xffffu;
-            if (lane < kRecWords) word = p.rec[e * kRecWords + lane];
-            else if (lane < 19) word = p.state[(int64_t)(lane - 16) * N + e];
-            else if (lane == 19) word = p.ep_return[e];
-            else if (lane == 20) tst = p.t_steps[e];
-            if (lane < n_obst && ((mask >> lane) & 1u)) {
-                const T *g = obst_row + e;
-                const int n_words = lane_is_cap ? 7 : 4;
-#pragma unroll
-                for (int c = 0; c < 7; c++)
-                    if (c < n_words) ob[c] = g[(int64_t)c * N];
-            }
-        };
-        uint64_t cur = p.view_list[idx];
-        uint64_t nxt = (idx + n_warps < count) ? p.view_list[idx + n_warps] : 0;
-        T word = T(0), ob[7];
-        int32_t tst = 0;
-#pragma unroll
-        for (int c = 0; c < 7; c++) ob[c] = T(0);
-        fetch(cur, word, tst, ob);
-
-        for (; idx < count; idx += n_warps) {
-            const int64_t ie = p.env_begin + (int64_t)(uint32_t)cur;
-            const unsigned mask = (unsigned)(cur >> 32) & 0xffffu;
-            const uint32_t cond = (uint32_t)(cur >> 48) & 31u;
-            // ---- stage the prefetched data, start the next fetches
-            if (lane < 20) s_ent[lane] = word;
-            const int32_t t_new = __shfl_sync(0xffffffffu, tst, 20);     // already incremented by the cull launch
-            __syncwarp();
-            const T pos[3] = {s_ent[16], s_ent[17], s_ent[18]};
-            if (lane < n_obst && ((mask >> lane) & 1u)) obstacle_ray_record<T>(pos, ob, lane_is_cap, s_pre + lane * kPreStride);
-            const uint64_t nn = (idx + 2 * n_warps < count) ? p.view_list[idx + 2 * n_warps] : 0;
-            if (idx + n_warps < count) fetch(nxt, word, tst, ob);
-            T R[9];
-            rzyx<T>(s_ent[0], s_ent[1], s_ent[2], s_ent[3], s_ent[4], s_ent[5], R);
-            const T poison = s_ent[REC_POISON];
-            __syncwarp();
-
-            // ---- cast rays against the in-view obstacles, pooled cells to the observation row
-            const T oa_dot = radar_env<T, RPL, false>(p, rl, R, poison, mask, s_pre, s_ray, lane, ie);
-
-            // ---- what the cull launch left open: the reward with its obstacle-avoidance term and the running return
-            //      (every lane computes the same values from the staged record, lane 0 stores)
-            const T r_oa = p.sum_beta_oa / oa_dot - T(1);      // docking3d.py:792
-            const T reward = step_reward<T>(p, s_ent[REC_A], s_ent[REC_B], s_ent[REC_R7], s_ent[REC_LPD], r_oa, cond);
-            const T ep_ret = s_ent[19] + reward;
-            const bool done = cond != 0;
-            if (lane == 0) {
-                p.reward[ie] = reward;
-                if (done && p.ep_return_out) p.ep_return_out[ie] = ep_ret;
-                if (!(done && p.auto_reset)) p.ep_return[ie] = ep_ret;
-            }
-            if (done) {       // warp-uniform
-                double mine = 0.0;
-                if (lane == DOCKAUV_STAT_EPISODES) mine = 1.0;
-                else if (lane == DOCKAUV_STAT_SUM_RETURN) mine = (double)ep_ret;
-                else if (lane == DOCKAUV_STAT_SUM_LENGTH) mine = (double)t_new;
-                else if (lane >= DOCKAUV_STAT_COND0 && lane < DOCKAUV_STAT_COND0 + 5) mine = ((cond >> (lane - DOCKAUV_STAT_COND0)) & 1u) ? 1.0 : 0.0;
-                else if (lane == DOCKAUV_STAT_SUM_FINAL_DELTA_D) mine = (double)s_ent[REC_DD];
-                else if (lane == DOCKAUV_STAT_NAN_ENVS) mine = (reward != reward) ? 1.0 : 0.0;
-                stat_acc += mine;
-                __syncwarp();      // the pooled cells of the row are in place before it is moved
-                end_episode_warp<T>(p, ie, lane);
-            }
-            __syncwarp();
-            cur = nxt;
-            nxt = nn;
-        }
+    // software pipeline over the list: the data of entry n + 1 is on its way into the other stage buffer while entry n is
+    // cast.  What a lane fetches: lane c < 20 one word (record, position, running return) through a per-lane pointer and
+    // stride, lane 20 the step counter, lane k < n_obst with bit k of the mask obstacle k.
+    const bool lane_is_cap = lane < n_caps;
+    const T *obst_row = lane_is_cap ? p.capsules + (int64_t)(lane * 7) * N : p.spheres + (int64_t)((lane - n_caps) * 4) * N;
+    const int obst_words = lane_is_cap ? 7 : 4;
+    const T *word_src = p.rec + lane;            // lanes 0..15: record word `lane`, stride 16
+    int64_t word_stride = kRecWords;
+    if (lane >= 16) {
+        word_stride = 1;
+        word_src = lane < 19 ? p.state + (int64_t)(lane - 16) * N : p.ep_return;
     }
-    // ---- episodes that ended in the cull launch (nothing in view): one warp per env moves the terminal-observation row
-    //      and re-initialises the env.  A reset is a ~3000-instruction chain for one thread and the ~1 % of envs it hits
-    //      are scattered; here they are spread over all warps of this persistent grid.
-    {
-        const int64_t n_range = p.env_end - p.env_begin;
-        for (unsigned k = w_global; k < n_ended; k += n_warps) {
-            const int64_t ie = p.env_begin + (int64_t)(uint32_t)p.view_list[n_range - 1 - k];
-            end_episode_warp<T>(p, ie, lane);
+    // shared-window addresses of this lane's slots in stage buffer 0 (buffer 1: + kStageWords words)
+    const unsigned sa_word = (unsigned)__cvta_generic_to_shared(s_warp + lane);
+    const unsigned sa_obst = (unsigned)__cvta_generic_to_shared(s_warp + kStageObst + 8 * (lane & 15));
+    auto fetch = [&](uint64_t entry, int b) {
+        const int64_t e = p.env_begin + (int64_t)(uint32_t)entry;
+        const unsigned mask = (unsigned)(entry >> 32) & 0xffffu;
+        const unsigned boff = b ? (unsigned)(kStageWords * sizeof(T)) : 0u;
+        if (lane < 20) cp_async_word<T>(sa_word + boff, word_src + e * word_stride);
+        if (lane == 20) cp_async_word<int32_t>(sa_word + boff, p.t_steps + e);
+        if (lane < n_obst && ((mask >> lane) & 1u)) {
+            const T *g = obst_row + e;
+#pragma unroll
+            for (int c = 0; c < 7; c++)
+                if (c < obst_words) cp_async_word<T>(sa_obst + boff + c * (unsigned)sizeof(T), g + (int64_t)c * N);
         }
+    };
+    uint64_t cur = p.view_list[idx];
+    uint64_t nxt = (idx + n_warps < count) ? p.view_list[idx + n_warps] : 0;
+    fetch(cur, 0);
+    double stat_acc = 0.0;       // lane k < DOCKAUV_STAT_ENV_STEPS accumulates statistic k of the episodes this warp ended
+    int buf = 0;
+
+    for (; idx < count; idx += n_warps, buf ^= 1) {
+        const int64_t ie = p.env_begin + (int64_t)(uint32_t)cur;
+        const unsigned mask = (unsigned)(cur >> 32) & 0xffffu;
+        const uint32_t cond = (uint32_t)(cur >> 48) & 31u;
+        const T *s_ent = s_warp + buf * kStageWords;
+        // ---- the staged data of this entry is complete; start the next fetch into the other buffer (last read one
+        //      iteration ago, before that iteration's closing __syncwarp)
+        cp_async_wait_all();
+        __syncwarp();
+        const uint64_t nn = (idx + 2 * n_warps < count) ? p.view_list[idx + 2 * n_warps] : 0;
+        if (idx + n_warps < count) fetch(nxt, buf ^ 1);
+        const T pos[3] = {s_ent[16], s_ent[17], s_ent[18]};
+        if (lane < n_obst && ((mask >> lane) & 1u)) {
+            T ob[7];
+#pragma unroll
+            for (int c = 0; c < 7; c++) ob[c] = c < obst_words ? s_ent[kStageObst + 8 * lane + c] : T(0);
+            obstacle_ray_record<T>(pos, ob, lane_is_cap, s_pre + lane * kPreStride);
+        }
+        T R[9];
+        rzyx<T>(s_ent[0], s_ent[1], s_ent[2], s_ent[3], s_ent[4], s_ent[5], R);
+        const T poison = s_ent[REC_POISON];
+        __syncwarp();
+
+        // ---- cast rays against the in-view obstacles, pooled cells to the observation row
+        const T oa_dot = radar_env<T, RPL, false, RayLaneShared<T, RPL>>(p, rl, R, poison, mask, s_pre, s_ray, lane, ie);
+
+        // ---- what the cull launch left open: the reward with its obstacle-avoidance term and the running return
+        //      (every lane computes the same values from the staged record, lane 0 stores)
+        const T r_oa = p.sum_beta_oa / oa_dot - T(1);      // docking3d.py:792 (IEEE division: the other layouts' bits)
+        const T reward = step_reward<T>(p, s_ent[REC_A], s_ent[REC_B], s_ent[REC_R7], s_ent[REC_LPD], r_oa, cond);
+        const T ep_ret = s_ent[19] + reward;
+        const bool done = cond != 0;
+        if (lane == 0) {
+            p.reward[ie] = reward;
+            if (done && p.ep_return_out) p.ep_return_out[ie] = ep_ret;
+            if (!(done && p.auto_reset)) p.ep_return[ie] = ep_ret;
+        }
+        if (done) {       // warp-uniform, ~1 % of the listed envs
+            const int32_t t_new = reinterpret_cast<const int32_t *>(s_ent + 20)[0];     // already incremented by the cull launch
+            double mine = 0.0;
+            if (lane == DOCKAUV_STAT_EPISODES) mine = 1.0;
+            else if (lane == DOCKAUV_STAT_SUM_RETURN) mine = (double)ep_ret;
+            else if (lane == DOCKAUV_STAT_SUM_LENGTH) mine = (double)t_new;
+            else if (lane >= DOCKAUV_STAT_COND0 && lane < DOCKAUV_STAT_COND0 + 5) mine = ((cond >> (lane - DOCKAUV_STAT_COND0)) & 1u) ? 1.0 : 0.0;
+            else if (lane == DOCKAUV_STAT_SUM_FINAL_DELTA_D) mine = (double)s_ent[REC_DD];
+            else if (lane == DOCKAUV_STAT_NAN_ENVS) mine = (reward != reward) ? 1.0 : 0.0;
+            stat_acc += mine;
+            if (lane == 0) p.ended_list[atomicAdd(&p.view_count[1], 1u)] = (uint32_t)cur;
+        }
+        __syncwarp();
+        cur = nxt;
+        nxt = nn;
     }
     if (lane < DOCKAUV_STAT_ENV_STEPS && stat_acc != 0.0)
         atomicAdd(&p.stats[(blockIdx.x & (DOCKAUV_STAT_COPIES - 1)) * DOCKAUV_N_STATS + lane], stat_acc);
 }
 
+// ------------------------------------------------------------------------------------------------------- 4. episode end
+// The ENDED envs of the step (compact list, ~1 % of the batch): the last observation is kept as terminal_observation, the
+// all-zero reset observation is handed back (docking3d.py:269,322) and the env is re-initialised.  One CTA of eight warps
+// per 32 list entries: lane = env, warp = reset role (reset_envs_cta) and 16-byte piece of the observation row.
+// Measured alternatives (1M-env step): one WARP per ended env (round 1, and the first version of this pipeline, inside the
+// ray launch): ~4000 warp instructions per reset at 1..8 active lanes, 28 M per half batch, a third of the ray launch; one
+// THREAD per ended env: 40x leaner but a 5500-instruction dependent chain, 70 us for a launch that occupies 5 % of the GPU;
+// eight LANES per env: the roles serialise inside the warp, same 70 us.
+template <typename T>
+__global__ void __launch_bounds__(kResetCta) episode_end_kernel(const __grid_constant__ KParams<T> p) {
+    const unsigned n_ended = p.view_count[1];
+    const int n_obs = p.n_obs;
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    // every thread of a CTA runs the same number of trips (reset_envs_cta has a barrier)
+    const unsigned trips = (n_ended + gridDim.x * 32 - 1) / (gridDim.x * 32);
+    unsigned k = blockIdx.x * 32 + lane;
+    for (unsigned trip = 0; trip < trips; trip++, k += gridDim.x * 32) {
+        const bool valid = k < n_ended;
+        int64_t ie = 0;
+        if (valid) {
+            ie = p.env_begin + (int64_t)p.ended_list[k];
+            float *row = p.obs + ie * n_obs;
+            float *trow = p.terminal_obs ? p.terminal_obs + ie * n_obs : nullptr;
+            if ((n_obs & 3) == 0) {
+                float4 *r4 = reinterpret_cast<float4 *>(row), *t4 = reinterpret_cast<float4 *>(trow);
+                for (int c = role; c < (n_obs >> 2); c += kResetRoles) {
+                    if (trow) t4[c] = r4[c];
+                    if (p.auto_reset) r4[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+            } else {
+                for (int c = role; c < n_obs; c += kResetRoles) {
+                    if (trow) trow[c] = row[c];
+                    if (p.auto_reset) row[c] = 0.0f;
+                }
+            }
+        }
+        if (p.auto_reset) reset_envs_cta<T>(p, ie, valid);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------- launcher
-template <typename T, int VEH, int NU>
+template <typename T, int VEH, int NU, bool FIN>
 static cudaError_t launch_dynamics(const KParams<T> &k, unsigned blocks, cudaStream_t st) {
     const bool cur = k.has_current != 0, spm = k.sparse_minv != 0;
-    if (cur && spm) dynamics_kernel<T, VEH, NU, true, true><<<blocks, kDynThreads, 0, st>>>(k);
-    else if (cur) dynamics_kernel<T, VEH, NU, true, false><<<blocks, kDynThreads, 0, st>>>(k);
-    else if (spm) dynamics_kernel<T, VEH, NU, false, true><<<blocks, kDynThreads, 0, st>>>(k);
-    else dynamics_kernel<T, VEH, NU, false, false><<<blocks, kDynThreads, 0, st>>>(k);
+    if (cur && spm) dynamics_kernel<T, VEH, NU, true, true, FIN><<<blocks, kDynThreads, 0, st>>>(k);
+    else if (cur) dynamics_kernel<T, VEH, NU, true, false, FIN><<<blocks, kDynThreads, 0, st>>>(k);
+    else if (spm) dynamics_kernel<T, VEH, NU, false, true, FIN><<<blocks, kDynThreads, 0, st>>>(k);
+    else dynamics_kernel<T, VEH, NU, false, false, FIN><<<blocks, kDynThreads, 0, st>>>(k);
     return cudaGetLastError();
 }
 
@@ -526,21 +649,23 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     KParams<T> kc = k;
     kc.view_count = k.view_count + kListCounters * (k.env_begin / kWarpEnvs);   // counters per concurrently stepped env range
     kc.view_list = k.view_list + k.env_begin;
+    kc.ended_list = k.ended_list + k.env_begin;
     int n_mark = 0;
     auto mark = [&]() {
         if (marks) cudaEventRecord(marks[n_mark++], st);
     };
     mark();
-    cudaError_t e = launch_dynamics<T, VEH, NU>(kc, (unsigned)((n + kDynThreads - 1) / kDynThreads), st);
+    const bool has_obstacles = k.n_caps + k.n_sph > 0;
+    const unsigned dyn_blocks = (unsigned)((n + kDynThreads - 1) / kDynThreads);
+    // scenarios without obstacles are finished by the dynamics launch itself: no cull, no rays
+    cudaError_t e = has_obstacles ? launch_dynamics<T, VEH, NU, false>(kc, dyn_blocks, st) : launch_dynamics<T, VEH, NU, true>(kc, dyn_blocks, st);
     if (e != cudaSuccess) return e;
     mark();
-    cull_finish_kernel<T><<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, 0, st>>>(kc);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    mark();
-    // (scenarios without obstacles list nothing: the launch then only re-initialises the envs whose episode ended)
-    {
-        const RaysSmem<T> L(k.n_rays);
-        const int smem = kRayWarps * L.warp_words * (int)sizeof(T);
+    if (has_obstacles) {
+        cull_finish_kernel<T><<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, 0, st>>>(kc);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        mark();
+        const int smem = kRayWarps * (k.n_rays <= 64 ? RaysSmem<T, 2>(k.n_rays).warp_words : RaysSmem<T, 8>(k.n_rays).warp_words) * (int)sizeof(T);
         int64_t blocks = (int64_t)(k.sm_count > 0 ? k.sm_count : 148) * (DOCKAUV_RAY_CTAS_PER_SM * 4 / kRayWarps);
         const int64_t most = (n + kRayWarps - 1) / kRayWarps;
         if (blocks > most) blocks = most;
@@ -553,6 +678,15 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
             if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
             kern<<<(unsigned)blocks, kRayWarps * 32, smem, st>>>(kc);
         }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        mark();
+    }
+    {
+        // the list length is only known on the device: a grid for ~3 % of the range (32 entries per CTA), grid-stride beyond
+        int64_t blocks = n / 1024 + 1;
+        const int64_t cap = (int64_t)(k.sm_count > 0 ? k.sm_count : 148) * 4;
+        if (blocks > cap) blocks = cap;
+        episode_end_kernel<T><<<(unsigned)blocks, kResetCta, 0, st>>>(kc);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         mark();
     }

@@ -64,6 +64,7 @@ __device__ __forceinline__ void prefetch_dynamics_inputs(const KParams<T> &p, in
         }
         if ((lane & 3) == 0) pf((const char *)p.actions + (p.act_f32 ? 4 : 8) * NU * j);
         if ((lane & 7) == 0) pf(p.t_steps + j);
+        if ((lane & 15) == 0) pf(p.ep_return + j);
     }
 #endif
 }
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kWarpEnvs) step_warp_kernel(const __grid_const
                 T R[9];
 #pragma unroll
                 for (int c = 0; c < 9; c++) R[c] = pose[3 + c];
-                const T oa_dot = radar_env<T, RPL, DBG>(p, rl, R, poison, near_mask, s_pre + (s * slots) * kPreStride, s_ray,
+                const T oa_dot = radar_env<T, RPL, DBG, RayLane<T, RPL>>(p, rl, R, poison, near_mask, s_pre + (s * slots) * kPreStride, s_ray,
                                                         lane, i0 + e_warp + e);
                 if (lane == e) my_oa_dot = oa_dot;
             }

@@ -110,7 +110,7 @@ def test_cuda_reset_kernel_matches_reference(scenario):
 @pytest.mark.parametrize("layout", ["pipeline", "warp_rays", "thread_per_env"])
 @pytest.mark.parametrize("scenario", SCENARIO_NAMES)
 def test_cuda_auto_reset_matches_reference(scenario, layout):
-    """The in-step auto-reset (warp-cooperative in the pipeline layout, scalar in the others): every env is driven into
+    """The in-step auto-reset (the episode-end launch of the pipeline layout, in-kernel in the others): every env is driven into
     Done-max_t, and the state the step leaves behind must be the golden initial condition of the NEXT episode key."""
     import torch
     from gym_dockauv_b200 import envs
