@@ -40,23 +40,27 @@ N_SYNTH_SPHERES = 3
 
 # BASELINE.json configs with the ALGORITHMIC figures of SURVEY.md 8(d), per env-step and split over the launches of the
 # pipeline: dynamics = the 6-DOF integration + navigation errors + obs[0:16] + radar-free reward terms;
-# cull = body-collision tests + (for envs with nothing in view) reward / done / counters; rays = 64 rays x (rotate 25 +
-# 5 capsules x 33 + 3 spheres x 10 + pool / OA 8).  Bytes: every persistent item read once and written once.
+# cull_finish = body-collision tests + reward / done / counters; rays_finish = n_rays x (rotate 25 + K_c x 33 + K_s x 10 +
+# pool / OA 8) -- the contract's brute-force figure, PER ENV THE RAY LAUNCH VISITS: the culls are exact, an env with
+# nothing in view needs no ray test, so the launch's algorithmic work is that figure times the listed fraction (read live
+# from the library's work-list counter).  Bytes: every persistent item read once and written once, attributed to the
+# launch that moves it (state / command / action / goal / obs[0:16] -> dynamics; obstacles, counters, reward, flags ->
+# cull_finish; pooled ray cells -> rays_finish); their sum is the config's contract figure.
 CONFIGS = {
     "C2": dict(scenario="SimpleDocking3d", vehicle="BlueROV2", envs=65536, radar64=False, n_synth=0, h=0.1,
-               bytes=538, flops=2900, launch_flops=dict(dynamics=2900, cull_finish=0, rays_finish=0, episode_end=0),
-               launch_bytes=dict(dynamics=458, cull_finish=80, rays_finish=0, episode_end=0),
+               bytes=538, flops=2900, launch_flops=dict(dynamics=2900, episode_end=0),
+               launch_bytes=dict(dynamics=538, episode_end=0),
                workload="C2: SimpleDocking3d, BlueROV2, 65,536 envs, dynamics + reward only (no obstacles: every ray "
                         "reads max_dist), random actions U(-1,1) f32, auto-reset"),
     "C3": dict(scenario="CapsuleCurrentDocking3d", vehicle="LAUV", envs=262144, radar64=False, n_synth=0, h=0.02,
                bytes=534, flops=7250, launch_flops=dict(dynamics=3050, cull_finish=35, rays_finish=4165, episode_end=0),
-               launch_bytes=dict(dynamics=398, cull_finish=136, rays_finish=0, episode_end=0),
+               launch_bytes=dict(dynamics=336, cull_finish=118, rays_finish=80, episode_end=0),
                workload="C3: CapsuleCurrentDocking3d, LAUV with ocean current, 262,144 envs, docking-capsule collision "
                         "checks, t_step_size 0.02 (the reference's integrator diverges at its stock 0.1 for this "
                         "vehicle, SURVEY.md 8c), random actions U(-1,1) f32, auto-reset"),
     "C4": dict(scenario="ObstaclesDocking3d", vehicle="BlueROV2", envs=1 << 20, radar64=True, n_synth=N_SYNTH_SPHERES, h=0.1,
                bytes=898, flops=17700, launch_flops=dict(dynamics=2900, cull_finish=205, rays_finish=14592, episode_end=0),
-               launch_bytes=dict(dynamics=458, cull_finish=440, rays_finish=0, episode_end=0),
+               launch_bytes=dict(dynamics=400, cull_finish=434, rays_finish=64, episode_end=0),
                workload="C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions "
                         "U(-1,1) f32, auto-reset of finished envs"),
 }
@@ -373,6 +377,7 @@ def run_ours(args, rank, world, local_rank):
         per_launch.append(env.last_step_ms()[1])
     env.enable_timing(False)
     launch_ms = np.array(per_launch).mean(axis=0) if per_launch and per_launch[0] else np.zeros(0)
+    n_listed, n_ended = env.last_list_counts()      # work-list lengths of the last step
 
     # ---- end to end through the public API with host buffers (rank-local, then max over ranks)
     e2e_steps = max(3, min(args.e2e_steps, args.steps))
@@ -466,12 +471,18 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"bound": pipe_name, "unit": "TFLOP/s", "peak": pipe_peak,
                     "peak_source": "dockauv_measure_peaks: 8-chain FMA micro-kernel on this GPU, live (MEASURED_PEAKS.json "
                                    f"carries no FP64 figure; nominal {FP64_NOMINAL_TFLOPS} TFLOP/s at 1.965 GHz)"}
+        listed_frac = n_listed / N
+        roofline["work_lists"] = {"listed_frac": listed_frac, "ended_frac": n_ended / N,
+                                  "note": "envs with an obstacle in view (visited by the ray launch) / envs whose episode "
+                                          "ended, in the last step"}
         if dominant is not None and pipe_peak:
             dms = launches_ms[dominant]
-            ach = c["launch_flops"][dominant] * N / (dms * 1e-3) / 1e12
+            units = N * (listed_frac if dominant == "rays_finish" else 1.0)      # envs the launch has algorithmic work for
+            ach = c["launch_flops"][dominant] * units / (dms * 1e-3) / 1e12
             ach_gbs = c["launch_bytes"][dominant] * N / (dms * 1e-3) / 1e9
             roofline.update({
                 "kernel": dominant, "kernel_ms": dms, "algorithmic_flops_per_env": c["launch_flops"][dominant],
+                "envs_with_work_per_launch": units,
                 "achieved": ach, "frac": ach / pipe_peak, "frac_of_nominal": ach / FP64_NOMINAL_TFLOPS if pipe_name == "fp64" else None,
                 "executed_pipe_frac": (ncu["launches"][dominant].get("fp64_pipe_pct", 0.0) / 100.0) if ncu_ok else None,
                 "traffic": (ncu["launches"][dominant]["dram_bytes_per_env"] * N) if ncu_ok else None,

@@ -34,6 +34,7 @@ SYMBOLS = {
     "dockauv_clear_stats": (_i, [_vp, _vp]),
     "dockauv_measure_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dockauv_launch_count": (_i, [_vp, C.POINTER(_i64)]),
+    "dockauv_last_list_counts": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "dockauv_rollout_captures": (_i, [_vp, C.POINTER(_i64)]),
     "dockauv_enable_timing": (_i, [_vp, _i]),
     "dockauv_last_step_ms": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -968,6 +968,25 @@ extern "C" int dockauv_launch_count(DockauvHandle *h, int64_t *n) {
     return DOCKAUV_OK;
 }
 
+extern "C" int dockauv_last_list_counts(DockauvHandle *h, int64_t *n_listed, int64_t *n_ended, void *stream) {
+    if (!h || !n_listed || !n_ended) return fail(DOCKAUV_EINVAL, "null argument");
+    *n_listed = *n_ended = 0;
+    if (!h->pipe_buf) return DOCKAUV_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // one counter pair per concurrently stepped env range (at most kHostStreams parts, or the host chunks of step_host):
+    // pairs of ranges that were not stepped stay zero
+    const size_t n_cnt = 2 * ((size_t)h->n_envs / 128 + 2);
+    std::vector<unsigned int> host(n_cnt);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), h->kd.view_count, n_cnt * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (size_t k = 0; k + 1 < n_cnt; k += 2) {
+        *n_listed += host[k];
+        *n_ended += host[k + 1];
+    }
+    return DOCKAUV_OK;
+}
+
 extern "C" int dockauv_rollout_captures(DockauvHandle *h, int64_t *n) {
     if (!h || !n) return fail(DOCKAUV_EINVAL, "null argument");
     *n = h->rg_captures;

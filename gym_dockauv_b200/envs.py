@@ -392,6 +392,12 @@ class BaseDocking3d:
         _capi.check(self._lib.dockauv_step_graph_captures(self._handle, C.byref(n)))
         return n.value
 
+    def last_list_counts(self):
+        """(envs with an obstacle in view, envs whose episode ended) in the most recent step (pipeline layout)."""
+        a, b = C.c_int64(), C.c_int64()
+        _capi.check(self._lib.dockauv_last_list_counts(self._handle, C.byref(a), C.byref(b), self._stream()))
+        return a.value, b.value
+
     def rollout_captures(self):
         """How many times ``rollout(use_graph=True)`` had to capture its launch sequence (replays do not)."""
         n = C.c_int64()

@@ -303,6 +303,10 @@ DOCKAUV_API int dockauv_measure_peaks(int device, double *fp64_tflops, double *f
 /* Kernel-level accounting for bench.py: number of kernels launched by this handle so far, and CUDA-event
  * time (ms) of the most recent dockauv_step launch when timing is enabled. */
 DOCKAUV_API int dockauv_launch_count(DockauvHandle *h, int64_t *n_launches);
+/* Work-list lengths of the most recent step of the pipeline layout, summed over the stepped env ranges: envs that had an
+ * obstacle in view (the ray launch's work) and envs whose episode ended (the episode-end launch's work).  Synchronises
+ * `stream`; diagnostics for bench.py (the counters are re-used by the next step). */
+DOCKAUV_API int dockauv_last_list_counts(DockauvHandle *h, int64_t *n_listed, int64_t *n_ended, void *stream);
 /* how many times dockauv_rollout(use_graph) had to capture its launch sequence (a replay with the same pointers does not) */
 DOCKAUV_API int dockauv_rollout_captures(DockauvHandle *h, int64_t *n_captures);
 DOCKAUV_API int dockauv_enable_timing(DockauvHandle *h, int enabled);

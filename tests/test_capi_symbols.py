@@ -69,6 +69,7 @@ def test_argument_validation_without_gpu():
     assert lib.dockauv_step_host(None, None, 0, None, None, None, None, 1, None) == -1
     assert lib.dockauv_refresh_obstacles(None, None) == -1
     assert lib.dockauv_rollout_captures(None, None) == -1
+    assert lib.dockauv_last_list_counts(None, None, None, None) == -1
 
 
 def test_no_cpu_fallback():
