@@ -40,7 +40,7 @@ N_SYNTH_SPHERES = 3
 
 # BASELINE.json configs with the ALGORITHMIC figures of SURVEY.md 8(d), per env-step and split over the launches of the
 # pipeline: dynamics = the 6-DOF integration + navigation errors + obs[0:16] + radar-free reward terms;
-# cull_finish = body-collision tests + reward / done / counters; rays_finish = n_rays x (rotate 25 + K_c x 33 + K_s x 10 +
+# cull_finish = body-collision tests + reward / done / counters; rays_* = n_rays x (rotate 25 + K_c x 33 + K_s x 10 +
 # pool / OA 8) -- the contract's brute-force figure, PER ENV THE RAY LAUNCH VISITS: the culls are exact, an env with
 # nothing in view needs no ray test, so the launch's algorithmic work is that figure times the listed fraction (read live
 # from the library's work-list counter).  Bytes: every persistent item read once and written once, attributed to the
@@ -137,6 +137,10 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.proc, self.rows = index, None, []
 
+    def mark(self):
+        """Index of the next sample: brackets the timed region."""
+        return len(self.rows)
+
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
@@ -151,7 +155,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, first=0, last=None):
+        """Summary of the samples [first, last) (default: all); the timed region of a short run can fall between two
+        20 ms samples, so the caller passes the window from the start of the timed region to the end of the measurement
+        passes that follow it under the same load."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -161,7 +168,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[first:last]:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -318,6 +325,9 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()       # running well before the timed region (nvidia-smi needs ~0.1 s to deliver its first sample)
     # burn-in: brings the batch from "every env just reset" to a mixed episode-age distribution (episodes last
     # ~100 steps under random actions), so the timed steps see the steady-state mix of ray hits and resets
     for k in range(args.burn_in):
@@ -326,9 +336,7 @@ def run_ours(args, rank, world, local_rank):
         env.step(pool[k % len(pool)])
     env.clear_stats()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    clk_first = sampler.mark()
     launches0 = env.launch_count()
     # ---- the timed region: K steps; one statistics all-reduce per rollout on a side stream, at least one
     rollout = max(1, min(args.rollout, args.steps))
@@ -348,7 +356,7 @@ def run_ours(args, rank, world, local_rank):
             n_reduces += 1
     torch.cuda.current_stream(dev).wait_stream(side)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clk_timed_end = sampler.mark()
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = np.array([evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)])
     launches = env.launch_count() - launches0
@@ -378,6 +386,12 @@ def run_ours(args, rank, world, local_rank):
     env.enable_timing(False)
     launch_ms = np.array(per_launch).mean(axis=0) if per_launch and per_launch[0] else np.zeros(0)
     n_listed, n_ended = env.last_list_counts()      # work-list lengths of the last step
+    clocks = None
+    if rank == 0:
+        time.sleep(0.05)
+        clocks = sampler.stop(clk_first, None)
+        clocks["samples_inside_timed_region"] = max(0, clk_timed_end - clk_first)
+        clocks["window"] = "timed region + the per-launch timing pass that follows it (same kernels, same load)"
 
     # ---- end to end through the public API with host buffers (rank-local, then max over ranks)
     e2e_steps = max(3, min(args.e2e_steps, args.steps))
@@ -477,7 +491,7 @@ def run_ours(args, rank, world, local_rank):
                                           "ended, in the last step"}
         if dominant is not None and pipe_peak:
             dms = launches_ms[dominant]
-            units = N * (listed_frac if dominant == "rays_finish" else 1.0)      # envs the launch has algorithmic work for
+            units = N * (listed_frac if dominant.startswith("rays") else 1.0)      # envs the launch has algorithmic work for
             ach = c["launch_flops"][dominant] * units / (dms * 1e-3) / 1e12
             ach_gbs = c["launch_bytes"][dominant] * N / (dms * 1e-3) / 1e9
             roofline.update({

@@ -115,7 +115,9 @@ struct DockauvHandle {
         StepKey key;
         cudaGraphExec_t exec = nullptr;
         int64_t launches = 0;
+        std::vector<int64_t> begins;
     };
+    std::vector<int64_t> last_begins;     // first env of every range the most recent step call stepped (their list counters)
     std::vector<StepGraph> sg;
     size_t sg_next = 0;            // slot replaced next once the cache is full
     bool sg_enabled = true;
@@ -200,6 +202,9 @@ static void fill_kparams(const DockauvParams &s, int64_t n_envs, KParams<T> &k) 
     k.inv_max_attitude = (T)(1.0 / s.max_attitude);
     k.log_den_obs = (T)std::log(s.dist_goal_reached_tol / s.max_dist_from_goal);
     k.log_den_rew = (T)std::log(std::fmax(s.dist_goal_reached_tol, 0.001) / s.max_dist_from_goal);
+    k.inv_max_dist_from_goal = (T)(1.0 / s.max_dist_from_goal);
+    k.inv_log_den_obs = (T)(1.0 / std::log(s.dist_goal_reached_tol / s.max_dist_from_goal));
+    k.inv_log_den_rew = (T)(1.0 / std::log(std::fmax(s.dist_goal_reached_tol, 0.001) / s.max_dist_from_goal));
     k.w_d = (T)s.w_d; k.w_delta_psi = (T)s.w_delta_psi; k.w_delta_theta = (T)s.w_delta_theta;
     k.w_phi = (T)s.w_phi; k.w_theta = (T)s.w_theta; k.w_Thetadot = (T)s.w_Thetadot; k.w_oa = (T)s.w_oa;
     for (int i = 0; i < 5; i++) k.w_done[i] = (T)s.w_done[i];
@@ -328,8 +333,8 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         const size_t n = (size_t)n_envs;
         const int n_obsf = 2 * p->n_capsules + p->n_spheres;
         const size_t off_rec = 0, off_obsf = off_rec + 16 * esz * n, off_list = off_obsf + 16 * (size_t)n_obsf * n;
-        const size_t off_end = off_list + 8 * n, off_cnt = off_end + 4 * ((n + 1) & ~(size_t)1);
-        const size_t n_cnt = 2 * (n / 128 + 2);      // two list counters per concurrently stepped env range
+        const size_t off_end = off_list + 3 * 8 * n, off_cnt = off_end + 4 * ((n + 1) & ~(size_t)1);      // three view lists
+        const size_t n_cnt = 4 * (n / 128 + 2);      // four list counters per concurrently stepped env range
         cudaError_t e5 = cudaMalloc(&h->pipe_buf, off_cnt + 4 * n_cnt);
         if (e5 == cudaSuccess) e5 = cudaMemset(h->pipe_buf, 0, off_cnt + 4 * n_cnt);
         if (e5 != cudaSuccess) {
@@ -350,6 +355,10 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         h->kd.sm_count = h->kf.sm_count = sms;
+        h->kd.tpe_rays = h->kf.tpe_rays = (p->block_reduce == 2 && h->kd.n_rr <= 64) ? 1 : 0;
+#ifdef DOCKAUV_NO_TPE_RAYS      // tuning builds: every listed env through the warp-per-env ray launch
+        h->kd.tpe_rays = h->kf.tpe_rays = 0;
+#endif
         // one launch group over the whole batch by default: smaller chunks would keep the records in L2 but lose more
         // to partial waves than they gain (measured, profiles/r01/NOTES.md)
         h->kd.chunk_envs = h->kf.chunk_envs = p->split_chunk_envs > 0 ? p->split_chunk_envs : 0;
@@ -480,6 +489,7 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
         e = launch_step<float>(k, h->params.vehicle, layout, st, with_marks ? h->marks : nullptr, with_marks ? &h->n_marks : nullptr);
     }
     if (e != cudaSuccess) return fail(DOCKAUV_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+    h->last_begins.push_back(begin);
     const bool staged = dbg == nullptr;   // else: the fused kernel
     if (layout == DOCKAUV_LAYOUT_PIPELINE && staged) {
         const int64_t chunk = h->kd.chunk_envs > 0 ? h->kd.chunk_envs : (end - begin);
@@ -608,6 +618,7 @@ static int step_graph(DockauvHandle *h, const void *actions, int action_dtype, c
         cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
         int rc = DOCKAUV_OK;
         const int64_t before = h->launches;
+        h->last_begins.clear();
         if (e == cudaSuccess) {
             rc = step_device(h, actions, action_dtype, noise, out, nullptr, auto_reset, cs, false);
             e = cudaStreamEndCapture(cs, &graph);
@@ -623,6 +634,7 @@ static int step_graph(DockauvHandle *h, const void *actions, int action_dtype, c
         fresh.key = key;
         fresh.exec = exec;
         fresh.launches = n_launch;
+        fresh.begins = h->last_begins;
         if (h->sg.size() < (size_t)DOCKAUV_STEP_GRAPHS) {
             h->sg.push_back(fresh);
             g = &h->sg.back();
@@ -637,6 +649,7 @@ static int step_graph(DockauvHandle *h, const void *actions, int action_dtype, c
     }
     CUDA_TRY(cudaGraphLaunch(g->exec, st));
     h->launches += g->launches;
+    h->last_begins = g->begins;
     return DOCKAUV_OK;
 }
 
@@ -657,6 +670,7 @@ extern "C" int dockauv_step(DockauvHandle *h, const void *actions_dev, int actio
         }
         CUDA_TRY(cudaEventRecord(h->ev0, st));
     }
+    h->last_begins.clear();
     if (!h->timing && dbg == nullptr && h->sg_enabled) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
@@ -713,6 +727,7 @@ extern "C" int dockauv_step_host(DockauvHandle *h, const void *actions_host, int
     const size_t esz = h->params.precision == DOCKAUV_F64 ? 8 : 4;
     int rc = ensure_host_pipeline(h, asz * (size_t)N);
     if (rc != DOCKAUV_OK) return rc;
+    h->last_begins.clear();
     // chunks: multiples of 4096 envs, at most 12 per call so copies of chunk c+1 overlap the kernel of chunk c
     int64_t chunk = (N + DOCKAUV_HOST_CHUNKS - 1) / DOCKAUV_HOST_CHUNKS;
     chunk = ((chunk + 4095) / 4096) * 4096;
@@ -974,15 +989,17 @@ extern "C" int dockauv_last_list_counts(DockauvHandle *h, int64_t *n_listed, int
     if (!h->pipe_buf) return DOCKAUV_OK;
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    // one counter pair per concurrently stepped env range (at most kHostStreams parts, or the host chunks of step_host):
-    // pairs of ranges that were not stepped stay zero
-    const size_t n_cnt = 2 * ((size_t)h->n_envs / 128 + 2);
+    // one counter pair per env range the most recent step call stepped (halves of the batch, chunks of step_host)
+    const size_t n_cnt = 4 * ((size_t)h->n_envs / 128 + 2);
     std::vector<unsigned int> host(n_cnt);
     CUDA_TRY(cudaMemcpyAsync(host.data(), h->kd.view_count, n_cnt * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    for (size_t k = 0; k + 1 < n_cnt; k += 2) {
-        *n_listed += host[k];
-        *n_ended += host[k + 1];
+    for (int64_t b : h->last_begins) {
+        const size_t k = 4 * (size_t)(b / 128);
+        if (k + 3 < n_cnt) {
+            *n_listed += (int64_t)host[k] + host[k + 1] + host[k + 2];
+            *n_ended += host[k + 3];
+        }
     }
     return DOCKAUV_OK;
 }

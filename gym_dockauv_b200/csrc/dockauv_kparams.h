@@ -35,6 +35,7 @@ struct KParams {
     T inv_u_max, inv_v_max, inv_w_max, inv_p_max, inv_q_max, inv_r_max, inv_max_attitude;
     T log_den_obs;    // log(dist_goal_reached_tol / max_dist_from_goal), docking3d.py:465-466
     T log_den_rew;    // log(max(tol, 1e-3) / max_dist), docking3d.py:723
+    T inv_max_dist_from_goal, inv_log_den_obs, inv_log_den_rew;   // their reciprocals (same one-ulp caveat as above)
     T w_d, w_delta_psi, w_delta_theta, w_phi, w_theta, w_Thetadot, w_oa;
     T w_done[5];
     T arf[DOCKAUV_MAX_U];
@@ -73,6 +74,7 @@ struct KParams {
     T *rec;
     float4 *obsf;
     int32_t n_obsf, cull_exact;      // cull_exact: coordinates too large for the float cull -> decide everything in T
+    int32_t tpe_rays;                // the thread-per-env ray launch covers this radar (2x2 pooling, <= 64 pooled cells)
     unsigned long long *view_list;
     uint32_t *ended_list;
     unsigned int *view_count;

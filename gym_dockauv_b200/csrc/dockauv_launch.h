@@ -9,7 +9,7 @@ namespace dockauv {
 
 // marks (nullable): kMaxStepLaunches + 1 events; when given, the multi-launch layouts record one before their first
 // launch and one after each launch, *n_marks receives how many were recorded (0 for single-launch layouts)
-constexpr int kMaxStepLaunches = 4;
+constexpr int kMaxStepLaunches = 6;
 template <typename T>
 cudaError_t launch_step(const KParams<T> &k, int vehicle, int layout, cudaStream_t st, cudaEvent_t *marks = nullptr,
                         int *n_marks = nullptr);

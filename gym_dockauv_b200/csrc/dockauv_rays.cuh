@@ -107,6 +107,89 @@ struct RayLaneShared {
     }
 };
 
+// One ray against one capsule record (shape.py:341-390: cylinder root, body hit if 0 < y < baba, else end cap) / one
+// sphere record (shape.py:252-263: nearest root): returns min(best, distance) over the POSITIVE distances
+// (docking3d.py:438-439).  Branch-free sqrt / reciprocal in the hit path.  Shared by every radar mapping -> same bits.
+template <typename T>
+__device__ __forceinline__ T cast_capsule(const T rd[3], const T ba[3], const T oa[3], T baba, T baoa, T cc, T c2a, T c2b, T best) {
+    const T bard = rd[0] * ba[0] + rd[1] * ba[1] + rd[2] * ba[2];
+    const T rdoa = rd[0] * oa[0] + rd[1] * oa[1] + rd[2] * oa[2];
+    const T a = baba - bard * bard;
+    const T b = baba * rdoa - baoa * bard;
+    const T h = b * b - a * cc;
+    if (h > T(0)) {
+        const T t = (-b - Mth<T>::sqrt_pos(h)) * Mth<T>::rcp_(a);
+        const T y = baoa + t * bard;
+        T v = t;
+        if (!(y > T(0) && y < baba)) {
+            const bool far_end = y >= T(0);
+            const T b2 = far_end ? rdoa - bard : rdoa;     // rd . (pos - cap end)
+            const T h2 = b2 * b2 - (far_end ? c2b : c2a);
+            v = (h2 > T(0)) ? (-b2 - Mth<T>::sqrt_pos(h2 > T(0) ? h2 : T(1))) : T(-1);
+        }
+        if (v > T(0) && v < best) best = v;
+    }
+    return best;
+}
+
+// cast_capsule for mappings where the lanes of a warp are different envs (some lane always hits, so the hit path runs
+// anyway): straight-line code, which lets the compiler interleave the independent rays of a lane; only the end-cap root
+// (second square root) sits behind a warp vote.  Every value is formed by the same expression as in cast_capsule /
+// cast_sphere, so hits give identical bits.  Must be called by all 32 lanes.
+//   A SPHERE goes through the same code as a capsule whose cylinder quadratic IS the sphere quadratic (sphere_as_capsule:
+//   ba = 0, baba = 1, baoa = 1/2, cc = |oc|^2 - r^2 -> a = 1, b = rd . oc, h = b^2 - cc, y = 1/2: always a "body" hit);
+//   `touch` marks such a record: a tangent ray (h == 0) counts as a hit there (shape.py:258 tests h < 0 for "miss") and
+//   the root is not multiplied by 1 / a.
+template <typename T>
+__device__ __forceinline__ T cast_capsule_bf(const T rd[3], const T ba[3], const T oa[3], T baba, T baoa, T cc, T c2a, T c2b,
+                                             bool touch, T best) {
+    const T bard = rd[0] * ba[0] + rd[1] * ba[1] + rd[2] * ba[2];
+    const T rdoa = rd[0] * oa[0] + rd[1] * oa[1] + rd[2] * oa[2];
+    const T a = baba - bard * bard;
+    const T b = baba * rdoa - baoa * bard;
+    const T h = touch ? Mth<T>::fma_(b, b, -cc) : (b * b - a * cc);
+    const T sq = Mth<T>::sqrt_pos(h > T(0) ? h : T(1));
+    const T root = -b - (h > T(0) ? sq : T(0));
+    const T t = touch ? root : root * Mth<T>::rcp_(a);
+    const T y = baoa + t * bard;
+    const bool cand = touch ? (h >= T(0)) : (h > T(0));
+    const bool body = y > T(0) && y < baba;
+    T v = t;
+    bool okv = cand && body;
+    if (__any_sync(0xffffffffu, cand && !body)) {      // an end cap is in play for some env of the warp
+        const bool far_end = y >= T(0);
+        const T b2 = far_end ? rdoa - bard : rdoa;     // rd . (pos - cap end)
+        const T h2 = b2 * b2 - (far_end ? c2b : c2a);
+        const T v2 = -b2 - Mth<T>::sqrt_pos(h2 > T(0) ? h2 : T(1));
+        if (!body) {
+            v = v2;
+            okv = cand && (h2 > T(0));
+        }
+    }
+    return (okv && v > T(0) && v < best) ? v : best;
+}
+
+// the capsule-shaped record of a sphere for cast_capsule_bf: w = ba[3] oa[3] baba baoa c c2a c2b (obstacle_ray_record layout),
+// from the sphere record oc[3], c
+template <typename T>
+__device__ __forceinline__ void sphere_as_capsule(T w[11]) {
+    const T oc0 = w[0], oc1 = w[1], oc2 = w[2], c = w[3];
+    w[0] = w[1] = w[2] = T(0);
+    w[3] = oc0; w[4] = oc1; w[5] = oc2;
+    w[6] = T(1); w[7] = T(0.5); w[8] = c; w[9] = c; w[10] = c;
+}
+
+template <typename T>
+__device__ __forceinline__ T cast_sphere(const T rd[3], T ocx, T ocy, T ocz, T c, T best) {
+    const T b = ocx * rd[0] + ocy * rd[1] + ocz * rd[2];
+    const T h = b * b - c;
+    if (h >= T(0)) {
+        const T v = -b - (h > T(0) ? Mth<T>::sqrt_pos(h) : T(0));
+        if (v > T(0) && v < best) best = v;
+    }
+    return best;
+}
+
 // Casts this lane's rays against the obstacles of `mask` (bit k = obstacle k, capsules first; records in shared memory
 // at pre_env + k * kPreStride), clamps (sensor.py:117), writes the 2x2 zero-padded max-pool of the distances straight into
 // the env's observation row (obs[16:], docking3d.py:487) and returns sum(max((d/d_max)^2, eps_c) * beta) on every lane.
@@ -139,26 +222,7 @@ __device__ __forceinline__ T radar_env(const KParams<T> &p, const LANE &rl, cons
             const T ba[3] = {v0.x, v0.y, v1.x}, oa[3] = {v1.y, v2.x, v2.y};
             const T baba = v3.x, baoa = v3.y, cc = v4.x, c2a = v4.y, c2b = v5.x;
 #pragma unroll
-            for (int j = 0; j < RPL; j++) {
-                // shape.py:341-390 for one ray: cylinder root, body hit if 0 < y < baba, else end cap
-                const T bard = rd[j][0] * ba[0] + rd[j][1] * ba[1] + rd[j][2] * ba[2];
-                const T rdoa = rd[j][0] * oa[0] + rd[j][1] * oa[1] + rd[j][2] * oa[2];
-                const T a = baba - bard * bard;
-                const T b = baba * rdoa - baoa * bard;
-                const T h = b * b - a * cc;
-                if (h > T(0)) {
-                    const T t = (-b - Mth<T>::sqrt_pos(h)) * Mth<T>::rcp_(a);
-                    const T y = baoa + t * bard;
-                    T v = t;
-                    if (!(y > T(0) && y < baba)) {
-                        const bool far_end = y >= T(0);
-                        const T b2 = far_end ? rdoa - bard : rdoa;     // rd . (pos - cap end)
-                        const T h2 = b2 * b2 - (far_end ? c2b : c2a);
-                        v = (h2 > T(0)) ? (-b2 - Mth<T>::sqrt_pos(h2 > T(0) ? h2 : T(1))) : T(-1);
-                    }
-                    if (v > T(0) && v < best[j]) best[j] = v;
-                }
-            }
+            for (int j = 0; j < RPL; j++) best[j] = cast_capsule<T>(rd[j], ba, oa, baba, baoa, cc, c2a, c2b, best[j]);
         }
         while (sph_mask) {
             const int k = __ffs(sph_mask) - 1;
@@ -166,15 +230,7 @@ __device__ __forceinline__ T radar_env(const KParams<T> &p, const LANE &rl, cons
             const P2 *w2 = reinterpret_cast<const P2 *>(pre_env + (n_caps + k) * kPreStride);
             const P2 v0 = w2[0], v1 = w2[1];
 #pragma unroll
-            for (int j = 0; j < RPL; j++) {
-                // shape.py:252-263: nearest root of the ray / sphere quadratic
-                const T b = v0.x * rd[j][0] + v0.y * rd[j][1] + v1.x * rd[j][2];
-                const T h = b * b - v1.y;
-                if (h >= T(0)) {
-                    const T v = -b - (h > T(0) ? Mth<T>::sqrt_pos(h) : T(0));
-                    if (v > T(0) && v < best[j]) best[j] = v;
-                }
-            }
+            for (int j = 0; j < RPL; j++) best[j] = cast_sphere<T>(rd[j], v0.x, v0.y, v1.x, v1.y, best[j]);
         }
     }
     // ---- clamp (sensor.py:117), obstacle-avoidance partial sum (docking3d.py:767-792), stash for pooling

@@ -36,8 +36,23 @@ constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #ifndef DOCKAUV_MINB_CULL
 #define DOCKAUV_MINB_CULL 4
 #endif
+#ifndef DOCKAUV_MINB_TPE
+#define DOCKAUV_MINB_TPE 4          // thread-per-env ray launch: (128, 4) = 128 registers
+#endif
+#ifndef DOCKAUV_TPE_CTAS_PER_SM
+#define DOCKAUV_TPE_CTAS_PER_SM 8   // persistent grid of the thread-per-env ray launch (twice what is resident: finer balance)
+#endif
+#ifndef DOCKAUV_TPE_WARP_CTAS_PER_SM
+#define DOCKAUV_TPE_WARP_CTAS_PER_SM 1   // CTAs per SM of that launch that run the warp-per-env loop over class 3
+#endif
+#ifndef DOCKAUV_TPE_SPLIT
+#define DOCKAUV_TPE_SPLIT 1         // lanes per env in the thread-per-env ray launch (each takes a run of pooled cells; 2: +8 %, 4: +11 % time)
+#endif
+#ifndef DOCKAUV_CULL_STAGE
+#define DOCKAUV_CULL_STAGE 0        // 1: all obstacle records of an env staged into shared memory by cp.async (measured: cull 125 vs 123 us, step 0.500 vs 0.487 ms: 53 KB of shared memory per CTA cost more than the loop's L2 hits)
+#endif
 #ifndef DOCKAUV_CULL_PREFETCH
-#define DOCKAUV_CULL_PREFETCH 1
+#define DOCKAUV_CULL_PREFETCH 1     // (without staging) L2 prefetch of the records
 #endif
 #ifndef DOCKAUV_MINB_RAYS
 #define DOCKAUV_MINB_RAYS 6         // ray launch: (128, 6) = 80 registers, 24 warps per SM
@@ -46,7 +61,7 @@ constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #define DOCKAUV_RAY_CTAS_PER_SM DOCKAUV_MINB_RAYS   // persistent grid of the ray launch, in 4-warp CTAs per SM (= what is resident)
 #endif
 
-constexpr int kListCounters = 2;    // work-list counters per stepped env range (see cull_finish_kernel)
+constexpr int kListCounters = 4;    // work-list counters per stepped env range: view lists of class 1, 2, 3 and the ended list
 
 // ---- the per-env record written by the dynamics launch
 constexpr int kRecWords = 16;
@@ -249,7 +264,7 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
             if (em) {
                 const int lane = threadIdx.x & 31, leader = __ffs(am) - 1;
                 unsigned base = 0;
-                if (lane == leader) base = atomicAdd(&p.view_count[1], (unsigned)__popc(em));
+                if (lane == leader) base = atomicAdd(&p.view_count[3], (unsigned)__popc(em));
                 base = __shfl_sync(am, base, leader);
                 if (done) p.ended_list[base + __popc(em & ((1u << lane) - 1u))] = (uint32_t)(i - p.env_begin);
             }
@@ -280,6 +295,7 @@ constexpr int kCullThreads = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_kernel(const __grid_constant__ KParams<T> p) {
+    extern __shared__ __align__(16) unsigned char cull_smem[];      // float4 [n_obsf][kCullThreads] when the records are staged
     const int64_t N = p.n_envs;
     const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kCullThreads;
     const int64_t i = i0 + threadIdx.x;
@@ -287,14 +303,24 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
     const int lane = threadIdx.x & 31;
     WarpStats bs;
     bool listed = false, ended = false;      // ended: episode over and nothing in view -> on the list of the episode-end launch
+    bool poison_free = true;
     uint32_t info = 0;                       // bits 0..15 in-view mask (capsules first), 16 collision
     uint32_t cond = 0;
     if (active) {
         const T *rec = p.rec + i * kRecWords;
         const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
-        // the obstacle records are walked one after the other (one register pair of float4 in flight): pulling all of
-        // them into L2 now turns the loop's round trips into L2 hits (it was 64 % of this launch's stall samples)
-#if DOCKAUV_CULL_PREFETCH
+        // ---- all float obstacle records of this env on their way into shared memory at once (cp.async, 16 bytes per
+        //      slot, [slot][thread]: conflict-free): the loop below then never waits for HBM.  With one register pair of
+        //      records in flight (round 2's first version) 64 % of this launch's stall samples sat on the loop's loads
+#if DOCKAUV_CULL_STAGE
+        float4 *s_obs = reinterpret_cast<float4 *>(cull_smem) + threadIdx.x;
+        if (!p.cull_exact) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(s_obs);
+            for (int sl = 0; sl < p.n_obsf; sl++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (unsigned)(sl * kCullThreads * 16)),
+                             "l"(p.obsf + (int64_t)sl * N + i) : "memory");
+        }
+#elif DOCKAUV_CULL_PREFETCH
         if (!p.cull_exact)
             for (int sl = 0; sl < p.n_obsf; sl++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obsf + (int64_t)sl * N + i));
 #endif
@@ -312,6 +338,16 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
             rzyx<float>((float)w[0], (float)w[1], (float)w[2], (float)w[3], (float)w[4], (float)w[5], Rf);
 #pragma unroll
             for (int c = 0; c < 3; c++) prel[c] = (float)w[REC_PREL + c];
+#if DOCKAUV_CULL_STAGE
+            asm volatile("cp.async.wait_all;" ::: "memory");      // this thread's own records: no barrier needed
+            int slot = 0;
+#pragma unroll 1
+            for (int k = 0; k < n_obst; k++) {
+                const bool is_cap = k < n_caps;
+                const float4 c0 = s_obs[slot * kCullThreads];
+                const float4 c1 = is_cap ? s_obs[(slot + 1) * kCullThreads] : make_float4(0.f, 0.f, 0.f, 0.f);
+                slot += is_cap ? 2 : 1;
+#else
             // the next obstacle's record is requested before the current one is evaluated
             const float4 *ob = p.obsf + i;
             float4 q0 = ob[0], q1 = n_caps > 0 ? ob[N] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -325,6 +361,7 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
                     if (k + 1 < n_caps) q1 = ob[(int64_t)(slot + 1) * N];
                     slot += (k + 1 < n_caps) ? 2 : 1;
                 }
+#endif
                 int hit3;
                 bool view;
                 cull_pair_rec<T>(p, prel, Rf, c0, c1, is_cap, hit3, view);
@@ -364,7 +401,8 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
         }
         // a non-finite pose poisons the rays like the reference's NaN propagation: such envs go through the ray launch
         // (without obstacles every ray reads max_dist whatever the pose, docking3d.py:441)
-        listed = (info & 0xffffu) != 0u || (n_obst > 0 && !(poison == T(0)));
+        poison_free = poison == T(0);
+        listed = (info & 0xffffu) != 0u || (n_obst > 0 && !poison_free);
         // ---- everything that does not depend on the rays is final for EVERY env: done, condition bits, counters.
         //      Stores of all lanes of the warp -> full sectors (a listed env only lacks its obstacle-avoidance term: its
         //      reward word is provisional here and rewritten by the ray launch together with the running return)
@@ -406,28 +444,30 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
             }
         }
     }
-    // ---- warp-aggregated appends to the two work lists
+    // ---- warp-aggregated appends to the work lists
     {
-        const unsigned lm = __ballot_sync(0xffffffffu, listed), em = __ballot_sync(0xffffffffu, ended);
-        if (lm) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&p.view_count[0], (unsigned)__popc(lm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (listed) {
-                const unsigned k = base + __popc(lm & ((1u << lane) - 1u));
-                p.view_list[k] = (unsigned long long)(uint32_t)(i - p.env_begin) | ((unsigned long long)(info & 0xffffu) << 32) |
-                                 ((unsigned long long)cond << 48);
-            }
+        int cls = 0;
+        if (listed) {
+            const int pc = __popc(info & 0xffffu);
+            cls = (p.tpe_rays && pc >= 1 && pc <= 2 && poison_free) ? pc : 3;
         }
-        if (em) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&p.view_count[1], (unsigned)__popc(em));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (ended) {
-                const unsigned k = base + __popc(em & ((1u << lane) - 1u));
-                p.ended_list[k] = (uint32_t)(i - p.env_begin);
-            }
-        }
+        const unsigned long long entry = (unsigned long long)(uint32_t)(i - p.env_begin) | ((unsigned long long)(info & 0xffffu) << 32) |
+                                         ((unsigned long long)cond << 48);
+        // the four appends of a warp (three view classes, ended list) reserve their slots with ONE atomic instruction: lane c
+        // adds the warp's count to counter c, so the four round trips overlap (as four dependent atomics they were 15 % of
+        // this launch's stall samples)
+        const unsigned m1 = __ballot_sync(0xffffffffu, cls == 1), m2 = __ballot_sync(0xffffffffu, cls == 2);
+        const unsigned m3 = __ballot_sync(0xffffffffu, cls == 3), m4 = __ballot_sync(0xffffffffu, ended);
+        const unsigned mine = lane == 0 ? m1 : (lane == 1 ? m2 : (lane == 2 ? m3 : (lane == 3 ? m4 : 0u)));
+        unsigned base = 0;
+        if (mine) base = atomicAdd(&p.view_count[lane], (unsigned)__popc(mine));
+        const unsigned b1 = __shfl_sync(0xffffffffu, base, 0), b2 = __shfl_sync(0xffffffffu, base, 1);
+        const unsigned b3 = __shfl_sync(0xffffffffu, base, 2), b4 = __shfl_sync(0xffffffffu, base, 3);
+        const unsigned below = (1u << lane) - 1u;
+        if (cls == 1) p.view_list[b1 + __popc(m1 & below)] = entry;
+        else if (cls == 2) p.view_list[p.n_envs + b2 + __popc(m2 & below)] = entry;
+        else if (cls == 3) p.view_list[2 * p.n_envs + b3 + __popc(m3 & below)] = entry;
+        if (ended) p.ended_list[b4 + __popc(m4 & below)] = (uint32_t)(i - p.env_begin);
     }
     bs.flush_direct(p.stats, threadIdx.x == 0 ? (int)min((int64_t)kCullThreads, p.env_end - i0) : 0);
 }
@@ -468,18 +508,19 @@ __device__ __forceinline__ void cp_async_word(unsigned dst_shared, const T *src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// the loop of ONE warp over the class-3 list: warp w_global of n_warps (called by all 32 lanes; smem_raw = the CTA's
+// dynamic shared memory, kRayWarps * RaysSmem::warp_words words)
 template <typename T, int RPL>
-__global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWarps) rays_finish_kernel(const __grid_constant__ KParams<T> p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void rays_warp_loop(const KParams<T> &p, unsigned char *smem_raw, unsigned w_global, unsigned n_warps) {
     const RaysSmem<T, RPL> L(p.n_rays);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T *s_warp = reinterpret_cast<T *>(smem_raw) + warp * L.warp_words;
     T *s_pre = s_warp + L.pre_off;
     T *s_ray = s_warp + L.ray_off;
     const int64_t N = p.n_envs;
-    const unsigned count = p.view_count[0];
-    const unsigned n_warps = gridDim.x * kRayWarps;
-    unsigned idx = blockIdx.x * kRayWarps + warp;
+    const unsigned count = p.view_count[2];
+    const unsigned long long *list = p.view_list + 2 * p.n_envs;
+    unsigned idx = w_global;
     if (idx >= count) return;
 
     const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
@@ -514,8 +555,8 @@ __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWa
                 if (c < obst_words) cp_async_word<T>(sa_obst + boff + c * (unsigned)sizeof(T), g + (int64_t)c * N);
         }
     };
-    uint64_t cur = p.view_list[idx];
-    uint64_t nxt = (idx + n_warps < count) ? p.view_list[idx + n_warps] : 0;
+    uint64_t cur = list[idx];
+    uint64_t nxt = (idx + n_warps < count) ? list[idx + n_warps] : 0;
     fetch(cur, 0);
     double stat_acc = 0.0;       // lane k < DOCKAUV_STAT_ENV_STEPS accumulates statistic k of the episodes this warp ended
     int buf = 0;
@@ -529,7 +570,7 @@ __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWa
         //      iteration ago, before that iteration's closing __syncwarp)
         cp_async_wait_all();
         __syncwarp();
-        const uint64_t nn = (idx + 2 * n_warps < count) ? p.view_list[idx + 2 * n_warps] : 0;
+        const uint64_t nn = (idx + 2 * n_warps < count) ? list[idx + 2 * n_warps] : 0;
         if (idx + n_warps < count) fetch(nxt, buf ^ 1);
         const T pos[3] = {s_ent[16], s_ent[17], s_ent[18]};
         if (lane < n_obst && ((mask >> lane) & 1u)) {
@@ -567,7 +608,7 @@ __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWa
             else if (lane == DOCKAUV_STAT_SUM_FINAL_DELTA_D) mine = (double)s_ent[REC_DD];
             else if (lane == DOCKAUV_STAT_NAN_ENVS) mine = (reward != reward) ? 1.0 : 0.0;
             stat_acc += mine;
-            if (lane == 0) p.ended_list[atomicAdd(&p.view_count[1], 1u)] = (uint32_t)cur;
+            if (lane == 0) p.ended_list[atomicAdd(&p.view_count[3], 1u)] = (uint32_t)cur;
         }
         __syncwarp();
         cur = nxt;
@@ -575,6 +616,178 @@ __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWa
     }
     if (lane < DOCKAUV_STAT_ENV_STEPS && stat_acc != 0.0)
         atomicAdd(&p.stats[(blockIdx.x & (DOCKAUV_STAT_COPIES - 1)) * DOCKAUV_N_STATS + lane], stat_acc);
+}
+
+// the warp-per-env ray launch on its own (radars the thread mapping does not cover: every listed env is class 3)
+template <typename T, int RPL>
+__global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWarps) rays_finish_kernel(const __grid_constant__ KParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    rays_warp_loop<T, RPL>(p, smem_raw, blockIdx.x * kRayWarps + (threadIdx.x >> 5), gridDim.x * kRayWarps);
+}
+
+// ------------------------------------------------------------------------------------------------------- 3b. rays, thread per env
+// The envs with exactly one or two obstacles in view -- nine in ten of the listed ones -- with LANES = ENVS: every lane
+// walks over the rays of its own env (SPLIT lanes share one env, each takes a contiguous run of pooled cells), the
+// ray-test records of its obstacles stay in registers.  Against the warp-per-env mapping, everything that is per-env
+// scalar work there (list entry, record fetch, Rzyx, obstacle records, reward: ~450 of its ~600 warp instructions per env,
+// done by 32 lanes redundantly) is amortised over the envs of a warp here.  The ray tests are straight-line code
+// (cast_capsule_bf; spheres take the same path as degenerate capsules, so lanes never diverge on the obstacle type) and
+// the four rays of a pooled cell are independent chains the compiler interleaves.  The body-frame ray table is walked in
+// pooled-cell order (shared memory), so a cell's maximum is complete after four rays and goes straight into the
+// observation row.  One persistent launch covers both classes: tiles of class 2 (the longer ones) first, then class 1.
+constexpr int kTpeThreads = 128;
+constexpr int kTpeMaxCells = 64;      // pooled cells the shared ray table holds
+
+template <typename T, int NOB, int SPLIT>
+__device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s_tab, unsigned tile, unsigned count) {
+    const int64_t N = p.n_envs;
+    const int n_rr = p.n_rr;
+    const unsigned tg = tile * kTpeThreads + threadIdx.x;
+    const unsigned eidx = tg / SPLIT;
+    const int part = (int)(tg % SPLIT);
+    const bool valid = eidx < count;
+    const unsigned long long entry = valid ? p.view_list[(int64_t)(NOB - 1) * N + eidx] : 0ull;
+    const int64_t ie = p.env_begin + (int64_t)(uint32_t)entry;
+    unsigned mask = (unsigned)(entry >> 32) & 0xffffu;
+    const uint32_t cond = (uint32_t)(entry >> 48) & 31u;
+    const T *rec = p.rec + ie * kRecWords;
+    // ---- pose and the ray-test records of the in-view obstacles (registers)
+    T R[9], w[NOB][11];
+    bool sph[NOB];
+    {
+        T trig[6], pos[3];
+        RecIO<T>::template load<0, 3>(rec, trig);
+#pragma unroll
+        for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + ie];
+        rzyx<T>(trig[0], trig[1], trig[2], trig[3], trig[4], trig[5], R);
+#pragma unroll
+        for (int o = 0; o < NOB; o++) {
+            const int k = mask ? __ffs(mask) - 1 : 0;
+            mask &= mask - 1;
+            const bool is_cap = k < p.n_caps;
+            sph[o] = !is_cap;
+            const T *g = is_cap ? p.capsules + (int64_t)(k * 7) * N + ie : p.spheres + (int64_t)((k - p.n_caps) * 4) * N + ie;
+            T ob[7];
+#pragma unroll
+            for (int c = 0; c < 7; c++) ob[c] = (c < 4 || is_cap) ? g[(int64_t)c * N] : T(0);
+#pragma unroll
+            for (int c = 0; c < 11; c++) w[o][c] = T(0);
+            obstacle_ray_record<T>(pos, ob, is_cap, w[o]);
+            if (!is_cap) sphere_as_capsule<T>(w[o]);
+        }
+    }
+    // ---- this lane's run of pooled cells: multiples of four, so the row is written in 16-byte pieces
+    const int cpp = (((n_rr + SPLIT - 1) / SPLIT) + 3) & ~3;
+    const int c_begin = part * cpp;
+    const T dmax = p.radar_max_dist, inv_dmax = T(1) / dmax;
+    float *orow = p.obs + ie * p.n_obs + 16;
+    const bool vec_row = (p.n_obs & 3) == 0 && (n_rr & 3) == 0;
+    T oa_part = T(0);
+    float o4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    // (every lane runs all cpp trips: cast_capsule_bf contains a warp vote; cells beyond the grid are computed and dropped)
+#pragma unroll 1
+    for (int cc = 0; cc < cpp; cc++) {
+        const bool live = c_begin + cc < n_rr;
+        const int cell = live ? c_begin + cc : 0;
+        T dq[4], bwq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const T *tb = s_tab + 4 * (4 * cell + q);
+            const T b0 = tb[0], b1 = tb[1], b2 = tb[2];
+            bwq[q] = tb[3];
+            T rd[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) rd[c] = R[3 * c] * b0 + R[3 * c + 1] * b1 + R[3 * c + 2] * b2;
+            T best = Mth<T>::inf();
+#pragma unroll
+            for (int o = 0; o < NOB; o++) {
+                const T ba[3] = {w[o][0], w[o][1], w[o][2]}, oa[3] = {w[o][3], w[o][4], w[o][5]};
+                best = cast_capsule_bf<T>(rd, ba, oa, w[o][6], w[o][7], w[o][8], w[o][9], w[o][10], sph[o], best);
+            }
+            dq[q] = best > dmax ? dmax : best;        // clamp (sensor.py:117)
+        }
+        T mx = T(0);                                  // block_reduce pads with cval = 0 (sensor.py:131-137)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (bwq[q] < T(0) || !live) continue;     // padding slot of the ray table: no ray
+            // obstacle-avoidance partial sum (docking3d.py:767-792), 2x2 max-pool
+            const T x = dq[q] * inv_dmax;
+            const T qq = x * x;
+            const T mq = !(qq <= T(0.001)) ? qq : T(0.001);     // np.maximum, NaN propagates
+            oa_part += mq * bwq[q];
+            mx = !(dq[q] <= mx) ? dq[q] : mx;         // np.max, NaN propagates
+        }
+        T o = mx * inv_dmax;                          // clip(d / max_dist, 0, 1), docking3d.py:487
+        o = o > T(1) ? T(1) : o;
+        if (vec_row) {
+            o4[cell & 3] = (float)o;
+            if ((cell & 3) == 3 && valid && live) reinterpret_cast<float4 *>(orow)[cell >> 2] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        } else if (valid && live) {
+            orow[cell] = (float)o;
+        }
+    }
+    // ---- the env's obstacle-avoidance sum: add up the SPLIT lanes of the env
+    T oa_dot = oa_part;
+#pragma unroll
+    for (int s = 1; s < SPLIT; s <<= 1) oa_dot += __shfl_xor_sync(0xffffffffu, oa_dot, s);
+    if (valid && part == 0) {
+        // ---- what the cull launch left open: the reward with its obstacle-avoidance term and the running return
+        T wf[6];
+        RecIO<T>::template load<4, 3>(rec, wf);       // prel_z, A, B, r7, lp_d, delta_d
+        const T r_oa = p.sum_beta_oa / oa_dot - T(1);      // docking3d.py:792
+        const T reward = step_reward<T>(p, wf[1], wf[2], wf[3], wf[4], r_oa, cond);
+        const T ep_ret = p.ep_return[ie] + reward;
+        const bool done = cond != 0;
+        p.reward[ie] = reward;
+        if (done && p.ep_return_out) p.ep_return_out[ie] = ep_ret;
+        if (!(done && p.auto_reset)) p.ep_return[ie] = ep_ret;
+        if (done) {      // ~1 % of the listed envs
+            WarpStats bs;
+            bs.done = true;
+            bs.cond = cond;
+            bs.length = p.t_steps[ie];                // already incremented by the cull launch
+            bs.ep_return = (double)ep_ret;
+            bs.delta_d = (double)wf[5];
+            bs.nan = reward != reward;
+            bs.flush_direct(p.stats, 0);
+            p.ended_list[atomicAdd(&p.view_count[3], 1u)] = (uint32_t)entry;
+        }
+    }
+}
+
+// One launch for all three classes: the first `warp_ctas` CTAs run the warp-per-env loop over class 3 (few entries, each a
+// long latency chain: started first, they run alongside the tiles instead of as a launch of their own that leaves the GPU
+// 60 % idle for 11 us), the others are the persistent tile loop of classes 2 and 1.
+template <typename T, int SPLIT, int RPL>
+__global__ void __launch_bounds__(kTpeThreads, DOCKAUV_MINB_TPE) rays_thread_kernel(const __grid_constant__ KParams<T> p, unsigned warp_ctas) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(16) T s_tab[kTpeMaxCells * 4 * 4];      // slot = 4 * cell + q: rb[3], bw; bw < 0 marks zero padding
+    static_assert(kTpeThreads == kRayWarps * 32, "the two ray mappings share one CTA shape");
+    if (blockIdx.x < warp_ctas) {
+        rays_warp_loop<T, RPL>(p, smem_raw, blockIdx.x * kRayWarps + (threadIdx.x >> 5), warp_ctas * kRayWarps);
+        return;
+    }
+    const unsigned bid = blockIdx.x - warp_ctas, n_ctas = gridDim.x - warp_ctas;
+    const unsigned c1 = p.view_count[0], c2 = p.view_count[1];
+    constexpr unsigned per_tile = kTpeThreads / SPLIT;
+    const unsigned t2 = (c2 + per_tile - 1) / per_tile, t1 = (c1 + per_tile - 1) / per_tile;
+    if (bid >= t1 + t2) return;
+    const int n_rr = p.n_rr, n_r = p.n_rays;
+    for (int t = threadIdx.x; t < 4 * n_rr; t += kTpeThreads) {
+        const int cell = t >> 2, q = t & 3;
+        const int pr = cell / p.n_hr, pcol = cell - pr * p.n_hr;
+        const int rv = 2 * pr + (q >> 1), rh = 2 * pcol + (q & 1);
+        const bool ok = rv < p.n_vert && rh < p.n_horiz;
+        const int ir = ok ? rv * p.n_horiz + rh : 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) s_tab[4 * t + c] = ok ? p.ray_tab[c * n_r + ir] : T(0);
+        s_tab[4 * t + 3] = ok ? p.ray_tab[3 * n_r + ir] : T(-1);
+    }
+    __syncthreads();
+    for (unsigned tile = bid; tile < t1 + t2; tile += n_ctas) {
+        if (tile < t2) rays_thread_tile<T, 2, SPLIT>(p, s_tab, tile, c2);
+        else rays_thread_tile<T, 1, SPLIT>(p, s_tab, tile - t2, c1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------- 4. episode end
@@ -587,7 +800,7 @@ __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWa
 // eight LANES per env: the roles serialise inside the warp, same 70 us.
 template <typename T>
 __global__ void __launch_bounds__(kResetCta) episode_end_kernel(const __grid_constant__ KParams<T> p) {
-    const unsigned n_ended = p.view_count[1];
+    const unsigned n_ended = p.view_count[3];
     const int n_obs = p.n_obs;
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     // every thread of a CTA runs the same number of trips (reset_envs_cta has a barrier)
@@ -662,21 +875,46 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     if (e != cudaSuccess) return e;
     mark();
     if (has_obstacles) {
-        cull_finish_kernel<T><<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, 0, st>>>(kc);
+        {
+            const int csmem = (DOCKAUV_CULL_STAGE && !k.cull_exact) ? k.n_obsf * kCullThreads * 16 : 0;
+            auto ckern = cull_finish_kernel<T>;
+            if (csmem > 48 * 1024 && (e = cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem)) != cudaSuccess) return e;
+            ckern<<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, csmem, st>>>(kc);
+        }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         mark();
         const int smem = kRayWarps * (k.n_rays <= 64 ? RaysSmem<T, 2>(k.n_rays).warp_words : RaysSmem<T, 8>(k.n_rays).warp_words) * (int)sizeof(T);
-        int64_t blocks = (int64_t)(k.sm_count > 0 ? k.sm_count : 148) * (DOCKAUV_RAY_CTAS_PER_SM * 4 / kRayWarps);
-        const int64_t most = (n + kRayWarps - 1) / kRayWarps;
-        if (blocks > most) blocks = most;
-        if (k.n_rays <= 64) {
-            auto kern = rays_finish_kernel<T, 2>;
-            if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-            kern<<<(unsigned)blocks, kRayWarps * 32, smem, st>>>(kc);
+        const int64_t sms = k.sm_count > 0 ? k.sm_count : 148;
+        if (k.tpe_rays) {
+            // ---- rays: one launch; thread per env for the envs with one or two obstacles in view (persistent grid over tiles
+            //      of 128 lanes; the counts are only known on the device), warp per env for the rest on its first CTAs
+            int64_t tb = (n * DOCKAUV_TPE_SPLIT + kTpeThreads - 1) / kTpeThreads;      // tiles if every env were listed
+            if (tb > sms * DOCKAUV_TPE_CTAS_PER_SM) tb = sms * DOCKAUV_TPE_CTAS_PER_SM;
+            int64_t wb = (n + kRayWarps - 1) / kRayWarps;
+            if (wb > sms * DOCKAUV_TPE_WARP_CTAS_PER_SM) wb = sms * DOCKAUV_TPE_WARP_CTAS_PER_SM;
+            if (k.n_rays <= 64) {
+                auto kern = rays_thread_kernel<T, DOCKAUV_TPE_SPLIT, 2>;
+                if (smem > 40 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+                kern<<<(unsigned)(wb + tb), kTpeThreads, smem, st>>>(kc, (unsigned)wb);
+            } else {
+                auto kern = rays_thread_kernel<T, DOCKAUV_TPE_SPLIT, 8>;
+                if (smem > 40 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+                kern<<<(unsigned)(wb + tb), kTpeThreads, smem, st>>>(kc, (unsigned)wb);
+            }
         } else {
-            auto kern = rays_finish_kernel<T, 8>;
-            if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-            kern<<<(unsigned)blocks, kRayWarps * 32, smem, st>>>(kc);
+            // ---- rays: warp per env for every listed env (persistent grid)
+            int64_t blocks = sms * (DOCKAUV_RAY_CTAS_PER_SM * 4 / kRayWarps);
+            const int64_t most = (n + kRayWarps - 1) / kRayWarps;
+            if (blocks > most) blocks = most;
+            if (k.n_rays <= 64) {
+                auto kern = rays_finish_kernel<T, 2>;
+                if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+                kern<<<(unsigned)blocks, kRayWarps * 32, smem, st>>>(kc);
+            } else {
+                auto kern = rays_finish_kernel<T, 8>;
+                if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+                kern<<<(unsigned)blocks, kRayWarps * 32, smem, st>>>(kc);
+            }
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         mark();

@@ -73,7 +73,7 @@ __device__ __forceinline__ void dyn_outputs(const KParams<T> &p, const T pos[3],
     const T sphi = tr1[0], cphi = tr1[1], sth = tr1[2], cth = tr1[3], spsi = tr1[4], cpsi = tr1[5];
     const T *nu = y + 3;
     {
-        T inv_cth = T(1) / cth, tth = sth * inv_cth;
+        T inv_cth = Mth<T>::rcp_(cth), tth = sth * inv_cth;
         T qs = sphi * nu[4] + cphi * nu[5];
         q.ed[0] = nu[3] + tth * qs;
         q.ed[1] = cphi * nu[4] - sphi * nu[5];
@@ -93,8 +93,8 @@ __device__ __forceinline__ void dyn_outputs(const KParams<T> &p, const T pos[3],
 
     // ---- observe (docking3d.py:462-488), entries 0..15
     T *o = q.o;
-    T lg = Mth<T>::log_(delta_d / p.max_dist_from_goal);
-    o[0] = clipv(T(1) - lg / p.log_den_obs, T(0), T(1));
+    T lg = Mth<T>::log_(delta_d * p.inv_max_dist_from_goal);
+    o[0] = clipv(T(1) - lg * p.inv_log_den_obs, T(0), T(1));
     o[1] = clipv(delta_theta * Mth<T>::inv_half_pi, T(-1), T(1));
     o[2] = clipv(delta_psi * Mth<T>::inv_pi, T(-1), T(1));
     o[3] = clipv(nu[0] * p.inv_u_max, T(-1), T(1));
@@ -124,7 +124,7 @@ __device__ __forceinline__ void dyn_outputs(const KParams<T> &p, const T pos[3],
     {
         // log_precision(delta_d, tol, max): shares the logarithm with obs[0] unless the epsilon guard bites
         T lgr = (delta_d < T(0.001)) ? log_cold<T>(T(0.001) / p.max_dist_from_goal) : lg;
-        lp_d = T(1) - clipv(lgr / p.log_den_rew, T(0), T(1));
+        lp_d = T(1) - clipv(lgr * p.inv_log_den_rew, T(0), T(1));
     }
     r[0] = -p.w_d * lp_d;
     if (p.reward_set == 1) {

@@ -20,6 +20,7 @@ from bench import kernel_source_hash  # noqa: E402
 
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 NAMES = (("dynamics_kernel", "dynamics"), ("cull_finish_kernel", "cull_finish"), ("rays_finish_kernel", "rays_finish"),
+         ("rays_thread_kernel", "rays_finish"),
          ("episode_end_kernel", "episode_end"))
 
 
