@@ -334,7 +334,7 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         const int n_obsf = 2 * p->n_capsules + p->n_spheres;
         const size_t off_rec = 0, off_obsf = off_rec + 16 * esz * n, off_list = off_obsf + 16 * (size_t)n_obsf * n;
         const size_t off_end = off_list + 3 * 8 * n, off_cnt = off_end + 4 * ((n + 1) & ~(size_t)1);      // three view lists
-        const size_t n_cnt = 4 * (n / 128 + 2);      // four list counters per concurrently stepped env range
+        const size_t n_cnt = 5 * (n / 128 + 2);      // four list counters + one tile-ticket counter per concurrently stepped env range
         cudaError_t e5 = cudaMalloc(&h->pipe_buf, off_cnt + 4 * n_cnt);
         if (e5 == cudaSuccess) e5 = cudaMemset(h->pipe_buf, 0, off_cnt + 4 * n_cnt);
         if (e5 != cudaSuccess) {
@@ -352,6 +352,7 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         h->kd.view_list = h->kf.view_list = (unsigned long long *)(base + off_list);
         h->kd.ended_list = h->kf.ended_list = (uint32_t *)(base + off_end);
         h->kd.view_count = h->kf.view_count = (unsigned int *)(base + off_cnt);
+        h->kd.tile_count = h->kf.tile_count = h->kd.view_count + 4 * (n / 128 + 2);
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         h->kd.sm_count = h->kf.sm_count = sms;

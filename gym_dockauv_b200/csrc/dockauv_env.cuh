@@ -237,17 +237,26 @@ template <typename T, int NU>
 __device__ __forceinline__ T command_and_penalty(const KParams<T> &p, int64_t i, T u[NU]) {
     const int64_t N = p.n_envs;
     T pen;
+    // every load of this function is issued before the first use: the float32 division below has a slow-path branch per
+    // actuator, loads are not moved across it, and with the loads inside the loop a thread paid NU memory round trips
+    // one after the other (ncu: 5 % of the dynamics launch's stall samples on these six waits)
+    T upv[NU];
+#pragma unroll
+    for (int k = 0; k < NU; k++) upv[k] = p.u_prev[(int64_t)k * N + i];
     if (p.act_f32) {
         const float *a = (const float *)p.actions + i * NU;
+        float av[NU];
+#pragma unroll
+        for (int k = 0; k < NU; k++) av[k] = a[k];
         float pen32 = 0.0f;
         double pen64 = 0.0;
 #pragma unroll
         for (int k = 0; k < NU; k++) {
-            float ak = a[k];
+            float ak = av[k];
             float c = ak < -1.0f ? -1.0f : (ak > 1.0f ? 1.0f : ak);
             float frac = (c + 1.0f) / 2.0f;                       // numpy keeps this in float32
             T x = p.u_lo[k] + p.u_span[k] * (T)frac;
-            T up = p.u_prev[(int64_t)k * N + i];
+            T up = upv[k];
             u[k] = p.lp_alpha * x + (T(1) - p.lp_alpha) * up;
             // numpy evaluates (|a| / n_u) ** 2 * w and the sum in float32 with one rounding per operation:
             // explicit _rn intrinsics keep the compiler from contracting them into FMAs
@@ -259,13 +268,16 @@ __device__ __forceinline__ T command_and_penalty(const KParams<T> &p, int64_t i,
         pen = p.action_factor_is_scalar ? (T)pen32 : (T)pen64;
     } else {
         const double *a = (const double *)p.actions + i * NU;
+        double av[NU];
+#pragma unroll
+        for (int k = 0; k < NU; k++) av[k] = a[k];
         T s = T(0);
 #pragma unroll
         for (int k = 0; k < NU; k++) {
-            T ak = (T)a[k];
+            T ak = (T)av[k];
             T frac = (clipv(ak, T(-1), T(1)) + T(1)) / T(2);
             T x = p.u_lo[k] + p.u_span[k] * frac;
-            T up = p.u_prev[(int64_t)k * N + i];
+            T up = upv[k];
             u[k] = p.lp_alpha * x + (T(1) - p.lp_alpha) * up;
             T q = Mth<T>::abs_(ak) / T(NU);
             s += (q * q) * p.arf[k];

@@ -54,6 +54,12 @@ constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #ifndef DOCKAUV_CULL_PREFETCH
 #define DOCKAUV_CULL_PREFETCH 1     // (without staging) L2 prefetch of the records
 #endif
+#ifndef DOCKAUV_DYN_PARK
+#define DOCKAUV_DYN_PARK 1          // the words the dynamics launch needs only after the integration wait in shared memory (cp.async)
+#endif
+#ifndef DOCKAUV_CULL_PARK
+#define DOCKAUV_CULL_PARK 1         // the words the cull launch needs only after its obstacle loop wait in shared memory (cp.async) instead of on the stack
+#endif
 #ifndef DOCKAUV_MINB_RAYS
 #define DOCKAUV_MINB_RAYS 6         // ray launch: (128, 6) = 80 registers, 24 warps per SM
 #endif
@@ -112,6 +118,14 @@ struct RecIO<float> {
     }
 };
 
+// one word global -> shared without a register in between (completion: cp_async_wait_all); dst = shared-window address
+template <typename T>
+__device__ __forceinline__ void cp_async_word(unsigned dst_shared, const T *src) {
+    if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_shared), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------------- finish helpers
 // is_done (docking3d.py:597-631): the five condition bits once the collision flag is known; t_steps is the counter before
 // its increment (:612 is evaluated pre-increment, so max_timesteps = 1000 ends an episode at step 1001)
@@ -139,21 +153,37 @@ __device__ __forceinline__ T step_reward(const KParams<T> &p, T A, T B, T r7, T 
 // CUR: the ocean current is evaluated (scenario with a current, injected current or noise); SPM: sparse M_inv;
 // FIN: the scenario has no obstacles -- every ray reads max_dist and nothing can collide, so the env is finished right
 // here (reward, done, counters, statistics, all-ones ray cells; no record, no cull / ray launch).
-template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN>
-__global__ void
-#ifdef DOCKAUV_DYN_MAXNREG
-__maxnreg__(DOCKAUV_DYN_MAXNREG)
-#else
-__launch_bounds__(kDynThreads, DOCKAUV_MINB_A)
-#endif
-dynamics_kernel(const __grid_constant__ KParams<T> p) {
-    const int64_t N = p.n_envs;
-    const int64_t i = p.env_begin + (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
-    // the cull launch appends to a list: this launch empties it
-    if (p.view_count != nullptr && blockIdx.x == 0 && threadIdx.x < kListCounters) p.view_count[threadIdx.x] = 0u;
-    prefetch_dynamics_inputs<T, NU>(p, i, threadIdx.x & 31, true);
-    if (i >= p.env_end) return;
+// one env of the dynamics launch.  steps_here (FIN only): env-steps this call accounts for in the statistics (the callers
+// pass a count from one lane per CTA / warp, 0 from the others)
+template <typename T, int NU, bool CUR, bool FIN>
+__device__ __forceinline__ void prefetch_tile_inputs(const KParams<T> &p, int64_t j, int lane);
 
+#ifndef DOCKAUV_DYN_PF_LATE
+#define DOCKAUV_DYN_PF_LATE 1       // persistent form: the next tile's inputs are prefetched after the integration (1) / at the top of the trip (0)
+#endif
+
+// j_next: the env this lane works on next (persistent form; < 0: none) -- its inputs are prefetched after the integration
+template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN>
+__device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t i, const int steps_here, const int64_t j_next = -1) {
+    const int64_t N = p.n_envs;
+#if DOCKAUV_DYN_PARK
+    // what is only needed after the integration (position, goal; FIN: step counter, running return) travels global -> shared
+    // by cp.async into this thread's own slots, [word][thread]: no register during the integration and no memory round trip
+    // after it (as late plain loads they were 3 % of this launch's stall samples, and a second round trip for FIN)
+    __shared__ __align__(8) T dyn_park[(FIN ? 8 : 6) * kDynThreads];
+    {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dyn_park + threadIdx.x);
+        constexpr unsigned kPlane = kDynThreads * (unsigned)sizeof(T);
+#pragma unroll
+        for (int c = 0; c < 3; c++) cp_async_word<T>(sa + c * kPlane, p.state + (int64_t)c * N + i);
+#pragma unroll
+        for (int c = 0; c < 3; c++) cp_async_word<T>(sa + (3 + c) * kPlane, p.goal + (int64_t)c * N + i);
+        if (FIN) {
+            cp_async_word<T>(sa + 6 * kPlane, p.ep_return + i);
+            cp_async_word<int32_t>(sa + 7 * kPlane, p.t_steps + i);
+        }
+    }
+#endif
     T y[9];
 #pragma unroll
     for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
@@ -191,15 +221,28 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
 #else
     rkf45_step<T, VEH, SPM, CUR>(p, y, tr0, tau, nu_c, pacc, tr1);
 #endif
+#if DOCKAUV_DYN_PF_LATE
+    // a lead of 0.2 .. 4 us is what works for these prefetches (measured: lines requested a whole integration ahead, ~14 us,
+    // are gone again when the loads come); what follows here takes ~3 us
+    if (j_next >= 0) prefetch_tile_inputs<T, NU, CUR, FIN>(p, j_next, threadIdx.x & 31);
+#endif
 #pragma unroll
     for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
     // position and goal are only needed from here on (their lines were prefetched into L2 by an earlier CTA): loading
     // them now keeps twelve registers free during the integration
     T pos[3], goal[3];
+#if DOCKAUV_DYN_PARK
+    cp_async_wait_all();
+#pragma unroll
+    for (int c = 0; c < 3; c++) pos[c] = dyn_park[c * kDynThreads + threadIdx.x];
+#pragma unroll
+    for (int c = 0; c < 3; c++) goal[c] = dyn_park[(3 + c) * kDynThreads + threadIdx.x];
+#else
 #pragma unroll
     for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
 #pragma unroll
     for (int c = 0; c < 3; c++) goal[c] = p.goal[(int64_t)c * N + i];
+#endif
 #pragma unroll
     for (int c = 0; c < 3; c++) pos[c] += pacc[c];
 #pragma unroll
@@ -232,13 +275,19 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
         } else {
             for (int c = 0; c < p.n_rr; c++) cells[c] = 1.0f;
         }
+#if DOCKAUV_DYN_PARK
+        const int32_t t_steps = reinterpret_cast<const int32_t *>(dyn_park + 7 * kDynThreads + threadIdx.x)[0];
+        const T ep_before = dyn_park[6 * kDynThreads + threadIdx.x];
+#else
         const int32_t t_steps = p.t_steps[i];
+        const T ep_before = p.ep_return[i];
+#endif
         const uint32_t cond = done_conditions<T>(p, q.cond, t_steps, false);
         const bool done = cond != 0;
         const int32_t t_new = t_steps + 1;
         const T r_oa = p.sum_beta_oa / p.sum_beta_oa - T(1);
         const T reward = step_reward<T>(p, A, B, q.r[7], q.r[6], r_oa, cond);
-        const T ep_ret = p.ep_return[i] + reward;
+        const T ep_ret = ep_before + reward;
         p.reward[i] = reward;
         p.done[i] = done ? 1 : 0;
         if (p.cond_bits) p.cond_bits[i] = (uint8_t)cond;
@@ -269,8 +318,7 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
                 if (done) p.ended_list[base + __popc(em & ((1u << lane) - 1u))] = (uint32_t)(i - p.env_begin);
             }
         }
-        const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kDynThreads;
-        bs.flush_direct(p.stats, threadIdx.x == 0 ? (int)min((int64_t)kDynThreads, p.env_end - i0) : 0);
+        bs.flush_direct(p.stats, steps_here);
         return;
     }
     T w[kRecWords];
@@ -290,12 +338,120 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
     RecIO<T>::store(p.rec + i * kRecWords, w);
 }
 
+#ifndef DOCKAUV_DYN_PERSIST
+#define DOCKAUV_DYN_PERSIST 0       // 1: persistent grid, every WARP draws tiles of 32 envs from a counter (see below); 0: one CTA per 128 envs
+#endif
+#ifndef DOCKAUV_DYN_TICKETS
+#define DOCKAUV_DYN_TICKETS 1       // persistent form: 1 = tiles drawn from the counter, 0 = static striding
+#endif
+#ifndef DOCKAUV_DYN_PF
+#define DOCKAUV_DYN_PF 3            // persistent form: the next tile's inputs are prefetched into 1 = L2, 2 = L1, 3 = both
+#endif
+
+// what one env of the dynamics launch reads, prefetched for env j (all 32 lanes call it with consecutive j: two lines per word)
+template <typename T, int NU, bool CUR, bool FIN>
+__device__ __forceinline__ void prefetch_tile_inputs(const KParams<T> &p, int64_t j, int lane) {
+    const int64_t N = p.n_envs;
+    auto pf = [](const void *a) {
+#if DOCKAUV_DYN_PF & 1
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+#endif
+#if DOCKAUV_DYN_PF & 2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+#endif
+    };
+#pragma unroll
+    for (int c = 0; c < 12; c++) pf(p.state + (int64_t)c * N + j);
+#pragma unroll
+    for (int c = 0; c < NU; c++) pf(p.u_prev + (int64_t)c * N + j);
+#pragma unroll
+    for (int c = 0; c < 3; c++) pf(p.goal + (int64_t)c * N + j);
+    if ((lane & 3) == 0) pf((const char *)p.actions + (p.act_f32 ? 4 : 8) * NU * j);
+    if (CUR) {
+#pragma unroll
+        for (int c = 0; c < 5; c++) pf(p.current + (int64_t)c * N + j);
+        if (p.noise) pf(p.noise + j);
+    }
+    if (FIN && (lane & 7) == 0) pf(p.t_steps + j);
+    if (FIN && (lane & 15) == 0) pf(p.ep_return + j);
+}
+
+// Persistent form (default): the grid is what is resident (148 SMs x 4 CTAs x 4 warps) and every WARP walks over tiles of
+// 32 consecutive envs -- the first one by its position in the grid, the following ones drawn from a counter (tile_count,
+// zeroed again by the episode-end launch).  The ticket for the next tile is drawn BEFORE the current one is integrated and
+// that tile's inputs are prefetched right away, a whole integration (~14 us) ahead: a third of a dynamics warp's lifetime
+// used to be the wait for its own first loads and the drain of its stores at exit (ncu: long_scoreboard 27 % + drain 6 %
+// of the stall samples at 16 warps per SM); in the loop the stores of one tile drain under the next one.
+template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN>
+__global__ void
+#ifdef DOCKAUV_DYN_MAXNREG
+__maxnreg__(DOCKAUV_DYN_MAXNREG)
+#else
+__launch_bounds__(kDynThreads, DOCKAUV_MINB_A)
+#endif
+dynamics_kernel(const __grid_constant__ KParams<T> p) {
+    // the cull launch appends to a list: this launch empties it
+    if (p.view_count != nullptr && blockIdx.x == 0 && threadIdx.x < kListCounters) p.view_count[threadIdx.x] = 0u;
+#if DOCKAUV_DYN_PERSIST
+    constexpr int kWarps = kDynThreads / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = p.env_end - p.env_begin;
+    const unsigned n_tiles = (unsigned)((n + 31) >> 5), n_static = gridDim.x * kWarps;
+    unsigned tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    int steps_acc = 0;
+#ifdef DOCKAUV_DYN_STAGGER_NS
+    // tuning: warps of an SM start out of phase (CTAs land on SMs round robin: resident slot = CTA / SMs)
+    __nanosleep((unsigned)(((blockIdx.x / (unsigned)p.sm_count) * kWarps + (threadIdx.x >> 5)) * DOCKAUV_DYN_STAGGER_NS));
+#endif
+#if DOCKAUV_DYN_TICKETS == 0
+    // static striding (tuning)
+    while (tile < n_tiles) {
+        const unsigned nxt = tile + n_static;
+#else
+    // the ticket drawn at the top of one trip is consumed at its end: the atomic's round trip hides under the integration
+    unsigned nxt = 0;
+    if (lane == 0) nxt = atomicAdd(p.tile_count, 1u);
+    nxt = __shfl_sync(0xffffffffu, nxt, 0) + n_static;
+    while (tile < n_tiles) {
+        unsigned after = 0;
+        if (lane == 0) after = atomicAdd(p.tile_count, 1u);
+#endif
+        const int64_t i = p.env_begin + (int64_t)tile * 32 + lane;
+        int64_t j = -1;
+        if (nxt < n_tiles) {
+            j = p.env_begin + (int64_t)nxt * 32 + lane;
+            if (j >= p.env_end) j = -1;
+        }
+#if !DOCKAUV_DYN_PF_LATE
+        if (j >= 0) prefetch_tile_inputs<T, NU, CUR, FIN>(p, j, lane);
+#endif
+        if (i < p.env_end) dynamics_env<T, VEH, NU, CUR, SPM, FIN>(p, i, 0, j);
+        if (FIN) steps_acc += (int)min((int64_t)32, p.env_end - (i - lane));
+        tile = nxt;
+#if DOCKAUV_DYN_TICKETS != 0
+        nxt = __shfl_sync(0xffffffffu, after, 0) + n_static;
+#endif
+    }
+    if (FIN && lane == 0 && steps_acc > 0)
+        atomicAdd(&p.stats[(blockIdx.x & (DOCKAUV_STAT_COPIES - 1)) * DOCKAUV_N_STATS + DOCKAUV_STAT_ENV_STEPS], (double)steps_acc);
+#else
+    const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kDynThreads;
+    const int64_t i = i0 + threadIdx.x;
+    prefetch_dynamics_inputs<T, NU>(p, i, threadIdx.x & 31, true);
+    if (i >= p.env_end) return;
+    dynamics_env<T, VEH, NU, CUR, SPM, FIN>(p, i, threadIdx.x == 0 ? (int)min((int64_t)kDynThreads, p.env_end - i0) : 0);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------------- 2. cull + finish
 constexpr int kCullThreads = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_kernel(const __grid_constant__ KParams<T> p) {
     extern __shared__ __align__(16) unsigned char cull_smem[];      // float4 [n_obsf][kCullThreads] when the records are staged
+#if DOCKAUV_CULL_PARK
+    __shared__ __align__(16) unsigned char cull_park[4 * kCullThreads * 16];     // four 16-byte slots per thread, [slot][thread]
+#endif
     const int64_t N = p.n_envs;
     const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kCullThreads;
     const int64_t i = i0 + threadIdx.x;
@@ -324,14 +480,38 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
         if (!p.cull_exact)
             for (int sl = 0; sl < p.n_obsf; sl++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obsf + (int64_t)sl * N + i));
 #endif
-        // everything this thread reads besides the obstacle records, requested up front
-        T w[10], wc[2], wf[4];
+        // everything this thread reads besides the obstacle records, requested up front.  What is only needed after the
+        // obstacle loop (reward terms, condition / poison words, running return, step counter) travels global -> shared
+        // by cp.async into the thread's own slots: no register, no wait here.  As plain loads these values were spilled to
+        // the stack under the 64-register cap, the spill stores waited for the loads (13 % of this launch's stall samples)
+        // and the reloads after the loop for lines that had left L1 again (another 15 %)
+        T w[10];
         RecIO<T>::template load<0, 5>(rec, w);       // trig, prel, A
+#if DOCKAUV_CULL_PARK
+        {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(cull_park) + (unsigned)threadIdx.x * 16u;
+            constexpr unsigned kPlane = kCullThreads * 16u;
+            if (sizeof(T) == 8) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(rec + 10) : "memory");              // B, r7
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + kPlane), "l"(rec + 12) : "memory");     // lp_d, delta_d
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 2 * kPlane), "l"(rec + 14) : "memory"); // cond, poison
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 3 * kPlane), "l"(p.ep_return + i) : "memory");
+            } else {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(rec + 8) : "memory");               // prel_z.. (8, 9), B, r7
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + kPlane), "l"(rec + 12) : "memory");     // lp_d, delta_d, cond, poison
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + 3 * kPlane), "l"(p.ep_return + i) : "memory");
+            }
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + 3 * kPlane + 8u), "l"(p.t_steps + i) : "memory");
+        }
+        const T A = w[REC_A];
+#else
+        T wc[2], wf[4];
         RecIO<T>::template load<7, 1>(rec, wc);      // cond, poison
         RecIO<T>::template load<5, 2>(rec, wf);      // B, r7, lp_d, delta_d
         const int32_t t_steps = p.t_steps[i];
         const T ep_return = p.ep_return[i];
-        const T A = w[REC_A], poison = wc[1];
+        const T A = w[REC_A];
+#endif
         if (n_obst > 0 && !p.cull_exact) {
             // ---- float culls + collision pre-test (cull_pair_rec)
             float Rf[9], prel[3];
@@ -399,6 +579,30 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
                 info |= hit ? (1u << 16) : 0u;
             }
         }
+#if DOCKAUV_CULL_PARK
+        // ---- the parked words (this thread's own slots: no barrier)
+        T wc[2], wf[4], ep_return;
+        int32_t t_steps;
+        {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            const unsigned char *sp = cull_park + threadIdx.x * 16;
+            constexpr int kPlane = kCullThreads * 16;
+            if (sizeof(T) == 8) {
+                const double2 a = *reinterpret_cast<const double2 *>(sp), b = *reinterpret_cast<const double2 *>(sp + kPlane);
+                const double2 c = *reinterpret_cast<const double2 *>(sp + 2 * kPlane);
+                wf[0] = (T)a.x; wf[1] = (T)a.y; wf[2] = (T)b.x; wf[3] = (T)b.y;
+                wc[0] = (T)c.x; wc[1] = (T)c.y;
+                ep_return = (T)*reinterpret_cast<const double *>(sp + 3 * kPlane);
+            } else {
+                const float4 a = *reinterpret_cast<const float4 *>(sp), b = *reinterpret_cast<const float4 *>(sp + kPlane);
+                wf[0] = (T)a.z; wf[1] = (T)a.w; wf[2] = (T)b.x; wf[3] = (T)b.y;
+                wc[0] = (T)b.z; wc[1] = (T)b.w;
+                ep_return = (T)*reinterpret_cast<const float *>(sp + 3 * kPlane);
+            }
+            t_steps = *reinterpret_cast<const int32_t *>(sp + 3 * kPlane + 8);
+        }
+#endif
+        const T poison = wc[1];
         // a non-finite pose poisons the rays like the reference's NaN propagation: such envs go through the ray launch
         // (without obstacles every ray reads max_dist whatever the pose, docking3d.py:441)
         poison_free = poison == T(0);
@@ -500,13 +704,6 @@ struct RaysSmem {
 #endif
 constexpr int kRayWarps = DOCKAUV_RAY_WARPS;     // warps per CTA of the ray launch
 
-// one word global -> shared without a register in between (completion: cp_async_wait_all); dst = shared-window address
-template <typename T>
-__device__ __forceinline__ void cp_async_word(unsigned dst_shared, const T *src) {
-    if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_shared), "l"(src) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // the loop of ONE warp over the class-3 list: warp w_global of n_warps (called by all 32 lanes; smem_raw = the CTA's
 // dynamic shared memory, kRayWarps * RaysSmem::warp_words words)
@@ -734,9 +931,10 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
         // ---- what the cull launch left open: the reward with its obstacle-avoidance term and the running return
         T wf[6];
         RecIO<T>::template load<4, 3>(rec, wf);       // prel_z, A, B, r7, lp_d, delta_d
+        const T ep_before = p.ep_return[ie];
         const T r_oa = p.sum_beta_oa / oa_dot - T(1);      // docking3d.py:792
         const T reward = step_reward<T>(p, wf[1], wf[2], wf[3], wf[4], r_oa, cond);
-        const T ep_ret = p.ep_return[ie] + reward;
+        const T ep_ret = ep_before + reward;
         const bool done = cond != 0;
         p.reward[ie] = reward;
         if (done && p.ep_return_out) p.ep_return_out[ie] = ep_ret;
@@ -801,6 +999,7 @@ __global__ void __launch_bounds__(kTpeThreads, DOCKAUV_MINB_TPE) rays_thread_ker
 template <typename T>
 __global__ void __launch_bounds__(kResetCta) episode_end_kernel(const __grid_constant__ KParams<T> p) {
     const unsigned n_ended = p.view_count[3];
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.tile_count[0] = 0u;      // tickets of the next dynamics launch over this range
     const int n_obs = p.n_obs;
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     // every thread of a CTA runs the same number of trips (reset_envs_cta has a barrier)
@@ -861,6 +1060,7 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     const int64_t n = k.env_end - k.env_begin;
     KParams<T> kc = k;
     kc.view_count = k.view_count + kListCounters * (k.env_begin / kWarpEnvs);   // counters per concurrently stepped env range
+    kc.tile_count = k.tile_count + (k.env_begin / kWarpEnvs);
     kc.view_list = k.view_list + k.env_begin;
     kc.ended_list = k.ended_list + k.env_begin;
     int n_mark = 0;
@@ -869,7 +1069,13 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     };
     mark();
     const bool has_obstacles = k.n_caps + k.n_sph > 0;
-    const unsigned dyn_blocks = (unsigned)((n + kDynThreads - 1) / kDynThreads);
+    unsigned dyn_blocks = (unsigned)((n + kDynThreads - 1) / kDynThreads);
+#if DOCKAUV_DYN_PERSIST
+    {   // persistent grid: what is resident
+        const unsigned resident = (unsigned)(k.sm_count > 0 ? k.sm_count : 148) * DOCKAUV_MINB_A;
+        if (dyn_blocks > resident) dyn_blocks = resident;
+    }
+#endif
     // scenarios without obstacles are finished by the dynamics launch itself: no cull, no rays
     cudaError_t e = has_obstacles ? launch_dynamics<T, VEH, NU, false>(kc, dyn_blocks, st) : launch_dynamics<T, VEH, NU, true>(kc, dyn_blocks, st);
     if (e != cudaSuccess) return e;
