@@ -238,6 +238,11 @@ static void fill_kparams(const DockauvParams &s, int64_t n_envs, KParams<T> &k) 
             const bool allowed = r == c || (r == 0 && c == 4) || (r == 4 && c == 0) || (r == 1 && c == 3) || (r == 3 && c == 1);
             if (!allowed && s.M_inv[6 * r + c] != 0.0) sparse = false;
         }
+    // ... and the same structure in C(nu) and G(eta): r_G and the buoyancy lever on the z axis, I_b diagonal
+    if (s.r_G[0] != 0.0 || s.r_G[1] != 0.0 || s.G_r[0] != 0.0 || s.G_r[1] != 0.0) sparse = false;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++)
+            if (r != c && s.I_b[3 * r + c] != 0.0) sparse = false;
 #ifdef DOCKAUV_FORCE_DENSE_MINV      // tuning builds
     sparse = false;
 #endif
@@ -334,7 +339,7 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         const int n_obsf = 2 * p->n_capsules + p->n_spheres;
         const size_t off_rec = 0, off_obsf = off_rec + 16 * esz * n, off_list = off_obsf + 16 * (size_t)n_obsf * n;
         const size_t off_end = off_list + 3 * 8 * n, off_cnt = off_end + 4 * ((n + 1) & ~(size_t)1);      // three view lists
-        const size_t n_cnt = 5 * (n / 128 + 2);      // four list counters + one tile-ticket counter per concurrently stepped env range
+        const size_t n_cnt = 16 * (n / 128 + 2);     // counter block (kCounterStride words) per concurrently stepped env range
         cudaError_t e5 = cudaMalloc(&h->pipe_buf, off_cnt + 4 * n_cnt);
         if (e5 == cudaSuccess) e5 = cudaMemset(h->pipe_buf, 0, off_cnt + 4 * n_cnt);
         if (e5 != cudaSuccess) {
@@ -352,7 +357,6 @@ extern "C" int dockauv_create(const DockauvParams *p, int64_t n_envs, int device
         h->kd.view_list = h->kf.view_list = (unsigned long long *)(base + off_list);
         h->kd.ended_list = h->kf.ended_list = (uint32_t *)(base + off_end);
         h->kd.view_count = h->kf.view_count = (unsigned int *)(base + off_cnt);
-        h->kd.tile_count = h->kf.tile_count = h->kd.view_count + 4 * (n / 128 + 2);
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         h->kd.sm_count = h->kf.sm_count = sms;
@@ -494,7 +498,7 @@ static int step_range(DockauvHandle *h, const void *actions, int action_dtype, c
     const bool staged = dbg == nullptr;   // else: the fused kernel
     if (layout == DOCKAUV_LAYOUT_PIPELINE && staged) {
         const int64_t chunk = h->kd.chunk_envs > 0 ? h->kd.chunk_envs : (end - begin);
-        h->launches += ((h->params.n_capsules + h->params.n_spheres) > 0 ? 4 : 2) * ((end - begin + chunk - 1) / chunk);
+        h->launches += (int64_t)dockauv::pipe_launches(h->kd) * ((end - begin + chunk - 1) / chunk);
     } else {
         h->launches += 1;
     }
@@ -991,12 +995,12 @@ extern "C" int dockauv_last_list_counts(DockauvHandle *h, int64_t *n_listed, int
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     // one counter pair per env range the most recent step call stepped (halves of the batch, chunks of step_host)
-    const size_t n_cnt = 4 * ((size_t)h->n_envs / 128 + 2);
+    const size_t n_cnt = 16 * ((size_t)h->n_envs / 128 + 2);
     std::vector<unsigned int> host(n_cnt);
     CUDA_TRY(cudaMemcpyAsync(host.data(), h->kd.view_count, n_cnt * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int64_t b : h->last_begins) {
-        const size_t k = 4 * (size_t)(b / 128);
+        const size_t k = 16 * (size_t)(b / 128) + 4;      // words 4..7 of a counter block: the values at the end of the step
         if (k + 3 < n_cnt) {
             *n_listed += (int64_t)host[k] + host[k + 1] + host[k + 2];
             *n_ended += host[k + 3];

@@ -139,18 +139,22 @@ __device__ __forceinline__ T ssa(T x) {
 }
 
 // sin / cos of (a + d) from (sin a, cos a) by angle addition.  The Runge-Kutta stage angles and the post-step
-// attitude are small shifts of the pre-step attitude (d = h * sum(a_ij k_j), |d| ~ h |Theta_dot|), so for
-// |d| <= 0.5 sin d and cos d - 1 are short Taylor polynomials (truncation < 5e-17 relative) instead of a library
-// sincos (~150 instructions with its range reduction); larger shifts and NaN / inf take the library call.
-// The result differs from sincos(a + d) by ~1 ulp, three orders of magnitude inside the 1e-9 budget.
+// attitude are small shifts of the pre-step attitude (d = h * sum(a_ij k_j), |d| ~ h |Theta_dot|), so sin d and
+// cos d - 1 are short Taylor polynomials instead of a library sincos (~150 instructions with its range reduction).
+// Two tiers: |d| <= 1/4 (attitude rates up to 2.5 rad/s at h = 0.1: every env of the C4 workload in steady state, where
+// one env in four exceeds 1.25 rad/s) inline with sin through d^11 (truncation < 1e-17 relative) and cos - 1 through d^12
+// (< 5e-20); anything else out of line: the round-1 polynomials for |d| <= 1/2 (sin through d^13, cos - 1 through d^14,
+// < 5e-17), the library call beyond that and for NaN / inf.  The result differs from sincos(a + d) by ~1 ulp, three
+// orders of magnitude inside the 1e-9 budget.
 // Taylor coefficients of sin d / d - 1 and cos d - 1 in d^2, in constant memory: a 64-bit literal costs two UMOVs in
 // front of every DFMA that uses it, a constant-bank word one load (or none)
 __constant__ double kTaylorSin[6] = {1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0};
 __constant__ double kTaylorCos[7] = {-1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0,
                                      1.0 / 24.0, -0.5};
 
+// second tier (cold): sin d and cos d - 1 for |d| > 1/4
 template <typename T>
-__device__ __forceinline__ void sincos_shift(T s0, T c0, T d, T *s, T *c) {
+static __device__ __noinline__ void sincos_shift_wide(T d, T *sd_out, T *cm1_out) {
     T sd, cm1;
     if (Mth<T>::abs_(d) <= T(0.5)) {
         const T d2 = d * d;
@@ -166,6 +170,26 @@ __device__ __forceinline__ void sincos_shift(T s0, T c0, T d, T *s, T *c) {
         T cd;
         Mth<T>::sincos_(d, &sd, &cd);
         cm1 = cd - T(1);
+    }
+    *sd_out = sd;
+    *cm1_out = cm1;
+}
+
+template <typename T>
+__device__ __forceinline__ void sincos_shift(T s0, T c0, T d, T *s, T *c) {
+    T sd, cm1;
+    if (Mth<T>::abs_(d) <= T(0.25)) {
+        const T d2 = d * d;
+        T ps = (T)kTaylorSin[1];
+#pragma unroll
+        for (int k = 2; k < 6; k++) ps = ps * d2 + (T)kTaylorSin[k];
+        sd = (d * d2) * ps + d;
+        T pc = (T)kTaylorCos[1];
+#pragma unroll
+        for (int k = 2; k < 7; k++) pc = pc * d2 + (T)kTaylorCos[k];
+        cm1 = d2 * pc;
+    } else {
+        sincos_shift_wide<T>(d, &sd, &cm1);
     }
     *s = s0 + (s0 * cm1 + c0 * sd);
     *c = c0 + (c0 * cm1 - s0 * sd);
@@ -272,11 +296,24 @@ __device__ __forceinline__ void nu_dot(const KParams<T> &p, const T nu[6], const
     {
         T c1[3], rgn2[3], t[3], rgc1[3], ibn2[3], t2[3];
         cross3(n2, n1, c1);                 // nu2 x nu1
-        cross3(p.r_G, n2, rgn2);            // r_G x nu2
-        cross3(n2, rgn2, t);                // nu2 x (r_G x nu2)
-        cross3(p.r_G, c1, rgc1);            // r_G x (nu2 x nu1)
+        if (SPM) {
+            // centre of gravity on the z axis and a diagonal I_b (what SPM stands for, checked on the host): the products
+            // with the exact zeros of r_G and I_b are left out.  Every term that remains is rounded exactly as in the
+            // general form (x * y - 0 * w and 0 * w + x * y are x * y), so finite results are identical bit for bit; a
+            // non-finite velocity still makes some f[i] non-finite through D(nu) nu and the poison term below does the rest
+            const T zg = p.r_G[2];
+            rgn2[0] = -(zg * n2[1]); rgn2[1] = zg * n2[0]; rgn2[2] = T(0);             // r_G x nu2
+            t[0] = -Mth<T>::mul_(n2[2], rgn2[1]); t[1] = Mth<T>::mul_(n2[2], rgn2[0]);  // nu2 x (r_G x nu2); never fused into c1 - t
+            t[2] = n2[0] * rgn2[1] - n2[1] * rgn2[0];
+            rgc1[0] = -(zg * c1[1]); rgc1[1] = zg * c1[0]; rgc1[2] = T(0);             // r_G x (nu2 x nu1)
+            ibn2[0] = p.I_b[0] * n2[0]; ibn2[1] = p.I_b[4] * n2[1]; ibn2[2] = p.I_b[8] * n2[2];
+        } else {
+            cross3(p.r_G, n2, rgn2);            // r_G x nu2
+            cross3(n2, rgn2, t);                // nu2 x (r_G x nu2)
+            cross3(p.r_G, c1, rgc1);            // r_G x (nu2 x nu1)
 #pragma unroll
-        for (int i = 0; i < 3; i++) ibn2[i] = p.I_b[3 * i] * n2[0] + p.I_b[3 * i + 1] * n2[1] + p.I_b[3 * i + 2] * n2[2];
+            for (int i = 0; i < 3; i++) ibn2[i] = p.I_b[3 * i] * n2[0] + p.I_b[3 * i + 1] * n2[1] + p.I_b[3 * i + 2] * n2[2];
+        }
         cross3(ibn2, n2, t2);               // (I_b nu2) x nu2
         T a1[3] = {p.MA[0] * n1[0], p.MA[1] * n1[1], p.MA[2] * n1[2]};
         T a2[3] = {p.MA[3] * n2[0], p.MA[4] * n2[1], p.MA[5] * n2[2]};
@@ -296,9 +333,14 @@ __device__ __forceinline__ void nu_dot(const KParams<T> &p, const T nu[6], const
         f[0] -= p.G_WB * sth;
         f[1] -= -p.G_WB * cs;
         f[2] -= -p.G_WB * cc;
-        f[3] -= -p.G_r[1] * cc + p.G_r[2] * cs;
-        f[4] -= p.G_r[2] * sth + p.G_r[0] * cc;
-        f[5] -= -p.G_r[0] * cs - p.G_r[1] * sth;
+        if (SPM) {      // centres of gravity and buoyancy on the z axis: G_r[0] = G_r[1] = 0 (host-checked), same bits as below
+            f[3] -= Mth<T>::mul_(p.G_r[2], cs);
+            f[4] -= Mth<T>::mul_(p.G_r[2], sth);
+        } else {
+            f[3] -= -p.G_r[1] * cc + p.G_r[2] * cs;
+            f[4] -= p.G_r[2] * sth + p.G_r[0] * cc;
+            f[5] -= -p.G_r[0] * cs - p.G_r[1] * sth;
+        }
     }
     if (SPM) {
         // M_inv of a vehicle whose centre of gravity is offset along z only (both stock vehicles): ten non-zeros, the

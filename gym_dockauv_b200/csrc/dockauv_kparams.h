@@ -78,7 +78,6 @@ struct KParams {
     unsigned long long *view_list;
     uint32_t *ended_list;
     unsigned int *view_count;
-    unsigned int *tile_count;        // ticket counter of the persistent dynamics launch, one per concurrently stepped env range
     int32_t sm_count;
     int32_t sparse_minv;             // M_inv has only the z_G pattern (diagonal + [0,4] [4,0] [1,3] [3,1]) filled in
     T *delta_d_out;

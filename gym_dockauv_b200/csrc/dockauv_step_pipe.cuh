@@ -48,17 +48,14 @@ constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #ifndef DOCKAUV_TPE_SPLIT
 #define DOCKAUV_TPE_SPLIT 1         // lanes per env in the thread-per-env ray launch (each takes a run of pooled cells; 2: +8 %, 4: +11 % time)
 #endif
-#ifndef DOCKAUV_CULL_STAGE
-#define DOCKAUV_CULL_STAGE 0        // 1: all obstacle records of an env staged into shared memory by cp.async (measured: cull 125 vs 123 us, step 0.500 vs 0.487 ms: 53 KB of shared memory per CTA cost more than the loop's L2 hits)
-#endif
 #ifndef DOCKAUV_CULL_PREFETCH
 #define DOCKAUV_CULL_PREFETCH 1     // (without staging) L2 prefetch of the records
 #endif
-#ifndef DOCKAUV_DYN_PARK
-#define DOCKAUV_DYN_PARK 1          // the words the dynamics launch needs only after the integration wait in shared memory (cp.async)
+#ifndef DOCKAUV_TPE_PF1
+#define DOCKAUV_TPE_PF1 0
 #endif
-#ifndef DOCKAUV_CULL_PARK
-#define DOCKAUV_CULL_PARK 1         // the words the cull launch needs only after its obstacle loop wait in shared memory (cp.async) instead of on the stack
+#ifndef DOCKAUV_TPE_BODY
+#define DOCKAUV_TPE_BODY 1          // thread-per-env ray tiles: obstacle records rotated into the body frame once instead of every ray into NED
 #endif
 #ifndef DOCKAUV_MINB_RAYS
 #define DOCKAUV_MINB_RAYS 6         // ray launch: (128, 6) = 80 registers, 24 warps per SM
@@ -67,7 +64,10 @@ constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #define DOCKAUV_RAY_CTAS_PER_SM DOCKAUV_MINB_RAYS   // persistent grid of the ray launch, in 4-warp CTAs per SM (= what is resident)
 #endif
 
-constexpr int kListCounters = 4;    // work-list counters per stepped env range: view lists of class 1, 2, 3 and the ended list
+// work-list counters per stepped env range (KParams::view_count): words 0..3 the live counters (view lists of class 1, 2, 3,
+// ended list), 4..7 their values at the end of the most recent step (dockauv_last_list_counts), 8 the ticket of the
+// episode-end launch, whose last CTA saves and zeroes the live counters for the next step
+constexpr int kListCounters = 4, kCounterStride = 16, kCounterLast = 4, kCounterTicket = 8;
 
 // ---- the per-env record written by the dynamics launch
 constexpr int kRecWords = 16;
@@ -150,27 +150,23 @@ __device__ __forceinline__ T step_reward(const KParams<T> &p, T A, T B, T r7, T 
 }
 
 // ------------------------------------------------------------------------------------------------------- 1. dynamics
-// CUR: the ocean current is evaluated (scenario with a current, injected current or noise); SPM: sparse M_inv;
+// CUR: the ocean current is evaluated (scenario with a current, injected current or noise); SPM: sparse M_inv / C / G;
 // FIN: the scenario has no obstacles -- every ray reads max_dist and nothing can collide, so the env is finished right
-// here (reward, done, counters, statistics, all-ones ray cells; no record, no cull / ray launch).
-// one env of the dynamics launch.  steps_here (FIN only): env-steps this call accounts for in the statistics (the callers
-// pass a count from one lane per CTA / warp, 0 from the others)
-template <typename T, int NU, bool CUR, bool FIN>
-__device__ __forceinline__ void prefetch_tile_inputs(const KParams<T> &p, int64_t j, int lane);
+// here (reward, done, counters, statistics, all-ones ray cells; no record, no cull / ray launch);
+// FUSE: the cull + finish code (section 2) runs in this launch, on the record while it is still in registers.
 
-#ifndef DOCKAUV_DYN_PF_LATE
-#define DOCKAUV_DYN_PF_LATE 1       // persistent form: the next tile's inputs are prefetched after the integration (1) / at the top of the trip (0)
-#endif
+// shared memory of one dynamics CTA: park[kParkWords][kDynThreads] words of T that are only needed after the integration
+// (position, goal; FIN / FUSE: running return, step counter), filled by cp.async into the thread's own slots -- no register
+// during the integration and no memory round trip after it
+constexpr int kParkWords = 8;
 
-// j_next: the env this lane works on next (persistent form; < 0: none) -- its inputs are prefetched after the integration
-template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN>
-__device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t i, const int steps_here, const int64_t j_next = -1) {
+// one env of the dynamics launch.  FIN: the env is finished here (steps_here: env-steps this call accounts for in the
+// statistics -- the callers pass the CTA's count from one thread, 0 from the others).  Otherwise the env's record is left
+// in w[kRecWords] and its post-step position in pos[3].
+template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN, bool LATE>
+__device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t i, const int steps_here, T *dyn_park, T w[kRecWords],
+                                             T pos[3]) {
     const int64_t N = p.n_envs;
-#if DOCKAUV_DYN_PARK
-    // what is only needed after the integration (position, goal; FIN: step counter, running return) travels global -> shared
-    // by cp.async into this thread's own slots, [word][thread]: no register during the integration and no memory round trip
-    // after it (as late plain loads they were 3 % of this launch's stall samples, and a second round trip for FIN)
-    __shared__ __align__(8) T dyn_park[(FIN ? 8 : 6) * kDynThreads];
     {
         const unsigned sa = (unsigned)__cvta_generic_to_shared(dyn_park + threadIdx.x);
         constexpr unsigned kPlane = kDynThreads * (unsigned)sizeof(T);
@@ -178,12 +174,11 @@ __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t 
         for (int c = 0; c < 3; c++) cp_async_word<T>(sa + c * kPlane, p.state + (int64_t)c * N + i);
 #pragma unroll
         for (int c = 0; c < 3; c++) cp_async_word<T>(sa + (3 + c) * kPlane, p.goal + (int64_t)c * N + i);
-        if (FIN) {
+        if (LATE) {
             cp_async_word<T>(sa + 6 * kPlane, p.ep_return + i);
             cp_async_word<int32_t>(sa + 7 * kPlane, p.t_steps + i);
         }
     }
-#endif
     T y[9];
 #pragma unroll
     for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
@@ -221,28 +216,15 @@ __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t 
 #else
     rkf45_step<T, VEH, SPM, CUR>(p, y, tr0, tau, nu_c, pacc, tr1);
 #endif
-#if DOCKAUV_DYN_PF_LATE
-    // a lead of 0.2 .. 4 us is what works for these prefetches (measured: lines requested a whole integration ahead, ~14 us,
-    // are gone again when the loads come); what follows here takes ~3 us
-    if (j_next >= 0) prefetch_tile_inputs<T, NU, CUR, FIN>(p, j_next, threadIdx.x & 31);
-#endif
 #pragma unroll
     for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
-    // position and goal are only needed from here on (their lines were prefetched into L2 by an earlier CTA): loading
-    // them now keeps twelve registers free during the integration
-    T pos[3], goal[3];
-#if DOCKAUV_DYN_PARK
+    // position and goal are only needed from here on: they have been waiting in shared memory
+    T goal[3];
     cp_async_wait_all();
 #pragma unroll
     for (int c = 0; c < 3; c++) pos[c] = dyn_park[c * kDynThreads + threadIdx.x];
 #pragma unroll
     for (int c = 0; c < 3; c++) goal[c] = dyn_park[(3 + c) * kDynThreads + threadIdx.x];
-#else
-#pragma unroll
-    for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
-#pragma unroll
-    for (int c = 0; c < 3; c++) goal[c] = p.goal[(int64_t)c * N + i];
-#endif
 #pragma unroll
     for (int c = 0; c < 3; c++) pos[c] += pacc[c];
 #pragma unroll
@@ -275,13 +257,8 @@ __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t 
         } else {
             for (int c = 0; c < p.n_rr; c++) cells[c] = 1.0f;
         }
-#if DOCKAUV_DYN_PARK
         const int32_t t_steps = reinterpret_cast<const int32_t *>(dyn_park + 7 * kDynThreads + threadIdx.x)[0];
         const T ep_before = dyn_park[6 * kDynThreads + threadIdx.x];
-#else
-        const int32_t t_steps = p.t_steps[i];
-        const T ep_before = p.ep_return[i];
-#endif
         const uint32_t cond = done_conditions<T>(p, q.cond, t_steps, false);
         const bool done = cond != 0;
         const int32_t t_new = t_steps + 1;
@@ -321,7 +298,6 @@ __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t 
         bs.flush_direct(p.stats, steps_here);
         return;
     }
-    T w[kRecWords];
 #pragma unroll
     for (int c = 0; c < 6; c++) w[REC_TRIG + c] = tr1[c];
 #pragma unroll
@@ -335,127 +311,27 @@ __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t 
     // 0 for a finite pose, NaN otherwise: added to every ray distance so that a blown-up state poisons the radar
     // outputs exactly like the reference's NaN propagation does
     w[REC_POISON] = (((pos[0] + pos[1]) + (pos[2] + y[0])) + (y[1] + y[2])) * T(0);
-    RecIO<T>::store(p.rec + i * kRecWords, w);
-}
-
-#ifndef DOCKAUV_DYN_PERSIST
-#define DOCKAUV_DYN_PERSIST 0       // 1: persistent grid, every WARP draws tiles of 32 envs from a counter (see below); 0: one CTA per 128 envs
-#endif
-#ifndef DOCKAUV_DYN_TICKETS
-#define DOCKAUV_DYN_TICKETS 1       // persistent form: 1 = tiles drawn from the counter, 0 = static striding
-#endif
-#ifndef DOCKAUV_DYN_PF
-#define DOCKAUV_DYN_PF 3            // persistent form: the next tile's inputs are prefetched into 1 = L2, 2 = L1, 3 = both
-#endif
-
-// what one env of the dynamics launch reads, prefetched for env j (all 32 lanes call it with consecutive j: two lines per word)
-template <typename T, int NU, bool CUR, bool FIN>
-__device__ __forceinline__ void prefetch_tile_inputs(const KParams<T> &p, int64_t j, int lane) {
-    const int64_t N = p.n_envs;
-    auto pf = [](const void *a) {
-#if DOCKAUV_DYN_PF & 1
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-#endif
-#if DOCKAUV_DYN_PF & 2
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-#endif
-    };
-#pragma unroll
-    for (int c = 0; c < 12; c++) pf(p.state + (int64_t)c * N + j);
-#pragma unroll
-    for (int c = 0; c < NU; c++) pf(p.u_prev + (int64_t)c * N + j);
-#pragma unroll
-    for (int c = 0; c < 3; c++) pf(p.goal + (int64_t)c * N + j);
-    if ((lane & 3) == 0) pf((const char *)p.actions + (p.act_f32 ? 4 : 8) * NU * j);
-    if (CUR) {
-#pragma unroll
-        for (int c = 0; c < 5; c++) pf(p.current + (int64_t)c * N + j);
-        if (p.noise) pf(p.noise + j);
-    }
-    if (FIN && (lane & 7) == 0) pf(p.t_steps + j);
-    if (FIN && (lane & 15) == 0) pf(p.ep_return + j);
-}
-
-// Persistent form (default): the grid is what is resident (148 SMs x 4 CTAs x 4 warps) and every WARP walks over tiles of
-// 32 consecutive envs -- the first one by its position in the grid, the following ones drawn from a counter (tile_count,
-// zeroed again by the episode-end launch).  The ticket for the next tile is drawn BEFORE the current one is integrated and
-// that tile's inputs are prefetched right away, a whole integration (~14 us) ahead: a third of a dynamics warp's lifetime
-// used to be the wait for its own first loads and the drain of its stores at exit (ncu: long_scoreboard 27 % + drain 6 %
-// of the stall samples at 16 warps per SM); in the loop the stores of one tile drain under the next one.
-template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN>
-__global__ void
-#ifdef DOCKAUV_DYN_MAXNREG
-__maxnreg__(DOCKAUV_DYN_MAXNREG)
-#else
-__launch_bounds__(kDynThreads, DOCKAUV_MINB_A)
-#endif
-dynamics_kernel(const __grid_constant__ KParams<T> p) {
-    // the cull launch appends to a list: this launch empties it
-    if (p.view_count != nullptr && blockIdx.x == 0 && threadIdx.x < kListCounters) p.view_count[threadIdx.x] = 0u;
-#if DOCKAUV_DYN_PERSIST
-    constexpr int kWarps = kDynThreads / 32;
-    const int lane = threadIdx.x & 31;
-    const int64_t n = p.env_end - p.env_begin;
-    const unsigned n_tiles = (unsigned)((n + 31) >> 5), n_static = gridDim.x * kWarps;
-    unsigned tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    int steps_acc = 0;
-#ifdef DOCKAUV_DYN_STAGGER_NS
-    // tuning: warps of an SM start out of phase (CTAs land on SMs round robin: resident slot = CTA / SMs)
-    __nanosleep((unsigned)(((blockIdx.x / (unsigned)p.sm_count) * kWarps + (threadIdx.x >> 5)) * DOCKAUV_DYN_STAGGER_NS));
-#endif
-#if DOCKAUV_DYN_TICKETS == 0
-    // static striding (tuning)
-    while (tile < n_tiles) {
-        const unsigned nxt = tile + n_static;
-#else
-    // the ticket drawn at the top of one trip is consumed at its end: the atomic's round trip hides under the integration
-    unsigned nxt = 0;
-    if (lane == 0) nxt = atomicAdd(p.tile_count, 1u);
-    nxt = __shfl_sync(0xffffffffu, nxt, 0) + n_static;
-    while (tile < n_tiles) {
-        unsigned after = 0;
-        if (lane == 0) after = atomicAdd(p.tile_count, 1u);
-#endif
-        const int64_t i = p.env_begin + (int64_t)tile * 32 + lane;
-        int64_t j = -1;
-        if (nxt < n_tiles) {
-            j = p.env_begin + (int64_t)nxt * 32 + lane;
-            if (j >= p.env_end) j = -1;
-        }
-#if !DOCKAUV_DYN_PF_LATE
-        if (j >= 0) prefetch_tile_inputs<T, NU, CUR, FIN>(p, j, lane);
-#endif
-        if (i < p.env_end) dynamics_env<T, VEH, NU, CUR, SPM, FIN>(p, i, 0, j);
-        if (FIN) steps_acc += (int)min((int64_t)32, p.env_end - (i - lane));
-        tile = nxt;
-#if DOCKAUV_DYN_TICKETS != 0
-        nxt = __shfl_sync(0xffffffffu, after, 0) + n_static;
-#endif
-    }
-    if (FIN && lane == 0 && steps_acc > 0)
-        atomicAdd(&p.stats[(blockIdx.x & (DOCKAUV_STAT_COPIES - 1)) * DOCKAUV_N_STATS + DOCKAUV_STAT_ENV_STEPS], (double)steps_acc);
-#else
-    const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kDynThreads;
-    const int64_t i = i0 + threadIdx.x;
-    prefetch_dynamics_inputs<T, NU>(p, i, threadIdx.x & 31, true);
-    if (i >= p.env_end) return;
-    dynamics_env<T, VEH, NU, CUR, SPM, FIN>(p, i, threadIdx.x == 0 ? (int)min((int64_t)kDynThreads, p.env_end - i0) : 0);
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------------- 2. cull + finish
-constexpr int kCullThreads = 256;
-
+// One env through the float culls and everything that can be finished without rays; called by EVERY thread of a CTA of
+// CTA threads (the list appends are warp-collective; `active` = the thread has an env).
+//   trig / prel      sin / cos of the post-step attitude, position relative to the goal (record words 0..8)
+//   fetch(slot)      float obstacle record `slot` of this env (KParams::obsf layout), from wherever the caller keeps it
+//   late()           CullLate: the record words 9..15, running return and step counter -- asked for AFTER the obstacle loop,
+//                    so that a caller that has them in memory does not hold them in registers through the loop
+//   pos_of(q)        post-step position (only for pairs within 2 mm of the collision threshold)
+// Returns whether the env is on a view list (its record must then be in KParams::rec for the ray launch).
 template <typename T>
-__global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_kernel(const __grid_constant__ KParams<T> p) {
-    extern __shared__ __align__(16) unsigned char cull_smem[];      // float4 [n_obsf][kCullThreads] when the records are staged
-#if DOCKAUV_CULL_PARK
-    __shared__ __align__(16) unsigned char cull_park[4 * kCullThreads * 16];     // four 16-byte slots per thread, [slot][thread]
-#endif
+struct CullLate {
+    T A, B, r7, lp_d, delta_d, cond012, poison, ep_return;
+    int32_t t_steps;
+};
+
+template <typename T, int CTA, typename FETCH, typename LATE, typename POS>
+__device__ __forceinline__ bool cull_finish_env(const KParams<T> &p, const int64_t i, const int64_t i0, const bool active,
+                                                const T trig[6], const T prel_T[3], FETCH fetch, LATE late, POS pos_of) {
     const int64_t N = p.n_envs;
-    const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kCullThreads;
-    const int64_t i = i0 + threadIdx.x;
-    const bool active = i < p.env_end;
     const int lane = threadIdx.x & 31;
     WarpStats bs;
     bool listed = false, ended = false;      // ended: episode over and nothing in view -> on the list of the episode-end launch
@@ -463,93 +339,32 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
     uint32_t info = 0;                       // bits 0..15 in-view mask (capsules first), 16 collision
     uint32_t cond = 0;
     if (active) {
-        const T *rec = p.rec + i * kRecWords;
         const int n_caps = p.n_caps, n_sph = p.n_sph, n_obst = n_caps + n_sph;
-        // ---- all float obstacle records of this env on their way into shared memory at once (cp.async, 16 bytes per
-        //      slot, [slot][thread]: conflict-free): the loop below then never waits for HBM.  With one register pair of
-        //      records in flight (round 2's first version) 64 % of this launch's stall samples sat on the loop's loads
-#if DOCKAUV_CULL_STAGE
-        float4 *s_obs = reinterpret_cast<float4 *>(cull_smem) + threadIdx.x;
-        if (!p.cull_exact) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(s_obs);
-            for (int sl = 0; sl < p.n_obsf; sl++)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (unsigned)(sl * kCullThreads * 16)),
-                             "l"(p.obsf + (int64_t)sl * N + i) : "memory");
-        }
-#elif DOCKAUV_CULL_PREFETCH
-        if (!p.cull_exact)
-            for (int sl = 0; sl < p.n_obsf; sl++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obsf + (int64_t)sl * N + i));
-#endif
-        // everything this thread reads besides the obstacle records, requested up front.  What is only needed after the
-        // obstacle loop (reward terms, condition / poison words, running return, step counter) travels global -> shared
-        // by cp.async into the thread's own slots: no register, no wait here.  As plain loads these values were spilled to
-        // the stack under the 64-register cap, the spill stores waited for the loads (13 % of this launch's stall samples)
-        // and the reloads after the loop for lines that had left L1 again (another 15 %)
-        T w[10];
-        RecIO<T>::template load<0, 5>(rec, w);       // trig, prel, A
-#if DOCKAUV_CULL_PARK
-        {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(cull_park) + (unsigned)threadIdx.x * 16u;
-            constexpr unsigned kPlane = kCullThreads * 16u;
-            if (sizeof(T) == 8) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(rec + 10) : "memory");              // B, r7
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + kPlane), "l"(rec + 12) : "memory");     // lp_d, delta_d
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 2 * kPlane), "l"(rec + 14) : "memory"); // cond, poison
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 3 * kPlane), "l"(p.ep_return + i) : "memory");
-            } else {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(rec + 8) : "memory");               // prel_z.. (8, 9), B, r7
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + kPlane), "l"(rec + 12) : "memory");     // lp_d, delta_d, cond, poison
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + 3 * kPlane), "l"(p.ep_return + i) : "memory");
-            }
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + 3 * kPlane + 8u), "l"(p.t_steps + i) : "memory");
-        }
-        const T A = w[REC_A];
-#else
-        T wc[2], wf[4];
-        RecIO<T>::template load<7, 1>(rec, wc);      // cond, poison
-        RecIO<T>::template load<5, 2>(rec, wf);      // B, r7, lp_d, delta_d
-        const int32_t t_steps = p.t_steps[i];
-        const T ep_return = p.ep_return[i];
-        const T A = w[REC_A];
-#endif
         if (n_obst > 0 && !p.cull_exact) {
             // ---- float culls + collision pre-test (cull_pair_rec)
             float Rf[9], prel[3];
-            rzyx<float>((float)w[0], (float)w[1], (float)w[2], (float)w[3], (float)w[4], (float)w[5], Rf);
+            rzyx<float>((float)trig[0], (float)trig[1], (float)trig[2], (float)trig[3], (float)trig[4], (float)trig[5], Rf);
 #pragma unroll
-            for (int c = 0; c < 3; c++) prel[c] = (float)w[REC_PREL + c];
-#if DOCKAUV_CULL_STAGE
-            asm volatile("cp.async.wait_all;" ::: "memory");      // this thread's own records: no barrier needed
-            int slot = 0;
-#pragma unroll 1
-            for (int k = 0; k < n_obst; k++) {
-                const bool is_cap = k < n_caps;
-                const float4 c0 = s_obs[slot * kCullThreads];
-                const float4 c1 = is_cap ? s_obs[(slot + 1) * kCullThreads] : make_float4(0.f, 0.f, 0.f, 0.f);
-                slot += is_cap ? 2 : 1;
-#else
+            for (int c = 0; c < 3; c++) prel[c] = (float)prel_T[c];
             // the next obstacle's record is requested before the current one is evaluated
-            const float4 *ob = p.obsf + i;
-            float4 q0 = ob[0], q1 = n_caps > 0 ? ob[N] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 q0 = fetch(0), q1 = n_caps > 0 ? fetch(1) : make_float4(0.f, 0.f, 0.f, 0.f);
             int slot = n_caps > 0 ? 2 : 1;
 #pragma unroll 1
             for (int k = 0; k < n_obst; k++) {
                 const bool is_cap = k < n_caps;
                 const float4 c0 = q0, c1 = q1;
                 if (k + 1 < n_obst) {
-                    q0 = ob[(int64_t)slot * N];
-                    if (k + 1 < n_caps) q1 = ob[(int64_t)(slot + 1) * N];
+                    q0 = fetch(slot);
+                    if (k + 1 < n_caps) q1 = fetch(slot + 1);
                     slot += (k + 1 < n_caps) ? 2 : 1;
                 }
-#endif
                 int hit3;
                 bool view;
                 cull_pair_rec<T>(p, prel, Rf, c0, c1, is_cap, hit3, view);
                 bool hit = hit3 == 1;
                 if (hit3 == 2) {      // within 2 mm of the collision threshold (or NaN): decided in T like the other layouts
                     T pos[3], o7[7];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
+                    pos_of(pos);
                     const T *g = is_cap ? p.capsules + (int64_t)(k * 7) * N + i : p.spheres + (int64_t)((k - n_caps) * 4) * N + i;
                     const int n_words = is_cap ? 7 : 4;
 #pragma unroll
@@ -562,9 +377,8 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
         } else if (n_obst > 0) {
             // ---- coordinates too large for float records: everything in T (obstacle_pair)
             T Rm[9], pos[3];
-            rzyx<T>(w[0], w[1], w[2], w[3], w[4], w[5], Rm);
-#pragma unroll
-            for (int c = 0; c < 3; c++) pos[c] = p.state[(int64_t)c * N + i];
+            rzyx<T>(trig[0], trig[1], trig[2], trig[3], trig[4], trig[5], Rm);
+            pos_of(pos);
 #pragma unroll 1
             for (int k = 0; k < n_obst; k++) {
                 const bool is_cap = k < n_caps;
@@ -579,46 +393,24 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
                 info |= hit ? (1u << 16) : 0u;
             }
         }
-#if DOCKAUV_CULL_PARK
-        // ---- the parked words (this thread's own slots: no barrier)
-        T wc[2], wf[4], ep_return;
-        int32_t t_steps;
-        {
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            const unsigned char *sp = cull_park + threadIdx.x * 16;
-            constexpr int kPlane = kCullThreads * 16;
-            if (sizeof(T) == 8) {
-                const double2 a = *reinterpret_cast<const double2 *>(sp), b = *reinterpret_cast<const double2 *>(sp + kPlane);
-                const double2 c = *reinterpret_cast<const double2 *>(sp + 2 * kPlane);
-                wf[0] = (T)a.x; wf[1] = (T)a.y; wf[2] = (T)b.x; wf[3] = (T)b.y;
-                wc[0] = (T)c.x; wc[1] = (T)c.y;
-                ep_return = (T)*reinterpret_cast<const double *>(sp + 3 * kPlane);
-            } else {
-                const float4 a = *reinterpret_cast<const float4 *>(sp), b = *reinterpret_cast<const float4 *>(sp + kPlane);
-                wf[0] = (T)a.z; wf[1] = (T)a.w; wf[2] = (T)b.x; wf[3] = (T)b.y;
-                wc[0] = (T)b.z; wc[1] = (T)b.w;
-                ep_return = (T)*reinterpret_cast<const float *>(sp + 3 * kPlane);
-            }
-            t_steps = *reinterpret_cast<const int32_t *>(sp + 3 * kPlane + 8);
-        }
-#endif
-        const T poison = wc[1];
+        const CullLate<T> L = late();
         // a non-finite pose poisons the rays like the reference's NaN propagation: such envs go through the ray launch
         // (without obstacles every ray reads max_dist whatever the pose, docking3d.py:441)
-        poison_free = poison == T(0);
+        poison_free = L.poison == T(0);
         listed = (info & 0xffffu) != 0u || (n_obst > 0 && !poison_free);
         // ---- everything that does not depend on the rays is final for EVERY env: done, condition bits, counters.
         //      Stores of all lanes of the warp -> full sectors (a listed env only lacks its obstacle-avoidance term: its
         //      reward word is provisional here and rewritten by the ray launch together with the running return)
-        cond = done_conditions<T>(p, (uint32_t)wc[0], t_steps, (info >> 16) != 0u);
+        const int32_t t_steps = L.t_steps;
+        cond = done_conditions<T>(p, (uint32_t)L.cond012, t_steps, (info >> 16) != 0u);
         const bool done = cond != 0;
         const int32_t t_new = t_steps + 1;
         const T r_oa = p.sum_beta_oa / p.sum_beta_oa - T(1);      // docking3d.py:792 with every ray at max_dist: exactly 0
-        const T reward = step_reward<T>(p, A, wf[0], wf[1], wf[2], r_oa, cond);
+        const T reward = step_reward<T>(p, L.A, L.B, L.r7, L.lp_d, r_oa, cond);
         p.reward[i] = reward;
         p.done[i] = done ? 1 : 0;
         if (p.cond_bits) p.cond_bits[i] = (uint8_t)cond;
-        if (p.delta_d_out) p.delta_d_out[i] = wf[3];
+        if (p.delta_d_out) p.delta_d_out[i] = L.delta_d;
         if (done && p.ep_len_out) p.ep_len_out[i] = t_new;
         if (listed) {
             p.t_steps[i] = t_new;        // the ray launch reads it back (and zeroes it if it re-initialises the env)
@@ -631,14 +423,14 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
             } else {
                 for (int c = 0; c < p.n_rr; c++) cells[c] = 1.0f;
             }
-            const T ep_ret = ep_return + reward;
+            const T ep_ret = L.ep_return + reward;
             if (done) {
                 if (p.ep_return_out) p.ep_return_out[i] = ep_ret;
                 bs.done = true;
                 bs.cond = cond;
                 bs.length = t_new;
                 bs.ep_return = (double)ep_ret;
-                bs.delta_d = (double)wf[3];
+                bs.delta_d = (double)L.delta_d;
                 bs.nan = reward != reward;      // episodes that ended on a NaN reward
                 ended = true;
             }
@@ -673,7 +465,123 @@ __global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_k
         else if (cls == 3) p.view_list[2 * p.n_envs + b3 + __popc(m3 & below)] = entry;
         if (ended) p.ended_list[b4 + __popc(m4 & below)] = (uint32_t)(i - p.env_begin);
     }
-    bs.flush_direct(p.stats, threadIdx.x == 0 ? (int)min((int64_t)kCullThreads, p.env_end - i0) : 0);
+    bs.flush_direct(p.stats, threadIdx.x == 0 ? (int)min((int64_t)CTA, p.env_end - i0) : 0);
+    return listed;
+}
+
+// ---- the dynamics launch (with the cull + finish code in it when FUSE)
+// FUSE: the env's float obstacle records travel global -> shared by cp.async at the very start ([slot][thread], dynamic
+// shared memory: 16 n_obsf bytes per thread) and wait there through the integration; the record never leaves the registers
+// unless the env ends up on a view list.  Against the separate cull launch this saves the record's round trip through HBM
+// (128 B written for every env, 128 B read back) and every memory wait of the obstacle loop.
+template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN, bool FUSE>
+__global__ void
+#ifdef DOCKAUV_DYN_MAXNREG
+__maxnreg__(DOCKAUV_DYN_MAXNREG)
+#else
+__launch_bounds__(kDynThreads, DOCKAUV_MINB_A)
+#endif
+dynamics_kernel(const __grid_constant__ KParams<T> p) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];      // FUSE: float4 [n_obsf][kDynThreads]
+    __shared__ __align__(8) T dyn_park[kParkWords * kDynThreads];
+    const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kDynThreads;
+    const int64_t i = i0 + threadIdx.x;
+    const bool active = i < p.env_end;
+    prefetch_dynamics_inputs<T, NU>(p, i, threadIdx.x & 31, true);
+    T w[kRecWords], pos[3];
+    if (!FUSE) {
+        if (!active) return;
+        dynamics_env<T, VEH, NU, CUR, SPM, FIN, FIN>(p, i, threadIdx.x == 0 ? (int)min((int64_t)kDynThreads, p.env_end - i0) : 0, dyn_park, w, pos);
+        if (!FIN) RecIO<T>::store(p.rec + i * kRecWords, w);
+        return;
+    }
+    const float4 *s_obs = reinterpret_cast<const float4 *>(dyn_smem) + threadIdx.x;
+    if (active) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(s_obs);
+        for (int sl = 0; sl < p.n_obsf; sl++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (unsigned)(sl * kDynThreads * 16)),
+                         "l"(p.obsf + (int64_t)sl * p.n_envs + i) : "memory");
+        dynamics_env<T, VEH, NU, CUR, SPM, false, true>(p, i, 0, dyn_park, w, pos);      // (its cp.async wait covers the records)
+    }
+    const bool listed = cull_finish_env<T, kDynThreads>(
+        p, i, i0, active, w + REC_TRIG, w + REC_PREL, [&](int sl) { return s_obs[sl * kDynThreads]; },
+        [&]() {
+            CullLate<T> L;
+            L.A = w[REC_A]; L.B = w[REC_B]; L.r7 = w[REC_R7]; L.lp_d = w[REC_LPD]; L.delta_d = w[REC_DD];
+            L.cond012 = w[REC_COND]; L.poison = w[REC_POISON];
+            L.ep_return = dyn_park[6 * kDynThreads + threadIdx.x];
+            L.t_steps = reinterpret_cast<const int32_t *>(dyn_park + 7 * kDynThreads + threadIdx.x)[0];
+            return L;
+        },
+        [&](T q[3]) { q[0] = pos[0]; q[1] = pos[1]; q[2] = pos[2]; });
+    if (listed) RecIO<T>::store(p.rec + i * kRecWords, w);      // the ray launch reads it
+}
+
+// ---- the cull + finish launch on its own (records from KParams::rec; used when the dynamics launch cannot take it in)
+constexpr int kCullThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kCullThreads, DOCKAUV_MINB_CULL) cull_finish_kernel(const __grid_constant__ KParams<T> p) {
+    // the words needed only after the obstacle loop (reward terms, condition / poison words, running return, step counter)
+    // travel global -> shared by cp.async into the thread's own slots, [slot][thread]: no register, no wait up front.  As
+    // plain loads these values were spilled to the stack under the 64-register cap, the spill stores waited for the loads
+    // (13 % of this launch's stall samples) and the reloads after the loop for lines that had left L1 again (another 15 %)
+    __shared__ __align__(16) unsigned char cull_park[4 * kCullThreads * 16];
+    const int64_t N = p.n_envs;
+    const int64_t i0 = p.env_begin + (int64_t)blockIdx.x * kCullThreads;
+    const int64_t i = i0 + threadIdx.x;
+    const bool active = i < p.env_end;
+    const T *rec = p.rec + i * kRecWords;
+    T w[10];
+#pragma unroll
+    for (int c = 0; c < 10; c++) w[c] = T(0);
+    if (active) {
+#if DOCKAUV_CULL_PREFETCH
+        if (!p.cull_exact)
+            for (int sl = 0; sl < p.n_obsf; sl++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obsf + (int64_t)sl * N + i));
+#endif
+        RecIO<T>::template load<0, 5>(rec, w);       // trig, prel, A
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(cull_park) + (unsigned)threadIdx.x * 16u;
+        constexpr unsigned kPlane = kCullThreads * 16u;
+        if (sizeof(T) == 8) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(rec + 10) : "memory");              // B, r7
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + kPlane), "l"(rec + 12) : "memory");     // lp_d, delta_d
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + 2 * kPlane), "l"(rec + 14) : "memory"); // cond, poison
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 3 * kPlane), "l"(p.ep_return + i) : "memory");
+        } else {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(rec + 8) : "memory");               // prel_z, A, B, r7
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + kPlane), "l"(rec + 12) : "memory");     // lp_d, delta_d, cond, poison
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + 3 * kPlane), "l"(p.ep_return + i) : "memory");
+        }
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + 3 * kPlane + 8u), "l"(p.t_steps + i) : "memory");
+    }
+    const T A = w[REC_A];
+    const float4 *ob = p.obsf + i;
+    cull_finish_env<T, kCullThreads>(
+        p, i, i0, active, w + REC_TRIG, w + REC_PREL, [&](int sl) { return ob[(int64_t)sl * N]; },
+        [&]() {
+            CullLate<T> L;
+            cp_async_wait_all();      // this thread's own slots: no barrier
+            const unsigned char *sp = cull_park + threadIdx.x * 16;
+            constexpr int kPlane = kCullThreads * 16;
+            if (sizeof(T) == 8) {
+                const double2 a = *reinterpret_cast<const double2 *>(sp), b = *reinterpret_cast<const double2 *>(sp + kPlane);
+                const double2 c = *reinterpret_cast<const double2 *>(sp + 2 * kPlane);
+                L.B = (T)a.x; L.r7 = (T)a.y; L.lp_d = (T)b.x; L.delta_d = (T)b.y; L.cond012 = (T)c.x; L.poison = (T)c.y;
+                L.ep_return = (T)*reinterpret_cast<const double *>(sp + 3 * kPlane);
+            } else {
+                const float4 a = *reinterpret_cast<const float4 *>(sp), b = *reinterpret_cast<const float4 *>(sp + kPlane);
+                L.B = (T)a.z; L.r7 = (T)a.w; L.lp_d = (T)b.x; L.delta_d = (T)b.y; L.cond012 = (T)b.z; L.poison = (T)b.w;
+                L.ep_return = (T)*reinterpret_cast<const float *>(sp + 3 * kPlane);
+            }
+            L.t_steps = *reinterpret_cast<const int32_t *>(sp + 3 * kPlane + 8);
+            L.A = A;
+            return L;
+        },
+        [&](T q[3]) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) q[c] = p.state[(int64_t)c * N + i];
+        });
 }
 
 // ------------------------------------------------------------------------------------------------------- 3. rays + finish
@@ -848,6 +756,12 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
     unsigned mask = (unsigned)(entry >> 32) & 0xffffu;
     const uint32_t cond = (uint32_t)(entry >> 48) & 31u;
     const T *rec = p.rec + ie * kRecWords;
+#if DOCKAUV_TPE_PF1
+    // the words read after the ray loop (second half of the record, running return): towards L1 now
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 8));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 12));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ep_return + ie));
+#endif
     // ---- pose and the ray-test records of the in-view obstacles (registers)
     T R[9], w[NOB][11];
     bool sph[NOB];
@@ -871,6 +785,16 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
             for (int c = 0; c < 11; c++) w[o][c] = T(0);
             obstacle_ray_record<T>(pos, ob, is_cap, w[o]);
             if (!is_cap) sphere_as_capsule<T>(w[o]);
+#if DOCKAUV_TPE_BODY
+            // the record's two vectors into the BODY frame (R^T v): a ray direction then is its table entry as it stands,
+            // (R b) . v = b . (R^T v) -- 18 products per obstacle instead of 9 per ray
+#pragma unroll
+            for (int v = 0; v < 2; v++) {
+                const T x = w[o][3 * v], y = w[o][3 * v + 1], z = w[o][3 * v + 2];
+#pragma unroll
+                for (int c = 0; c < 3; c++) w[o][3 * v + c] = R[c] * x + R[3 + c] * y + R[6 + c] * z;
+            }
+#endif
         }
     }
     // ---- this lane's run of pooled cells: multiples of four, so the row is written in 16-byte pieces
@@ -893,8 +817,12 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
             const T b0 = tb[0], b1 = tb[1], b2 = tb[2];
             bwq[q] = tb[3];
             T rd[3];
+#if DOCKAUV_TPE_BODY
+            rd[0] = b0; rd[1] = b1; rd[2] = b2;
+#else
 #pragma unroll
             for (int c = 0; c < 3; c++) rd[c] = R[3 * c] * b0 + R[3 * c + 1] * b1 + R[3 * c + 2] * b2;
+#endif
             T best = Mth<T>::inf();
 #pragma unroll
             for (int o = 0; o < NOB; o++) {
@@ -999,7 +927,6 @@ __global__ void __launch_bounds__(kTpeThreads, DOCKAUV_MINB_TPE) rays_thread_ker
 template <typename T>
 __global__ void __launch_bounds__(kResetCta) episode_end_kernel(const __grid_constant__ KParams<T> p) {
     const unsigned n_ended = p.view_count[3];
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.tile_count[0] = 0u;      // tickets of the next dynamics launch over this range
     const int n_obs = p.n_obs;
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     // every thread of a CTA runs the same number of trips (reset_envs_cta has a barrier)
@@ -1027,17 +954,39 @@ __global__ void __launch_bounds__(kResetCta) episode_end_kernel(const __grid_con
         }
         if (p.auto_reset) reset_envs_cta<T>(p, ie, valid);
     }
+    // ---- the last CTA to get here saves the list counters of this step and zeroes them for the next one (every CTA has
+    //      read the ended count and its list entries by now)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&p.view_count[kCounterTicket], 1u) == gridDim.x - 1) {
+#pragma unroll
+            for (int c = 0; c < kListCounters; c++) {
+                p.view_count[kCounterLast + c] = p.view_count[c];
+                p.view_count[c] = 0u;
+            }
+            p.view_count[kCounterTicket] = 0u;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------- launcher
-template <typename T, int VEH, int NU, bool FIN>
+template <typename T, int VEH, int NU, bool FIN, bool FUSE>
 static cudaError_t launch_dynamics(const KParams<T> &k, unsigned blocks, cudaStream_t st) {
     const bool cur = k.has_current != 0, spm = k.sparse_minv != 0;
-    if (cur && spm) dynamics_kernel<T, VEH, NU, true, true, FIN><<<blocks, kDynThreads, 0, st>>>(k);
-    else if (cur) dynamics_kernel<T, VEH, NU, true, false, FIN><<<blocks, kDynThreads, 0, st>>>(k);
-    else if (spm) dynamics_kernel<T, VEH, NU, false, true, FIN><<<blocks, kDynThreads, 0, st>>>(k);
-    else dynamics_kernel<T, VEH, NU, false, false, FIN><<<blocks, kDynThreads, 0, st>>>(k);
-    return cudaGetLastError();
+    const int smem = FUSE ? k.n_obsf * kDynThreads * 16 : 0;
+    auto go = [&](auto kern) {
+        if (smem > 32 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<blocks, kDynThreads, smem, st>>>(k);
+        return cudaGetLastError();
+    };
+    if (cur && spm) return go(dynamics_kernel<T, VEH, NU, true, true, FIN, FUSE>);
+    if (cur) return go(dynamics_kernel<T, VEH, NU, true, false, FIN, FUSE>);
+    if (spm) return go(dynamics_kernel<T, VEH, NU, false, true, FIN, FUSE>);
+    return go(dynamics_kernel<T, VEH, NU, false, false, FIN, FUSE>);
 }
 
 template <typename T, int VEH, int NU>
@@ -1059,8 +1008,7 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     }
     const int64_t n = k.env_end - k.env_begin;
     KParams<T> kc = k;
-    kc.view_count = k.view_count + kListCounters * (k.env_begin / kWarpEnvs);   // counters per concurrently stepped env range
-    kc.tile_count = k.tile_count + (k.env_begin / kWarpEnvs);
+    kc.view_count = k.view_count + kCounterStride * (k.env_begin / kWarpEnvs);   // counters per concurrently stepped env range
     kc.view_list = k.view_list + k.env_begin;
     kc.ended_list = k.ended_list + k.env_begin;
     int n_mark = 0;
@@ -1069,24 +1017,17 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     };
     mark();
     const bool has_obstacles = k.n_caps + k.n_sph > 0;
-    unsigned dyn_blocks = (unsigned)((n + kDynThreads - 1) / kDynThreads);
-#if DOCKAUV_DYN_PERSIST
-    {   // persistent grid: what is resident
-        const unsigned resident = (unsigned)(k.sm_count > 0 ? k.sm_count : 148) * DOCKAUV_MINB_A;
-        if (dyn_blocks > resident) dyn_blocks = resident;
-    }
-#endif
-    // scenarios without obstacles are finished by the dynamics launch itself: no cull, no rays
-    cudaError_t e = has_obstacles ? launch_dynamics<T, VEH, NU, false>(kc, dyn_blocks, st) : launch_dynamics<T, VEH, NU, true>(kc, dyn_blocks, st);
+    const unsigned dyn_blocks = (unsigned)((n + kDynThreads - 1) / kDynThreads);
+    // scenarios without obstacles are finished by the dynamics launch itself (no cull, no rays); with obstacles the cull +
+    // finish code runs inside it whenever the float records of a CTA fit in shared memory
+    const bool fuse = pipe_fuses_cull(k);
+    cudaError_t e = !has_obstacles ? launch_dynamics<T, VEH, NU, true, false>(kc, dyn_blocks, st)
+                    : fuse       ? launch_dynamics<T, VEH, NU, false, true>(kc, dyn_blocks, st)
+                                 : launch_dynamics<T, VEH, NU, false, false>(kc, dyn_blocks, st);
     if (e != cudaSuccess) return e;
     mark();
     if (has_obstacles) {
-        {
-            const int csmem = (DOCKAUV_CULL_STAGE && !k.cull_exact) ? k.n_obsf * kCullThreads * 16 : 0;
-            auto ckern = cull_finish_kernel<T>;
-            if (csmem > 48 * 1024 && (e = cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem)) != cudaSuccess) return e;
-            ckern<<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, csmem, st>>>(kc);
-        }
+        if (!fuse) cull_finish_kernel<T><<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, 0, st>>>(kc);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         mark();
         const int smem = kRayWarps * (k.n_rays <= 64 ? RaysSmem<T, 2>(k.n_rays).warp_words : RaysSmem<T, 8>(k.n_rays).warp_words) * (int)sizeof(T);

@@ -388,7 +388,7 @@ def test_step_in_parts_equals_one_launch_group():
     assert torch.equal(es[0].state, es[1].state) and torch.equal(es[0].episode, es[1].episode)
     s0, s1 = es[0].get_stats(), es[1].get_stats()
     assert s0["env_steps"] == s1["env_steps"] == 12 * n and s0["episodes"] == s1["episodes"]
-    assert es[0].launch_count() - es[1].launch_count() == 12 * 4      # 8 launches per step against 4
+    assert es[0].launch_count() - es[1].launch_count() == 12 * 3      # 6 launches per step against 3 (dynamics + cull, rays, episode end)
     for e in es:
         e.close()
 
