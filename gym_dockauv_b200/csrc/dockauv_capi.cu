@@ -1000,7 +1000,8 @@ extern "C" int dockauv_last_list_counts(DockauvHandle *h, int64_t *n_listed, int
     CUDA_TRY(cudaMemcpyAsync(host.data(), h->kd.view_count, n_cnt * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int64_t b : h->last_begins) {
-        const size_t k = 16 * (size_t)(b / 128) + 4;      // words 4..7 of a counter block: the values at the end of the step
+        // fused cull: words 4..7 of a counter block hold the values at the end of the step (0..3 are zero again); else 0..3
+        const size_t k = 16 * (size_t)(b / 128) + (pipe_fuses_cull(h->kd) ? 4 : 0);
         if (k + 3 < n_cnt) {
             *n_listed += (int64_t)host[k] + host[k + 1] + host[k + 2];
             *n_ended += host[k + 3];

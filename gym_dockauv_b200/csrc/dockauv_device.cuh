@@ -139,22 +139,21 @@ __device__ __forceinline__ T ssa(T x) {
 }
 
 // sin / cos of (a + d) from (sin a, cos a) by angle addition.  The Runge-Kutta stage angles and the post-step
-// attitude are small shifts of the pre-step attitude (d = h * sum(a_ij k_j), |d| ~ h |Theta_dot|), so sin d and
-// cos d - 1 are short Taylor polynomials instead of a library sincos (~150 instructions with its range reduction).
-// Two tiers: |d| <= 1/4 (attitude rates up to 2.5 rad/s at h = 0.1: every env of the C4 workload in steady state, where
-// one env in four exceeds 1.25 rad/s) inline with sin through d^11 (truncation < 1e-17 relative) and cos - 1 through d^12
-// (< 5e-20); anything else out of line: the round-1 polynomials for |d| <= 1/2 (sin through d^13, cos - 1 through d^14,
-// < 5e-17), the library call beyond that and for NaN / inf.  The result differs from sincos(a + d) by ~1 ulp, three
-// orders of magnitude inside the 1e-9 budget.
+// attitude are small shifts of the pre-step attitude (d = h * sum(a_ij k_j), |d| ~ h |Theta_dot|), so for
+// |d| <= 0.5 sin d and cos d - 1 are short Taylor polynomials (truncation < 5e-17 relative) instead of a library
+// sincos (~150 instructions with its range reduction); larger shifts and NaN / inf take the library call.
+// The result differs from sincos(a + d) by ~1 ulp, three orders of magnitude inside the 1e-9 budget.
+// (Measured and not kept: a first tier |d| <= 1/4 with one coefficient less per polynomial and everything else out of
+// line -- 28 DFMAs less per step, no faster; with the first tier at 1/8 one env in four of the C4 workload, whose roll
+// and yaw rates reach 2.5 rad/s, fell through to the library call: 8 % slower.)
 // Taylor coefficients of sin d / d - 1 and cos d - 1 in d^2, in constant memory: a 64-bit literal costs two UMOVs in
 // front of every DFMA that uses it, a constant-bank word one load (or none)
 __constant__ double kTaylorSin[6] = {1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0};
 __constant__ double kTaylorCos[7] = {-1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0,
                                      1.0 / 24.0, -0.5};
 
-// second tier (cold): sin d and cos d - 1 for |d| > 1/4
 template <typename T>
-static __device__ __noinline__ void sincos_shift_wide(T d, T *sd_out, T *cm1_out) {
+__device__ __forceinline__ void sincos_shift(T s0, T c0, T d, T *s, T *c) {
     T sd, cm1;
     if (Mth<T>::abs_(d) <= T(0.5)) {
         const T d2 = d * d;
@@ -170,26 +169,6 @@ static __device__ __noinline__ void sincos_shift_wide(T d, T *sd_out, T *cm1_out
         T cd;
         Mth<T>::sincos_(d, &sd, &cd);
         cm1 = cd - T(1);
-    }
-    *sd_out = sd;
-    *cm1_out = cm1;
-}
-
-template <typename T>
-__device__ __forceinline__ void sincos_shift(T s0, T c0, T d, T *s, T *c) {
-    T sd, cm1;
-    if (Mth<T>::abs_(d) <= T(0.25)) {
-        const T d2 = d * d;
-        T ps = (T)kTaylorSin[1];
-#pragma unroll
-        for (int k = 2; k < 6; k++) ps = ps * d2 + (T)kTaylorSin[k];
-        sd = (d * d2) * ps + d;
-        T pc = (T)kTaylorCos[1];
-#pragma unroll
-        for (int k = 2; k < 7; k++) pc = pc * d2 + (T)kTaylorCos[k];
-        cm1 = d2 * pc;
-    } else {
-        sincos_shift_wide<T>(d, &sd, &cm1);
     }
     *s = s0 + (s0 * cm1 + c0 * sd);
     *c = c0 + (c0 * cm1 - s0 * sd);

@@ -78,6 +78,7 @@ struct KParams {
     unsigned long long *view_list;
     uint32_t *ended_list;
     unsigned int *view_count;
+    int32_t counters_zeroed_at_end;  // 1: the last CTA of the episode-end launch saves and zeroes the list counters (the dynamics launch appends to the lists itself); 0: the dynamics launch zeroes them at its start
     int32_t sm_count;
     int32_t sparse_minv;             // M_inv has only the z_G pattern (diagonal + [0,4] [4,0] [1,3] [3,1]) filled in
     T *delta_d_out;

@@ -65,8 +65,8 @@ constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #endif
 
 // work-list counters per stepped env range (KParams::view_count): words 0..3 the live counters (view lists of class 1, 2, 3,
-// ended list), 4..7 their values at the end of the most recent step (dockauv_last_list_counts), 8 the ticket of the
-// episode-end launch, whose last CTA saves and zeroes the live counters for the next step
+// ended list); steps with the cull code fused into the dynamics launch: 4..7 their values at the end of the most recent
+// step (dockauv_last_list_counts), 8 the ticket of the episode-end launch, whose last CTA saves and zeroes the live counters
 constexpr int kListCounters = 4, kCounterStride = 16, kCounterLast = 4, kCounterTicket = 8;
 
 // ---- the per-env record written by the dynamics launch
@@ -490,6 +490,8 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
     prefetch_dynamics_inputs<T, NU>(p, i, threadIdx.x & 31, true);
     T w[kRecWords], pos[3];
     if (!FUSE) {
+        // the cull launch appends to the lists: this launch empties them
+        if (blockIdx.x == 0 && threadIdx.x < kListCounters) p.view_count[threadIdx.x] = 0u;
         if (!active) return;
         dynamics_env<T, VEH, NU, CUR, SPM, FIN, FIN>(p, i, threadIdx.x == 0 ? (int)min((int64_t)kDynThreads, p.env_end - i0) : 0, dyn_park, w, pos);
         if (!FIN) RecIO<T>::store(p.rec + i * kRecWords, w);
@@ -954,8 +956,11 @@ __global__ void __launch_bounds__(kResetCta) episode_end_kernel(const __grid_con
         }
         if (p.auto_reset) reset_envs_cta<T>(p, ie, valid);
     }
-    // ---- the last CTA to get here saves the list counters of this step and zeroes them for the next one (every CTA has
-    //      read the ended count and its list entries by now)
+    // ---- steps whose dynamics launch appends to the lists itself (cull code fused in) cannot have that launch empty
+    //      them: the last CTA to get here saves the list counters of this step and zeroes them for the next one (every CTA
+    //      has read the ended count and its list entries by now).  Other steps skip this: the ticket's round trip is on
+    //      the critical path of small batches (65,536-env SimpleDocking3d step: 24.3 against 22.6 us)
+    if (!p.counters_zeroed_at_end) return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -1021,6 +1026,7 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     // scenarios without obstacles are finished by the dynamics launch itself (no cull, no rays); with obstacles the cull +
     // finish code runs inside it whenever the float records of a CTA fit in shared memory
     const bool fuse = pipe_fuses_cull(k);
+    kc.counters_zeroed_at_end = fuse ? 1 : 0;
     cudaError_t e = !has_obstacles ? launch_dynamics<T, VEH, NU, true, false>(kc, dyn_blocks, st)
                     : fuse       ? launch_dynamics<T, VEH, NU, false, true>(kc, dyn_blocks, st)
                                  : launch_dynamics<T, VEH, NU, false, false>(kc, dyn_blocks, st);
