@@ -231,33 +231,48 @@ struct StepCarry {
     T ep_return;       // cumulative reward before this step
 };
 
+// what command_and_penalty reads of one env: the raw action (float32 or float64, as the caller handed it over) and the
+// previous low-passed command.  Loaded as one batch before anything is used: the float32 division of the penalty has a
+// slow-path branch per actuator, loads are not moved across it, and with the loads inside the loop a thread paid NU memory
+// round trips one after the other (ncu: 5 % of the dynamics launch's stall samples on these six waits)
+template <typename T, int NU>
+struct CommandIn {
+    float a32[NU];
+    double a64[NU];
+    T up[NU];
+};
+
+template <typename T, int NU>
+__device__ __forceinline__ void load_command(const KParams<T> &p, int64_t i, CommandIn<T, NU> &in) {
+    const int64_t N = p.n_envs;
+#pragma unroll
+    for (int k = 0; k < NU; k++) in.up[k] = p.u_prev[(int64_t)k * N + i];
+    if (p.act_f32) {
+        const float *a = (const float *)p.actions + i * NU;
+#pragma unroll
+        for (int k = 0; k < NU; k++) in.a32[k] = a[k];
+    } else {
+        const double *a = (const double *)p.actions + i * NU;
+#pragma unroll
+        for (int k = 0; k < NU; k++) in.a64[k] = a[k];
+    }
+}
+
 // action -> low-passed command (auvsim.py:67-87, lowpassfilter.py:29-42) and the action penalty
 // (docking3d.py:584-585).  Returns -(sum((|a|/n_u)^2 * w)).
 template <typename T, int NU>
-__device__ __forceinline__ T command_and_penalty(const KParams<T> &p, int64_t i, T u[NU]) {
-    const int64_t N = p.n_envs;
+__device__ __forceinline__ T command_and_penalty(const KParams<T> &p, const CommandIn<T, NU> &in, T u[NU]) {
     T pen;
-    // every load of this function is issued before the first use: the float32 division below has a slow-path branch per
-    // actuator, loads are not moved across it, and with the loads inside the loop a thread paid NU memory round trips
-    // one after the other (ncu: 5 % of the dynamics launch's stall samples on these six waits)
-    T upv[NU];
-#pragma unroll
-    for (int k = 0; k < NU; k++) upv[k] = p.u_prev[(int64_t)k * N + i];
     if (p.act_f32) {
-        const float *a = (const float *)p.actions + i * NU;
-        float av[NU];
-#pragma unroll
-        for (int k = 0; k < NU; k++) av[k] = a[k];
         float pen32 = 0.0f;
         double pen64 = 0.0;
 #pragma unroll
         for (int k = 0; k < NU; k++) {
-            float ak = av[k];
+            float ak = in.a32[k];
             float c = ak < -1.0f ? -1.0f : (ak > 1.0f ? 1.0f : ak);
             float frac = (c + 1.0f) / 2.0f;                       // numpy keeps this in float32
             T x = p.u_lo[k] + p.u_span[k] * (T)frac;
-            T up = upv[k];
-            u[k] = p.lp_alpha * x + (T(1) - p.lp_alpha) * up;
+            u[k] = p.lp_alpha * x + (T(1) - p.lp_alpha) * in.up[k];
             // numpy evaluates (|a| / n_u) ** 2 * w and the sum in float32 with one rounding per operation:
             // explicit _rn intrinsics keep the compiler from contracting them into FMAs
             float q = __fdiv_rn(fabsf(ak), (float)NU);
@@ -267,24 +282,26 @@ __device__ __forceinline__ T command_and_penalty(const KParams<T> &p, int64_t i,
         }
         pen = p.action_factor_is_scalar ? (T)pen32 : (T)pen64;
     } else {
-        const double *a = (const double *)p.actions + i * NU;
-        double av[NU];
-#pragma unroll
-        for (int k = 0; k < NU; k++) av[k] = a[k];
         T s = T(0);
 #pragma unroll
         for (int k = 0; k < NU; k++) {
-            T ak = (T)av[k];
+            T ak = (T)in.a64[k];
             T frac = (clipv(ak, T(-1), T(1)) + T(1)) / T(2);
             T x = p.u_lo[k] + p.u_span[k] * frac;
-            T up = upv[k];
-            u[k] = p.lp_alpha * x + (T(1) - p.lp_alpha) * up;
+            u[k] = p.lp_alpha * x + (T(1) - p.lp_alpha) * in.up[k];
             T q = Mth<T>::abs_(ak) / T(NU);
             s += (q * q) * p.arf[k];
         }
         pen = s;
     }
     return -pen;
+}
+
+template <typename T, int NU>
+__device__ __forceinline__ T command_and_penalty(const KParams<T> &p, int64_t i, T u[NU]) {
+    CommandIn<T, NU> in;
+    load_command<T, NU>(p, i, in);
+    return command_and_penalty<T, NU>(p, in, u);
 }
 
 // np.sum over the 13 reward terms in numpy's pairwise order for n = 13 (8 unrolled accumulators combined

@@ -163,10 +163,19 @@ constexpr int kParkWords = 8;
 // one env of the dynamics launch.  FIN: the env is finished here (steps_here: env-steps this call accounts for in the
 // statistics -- the callers pass the CTA's count from one thread, 0 from the others).  Otherwise the env's record is left
 // in w[kRecWords] and its post-step position in pos[3].
-template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN, bool LATE>
+//   stage(): the caller's own cp.async copies for this env (issued after the plain loads)
+template <typename T, int VEH, int NU, bool CUR, bool SPM, bool FIN, bool LATE, typename STAGE>
 __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t i, const int steps_here, T *dyn_park, T w[kRecWords],
-                                             T pos[3]) {
+                                             T pos[3], STAGE stage) {
     const int64_t N = p.n_envs;
+    // ---- what the integration starts from goes first: plain loads; the asynchronous copies of everything that is needed
+    //      later queue up behind them (issued ahead of the loads, the 21 copies of a thread delayed its first use of a loaded
+    //      value: 10 % of the fused launch's stall samples sat on that one wait)
+    T y[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
+    CommandIn<T, NU> cin;
+    load_command<T, NU>(p, i, cin);
     {
         const unsigned sa = (unsigned)__cvta_generic_to_shared(dyn_park + threadIdx.x);
         constexpr unsigned kPlane = kDynThreads * (unsigned)sizeof(T);
@@ -179,9 +188,7 @@ __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t 
             cp_async_word<int32_t>(sa + 7 * kPlane, p.t_steps + i);
         }
     }
-    T y[9];
-#pragma unroll
-    for (int c = 0; c < 9; c++) y[c] = p.state[(int64_t)(3 + c) * N + i];
+    stage();
     T tr0[6];
     Mth<T>::sincos_(y[0], &tr0[0], &tr0[1]);
     Mth<T>::sincos_(y[1], &tr0[2], &tr0[3]);
@@ -191,7 +198,7 @@ __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t 
     T tau[6], penalty;
     {
         T u[NU];
-        penalty = command_and_penalty<T, NU>(p, i, u);
+        penalty = command_and_penalty<T, NU>(p, cin, u);
 #pragma unroll
         for (int k = 0; k < NU; k++) p.u_prev[(int64_t)k * N + i] = u[k];
         dyn_tau<T, VEH, NU>(p, u, tau);
@@ -493,17 +500,19 @@ dynamics_kernel(const __grid_constant__ KParams<T> p) {
         // the cull launch appends to the lists: this launch empties them
         if (blockIdx.x == 0 && threadIdx.x < kListCounters) p.view_count[threadIdx.x] = 0u;
         if (!active) return;
-        dynamics_env<T, VEH, NU, CUR, SPM, FIN, FIN>(p, i, threadIdx.x == 0 ? (int)min((int64_t)kDynThreads, p.env_end - i0) : 0, dyn_park, w, pos);
+        dynamics_env<T, VEH, NU, CUR, SPM, FIN, FIN>(p, i, threadIdx.x == 0 ? (int)min((int64_t)kDynThreads, p.env_end - i0) : 0, dyn_park, w, pos,
+                                                     []() {});
         if (!FIN) RecIO<T>::store(p.rec + i * kRecWords, w);
         return;
     }
     const float4 *s_obs = reinterpret_cast<const float4 *>(dyn_smem) + threadIdx.x;
     if (active) {
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(s_obs);
-        for (int sl = 0; sl < p.n_obsf; sl++)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (unsigned)(sl * kDynThreads * 16)),
-                         "l"(p.obsf + (int64_t)sl * p.n_envs + i) : "memory");
-        dynamics_env<T, VEH, NU, CUR, SPM, false, true>(p, i, 0, dyn_park, w, pos);      // (its cp.async wait covers the records)
+        dynamics_env<T, VEH, NU, CUR, SPM, false, true>(p, i, 0, dyn_park, w, pos, [&]() {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(s_obs);
+            for (int sl = 0; sl < p.n_obsf; sl++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (unsigned)(sl * kDynThreads * 16)),
+                             "l"(p.obsf + (int64_t)sl * p.n_envs + i) : "memory");
+        });      // (the cp.async wait after the integration covers the records)
     }
     const bool listed = cull_finish_env<T, kDynThreads>(
         p, i, i0, active, w + REC_TRIG, w + REC_PREL, [&](int sl) { return s_obs[sl * kDynThreads]; },
