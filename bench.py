@@ -11,7 +11,7 @@ NCCL all-reduce of the episode statistics per rollout).  `--scaling strong` shar
 (config C4 as BASELINE.json words it); a run with more than one rank also measures that strong-scaling point in a second
 pass and reports it as `strong` next to the weak-scaling `value`.
 
-One "step" = one batched env.step() over every env of the rank (four launches -- dynamics, cull + finish, rays +
+One "step" = one batched env.step() over every env of the rank (three launches -- dynamics + cull + finish, rays +
 finish, episode end -- for each half of the batch, the halves on two streams).  Rank 0 prints ONE JSON line.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  The per-step
 working set (~0.9 GB at 1M envs) is far larger than L2 (126 MB), so no explicit L2 flush is needed at the default size
@@ -64,9 +64,23 @@ CONFIGS = {
                workload="C4: ObstaclesDocking3d, BlueROV2, 64-ray radar, 5 capsules + 3 spheres, random actions "
                         "U(-1,1) f32, auto-reset of finished envs"),
 }
-def launch_names(c):
-    return ("dynamics", "cull_finish", "rays_finish", "episode_end") if c["scenario"] != "SimpleDocking3d" else \
-        ("dynamics", "episode_end")
+def launch_names(c, n_launches):
+    """Names of the launches of one step, from how many the library timed: obstacle-free scenarios are finished by the
+    dynamics launch; with obstacles the cull + finish code normally runs inside the dynamics launch (three launches), as a
+    launch of its own otherwise (four)."""
+    if c["scenario"] == "SimpleDocking3d":
+        return ("dynamics", "episode_end")
+    if n_launches == 3:
+        return ("dynamics_cull_finish", "rays_finish", "episode_end")
+    return ("dynamics", "cull_finish", "rays_finish", "episode_end")
+
+
+def launch_figure(c, key, name):
+    """Algorithmic flops / bytes per env of one launch (the fused launch carries the sum of its two parts)."""
+    d = c[key]
+    if name == "dynamics_cull_finish":
+        return d["dynamics"] + d["cull_finish"]
+    return d[name]
 
 
 def workload_config(c):
@@ -477,14 +491,14 @@ def run_ours(args, rank, world, local_rank):
             print(f"peak measurement failed: {ex}", file=sys.stderr)
         pipe_name = "fp64" if args.precision == "f64" else "fp32"
         pipe_peak = fp64_peak if args.precision == "f64" else fp32_peak
-        names = launch_names(c)[:len(launch_ms)]
+        names = launch_names(c, len(launch_ms))[:len(launch_ms)]
         launches_ms = {n: float(v) for n, v in zip(names, launch_ms)}
         dominant = names[int(np.argmax(launch_ms))] if len(launch_ms) else None
         ncu, ncu_src = ncu_figures(args.config)
         ncu_ok = ncu is not None and args.precision == ncu.get("precision", "f64") and dominant in ncu.get("launches", {})
-        roofline = {"bound": pipe_name, "unit": "TFLOP/s", "peak": pipe_peak,
-                    "peak_source": "dockauv_measure_peaks: 8-chain FMA micro-kernel on this GPU, live (MEASURED_PEAKS.json "
-                                   f"carries no FP64 figure; nominal {FP64_NOMINAL_TFLOPS} TFLOP/s at 1.965 GHz)"}
+        pipe_peak_source = ("dockauv_measure_peaks: 8-chain FMA micro-kernel on this GPU, live (MEASURED_PEAKS.json "
+                            f"carries no FP64 figure; nominal {FP64_NOMINAL_TFLOPS} TFLOP/s at 1.965 GHz)")
+        roofline = {}
         listed_frac = n_listed / N
         roofline["work_lists"] = {"listed_frac": listed_frac, "ended_frac": n_ended / N,
                                   "note": "envs with an obstacle in view (visited by the ray launch) / envs whose episode "
@@ -492,20 +506,35 @@ def run_ours(args, rank, world, local_rank):
         if dominant is not None and pipe_peak:
             dms = launches_ms[dominant]
             units = N * (listed_frac if dominant.startswith("rays") else 1.0)      # envs the launch has algorithmic work for
-            ach = c["launch_flops"][dominant] * units / (dms * 1e-3) / 1e12
-            ach_gbs = c["launch_bytes"][dominant] * N / (dms * 1e-3) / 1e9
+            l_flops, l_bytes = launch_figure(c, "launch_flops", dominant), launch_figure(c, "launch_bytes", dominant)
+            ach = l_flops * units / (dms * 1e-3) / 1e12
+            ach_gbs = l_bytes * N / (dms * 1e-3) / 1e9
+            # the binding ceiling of the dominant launch: its algorithmic intensity against the machine balance of the two
+            # measured peaks (the fused dynamics + cull launch: 3,105 flop per 834 B = 3.7 flop/B against 5.2 -> HBM; the
+            # dynamics launch alone, 7.3 flop/B, and the ray launch -> the FP64 pipe)
+            intensity = l_flops * units / (l_bytes * N) if l_bytes else float("inf")
+            balance = pipe_peak * 1e12 / (hbm_peak * 1e9)
+            fp = {"algorithmic_flops_per_env": l_flops, "envs_with_work_per_launch": units, "achieved": ach, "peak": pipe_peak,
+                  "unit": "TFLOP/s", "frac": ach / pipe_peak,
+                  "frac_of_nominal": ach / FP64_NOMINAL_TFLOPS if pipe_name == "fp64" else None,
+                  "executed_pipe_frac": (ncu["launches"][dominant].get("fp64_pipe_pct", 0.0) / 100.0) if ncu_ok else None,
+                  "peak_source": pipe_peak_source}
+            hbm = {"algorithmic_bytes_per_env": l_bytes, "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": ach_gbs / hbm_peak, "peak_source": hbm_src}
+            binding = hbm if intensity < balance else fp
             roofline.update({
-                "kernel": dominant, "kernel_ms": dms, "algorithmic_flops_per_env": c["launch_flops"][dominant],
-                "envs_with_work_per_launch": units,
-                "achieved": ach, "frac": ach / pipe_peak, "frac_of_nominal": ach / FP64_NOMINAL_TFLOPS if pipe_name == "fp64" else None,
-                "executed_pipe_frac": (ncu["launches"][dominant].get("fp64_pipe_pct", 0.0) / 100.0) if ncu_ok else None,
+                "bound": "hbm" if intensity < balance else pipe_name,
+                "achieved": binding["achieved"], "peak": binding["peak"], "unit": binding["unit"], "frac": binding["frac"],
+                "peak_source": binding["peak_source"],
+                "kernel": dominant, "kernel_ms": dms,
+                "intensity_flop_per_byte": intensity, "machine_balance_flop_per_byte": balance,
                 "traffic": (ncu["launches"][dominant]["dram_bytes_per_env"] * N) if ncu_ok else None,
                 "traffic_source": ncu_src,
-                "hbm": {"algorithmic_bytes_per_env": c["launch_bytes"][dominant], "achieved": ach_gbs, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
-                "how": "achieved = algorithmic flops of the launch x envs per launch / its CUDA-event duration, measured "
+                pipe_name: fp, "hbm": hbm,
+                "how": "achieved = algorithmic bytes (flops) of the launch x envs per launch / its CUDA-event duration, measured "
                        "live between the launches of a step on the launching stream; the whole batch in one stream for "
-                       "this pass (the timed region steps it as two halves on two streams)"})
+                       "this pass (the timed region steps it as two halves on two streams); bound = whichever ceiling the "
+                       "launch's algorithmic intensity puts first"})
         step_tf = per_gpu_rate * c["flops"] / 1e12
         step_gbs = per_gpu_rate * c["bytes"] / 1e9
         roofline["step"] = {"ms": kern_ms, "launches_ms": launches_ms,

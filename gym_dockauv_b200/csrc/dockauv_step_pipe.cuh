@@ -27,10 +27,10 @@
 namespace dockauv {
 
 #ifndef DOCKAUV_DYN_THREADS
-#define DOCKAUV_DYN_THREADS 128     // CTA size of the dynamics launch
+#define DOCKAUV_DYN_THREADS 256     // CTA size of the dynamics launch (measured at 1M envs, fused form: 64 or 128 threads 252 us, 256 threads 239 us, 512 threads 266 us: the warps of a CTA run in step and share their instruction-cache lines, a 512-thread CTA drains the whole SM at once)
 #endif
 #ifndef DOCKAUV_MINB_A
-#define DOCKAUV_MINB_A 4            // its min-CTAs hint: (128, 4) = 128 registers, 16 warps per SM
+#define DOCKAUV_MINB_A 2            // its min-CTAs hint: (256, 2) = 128 registers, 16 warps per SM
 #endif
 constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #ifndef DOCKAUV_MINB_CULL
@@ -50,9 +50,6 @@ constexpr int kDynThreads = DOCKAUV_DYN_THREADS;
 #endif
 #ifndef DOCKAUV_CULL_PREFETCH
 #define DOCKAUV_CULL_PREFETCH 1     // (without staging) L2 prefetch of the records
-#endif
-#ifndef DOCKAUV_TPE_PF1
-#define DOCKAUV_TPE_PF1 0
 #endif
 #ifndef DOCKAUV_TPE_BODY
 #define DOCKAUV_TPE_BODY 1          // thread-per-env ray tiles: obstacle records rotated into the body frame once instead of every ray into NED
@@ -751,7 +748,7 @@ __global__ void __launch_bounds__(kRayWarps * 32, DOCKAUV_MINB_RAYS * 4 / kRayWa
 // the four rays of a pooled cell are independent chains the compiler interleaves.  The body-frame ray table is walked in
 // pooled-cell order (shared memory), so a cell's maximum is complete after four rays and goes straight into the
 // observation row.  One persistent launch covers both classes: tiles of class 2 (the longer ones) first, then class 1.
-constexpr int kTpeThreads = 128;
+constexpr int kTpeThreads = kRayWarps * 32;      // one CTA shape for both ray mappings of the launch
 constexpr int kTpeMaxCells = 64;      // pooled cells the shared ray table holds
 
 template <typename T, int NOB, int SPLIT>
@@ -767,12 +764,6 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
     unsigned mask = (unsigned)(entry >> 32) & 0xffffu;
     const uint32_t cond = (uint32_t)(entry >> 48) & 31u;
     const T *rec = p.rec + ie * kRecWords;
-#if DOCKAUV_TPE_PF1
-    // the words read after the ray loop (second half of the record, running return): towards L1 now
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 8));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + 12));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ep_return + ie));
-#endif
     // ---- pose and the ray-test records of the in-view obstacles (registers)
     T R[9], w[NOB][11];
     bool sph[NOB];
@@ -1042,9 +1033,11 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
     if (e != cudaSuccess) return e;
     mark();
     if (has_obstacles) {
-        if (!fuse) cull_finish_kernel<T><<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, 0, st>>>(kc);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        mark();
+        if (!fuse) {
+            cull_finish_kernel<T><<<(unsigned)((n + kCullThreads - 1) / kCullThreads), kCullThreads, 0, st>>>(kc);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            mark();
+        }
         const int smem = kRayWarps * (k.n_rays <= 64 ? RaysSmem<T, 2>(k.n_rays).warp_words : RaysSmem<T, 8>(k.n_rays).warp_words) * (int)sizeof(T);
         const int64_t sms = k.sm_count > 0 ? k.sm_count : 148;
         if (k.tpe_rays) {

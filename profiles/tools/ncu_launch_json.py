@@ -41,6 +41,11 @@ def main():
         short = next((s for k, s in NAMES if k in kname), None)
         if short is None:
             continue
+        if short == "dynamics":
+            # dynamics_kernel<T, VEH, NU, CUR, SPM, FIN, FUSE>: the last template argument says whether the cull + finish code runs in it
+            args = kname[kname.index("<") + 1:kname.rindex(">")].replace("(bool)", "").split(",")
+            if args[-1].strip() in ("1", "true"):
+                short = "dynamics_cull_finish"
         per[short].append({
             "us": val(r, "gpu__time_duration.sum"),
             "dram_bytes": val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
