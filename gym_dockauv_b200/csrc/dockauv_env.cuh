@@ -68,7 +68,10 @@ __device__ __forceinline__ void reset_env_role(const KParams<T> &p, int64_t i, i
     const int64_t N = p.n_envs;
     const uint64_t gid = p.env_id0 + (uint64_t)i;
     const double PI = 3.141592653589793;
+    // one Philox block yields two draws: the blocks a role needs are evaluated once each (role 0, the longest chain of the
+    // eight, took nine block evaluations for its nine draws when every draw evaluated its own)
     auto U = [&](uint32_t idx) { return philox_uniform(p.seed, gid, ep, idx); };
+    auto U2 = [&](uint32_t blk, double u[2]) { philox_uniform_pair(p.seed, gid, ep, blk, u); };
     const int scn = p.scenario;
     const bool has_goal_ring = scn >= DOCKAUV_SCN_CAPSULE;
     const bool has_dock = has_goal_ring && scn != DOCKAUV_SCN_OBSTACLES_NOCAP && p.n_caps > 0;
@@ -77,14 +80,17 @@ __device__ __forceinline__ void reset_env_role(const KParams<T> &p, int64_t i, i
     const int n_pillars = has_pillars ? max(0, min(4, p.n_caps - first_pillar)) : 0;
     // the goal (draws 7 and 8): stored by role 0, and the origin of every float obstacle record
     double goal[3] = {0.0, 0.0, 0.0};
+    double u67[2] = {0.0, 0.0}, u89[2] = {0.0, 0.0};      // draws 6..9: goal angle / depth here, yaw (role 0) and pillar phase below
+    if (has_goal_ring || role == 0) U2(3, u67);
     if (has_goal_ring) {                                                       // :860-886
-        double theta = U(7) * 2 * PI;
+        U2(4, u89);
+        double theta = u67[1] * 2 * PI;
         double radius = 1.0 + (double)p.safety_radius;
         double s, c;
         sincos(theta, &s, &c);
         goal[0] = c * radius;
         goal[1] = s * radius;
-        goal[2] = (U(8) - 0.5) * 4.0;
+        goal[2] = (u89[0] - 0.5) * 4.0;
     }
     const T goal_t[3] = {(T)goal[0], (T)goal[1], (T)goal[2]};
     // obstacle rows (T) + their float records for the cull launch
@@ -107,8 +113,12 @@ __device__ __forceinline__ void reset_env_role(const KParams<T> &p, int64_t i, i
         store_sphere_record<T>(p, i, k, c, goal_t);
     };
     if (role == 0) {
-        double heading = (U(0) - 0.5) * PI;                                   // :814
-        double r[3] = {U(1) - 0.5, U(2) - 0.5, U(3) - 0.5};                   // :694-696
+        double u01[2], u23[2], u45[2];
+        U2(0, u01);
+        U2(1, u23);
+        U2(2, u45);
+        double heading = (u01[0] - 0.5) * PI;                                 // :814
+        double r[3] = {u01[1] - 0.5, u23[0] - 0.5, u23[1] - 0.5};             // :694-696
         {
             double sg = (r[2] > 0.0) - (r[2] < 0.0);
             r[2] = fabs(r[0] + r[1]) / 3 * sg;
@@ -116,8 +126,8 @@ __device__ __forceinline__ void reset_env_role(const KParams<T> &p, int64_t i, i
         double sc = 15.0 / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
         double pos[3] = {r[0] * sc, r[1] * sc, r[2] * sc};
         double max_att = (double)p.max_attitude;
-        double att[3] = {(U(4) - 0.5) * 2 * (max_att * 0.7), (U(5) - 0.5) * 2 * (max_att * 0.7),
-                         (U(6) - 0.5) * 2 * PI};                               // :699-703
+        double att[3] = {(u45[0] - 0.5) * 2 * (max_att * 0.7), (u45[1] - 0.5) * 2 * (max_att * 0.7),
+                         (u67[0] - 0.5) * 2 * PI};                             // :699-703
         // vec_line_point(goal, top=(0,0,-2), bot=(0,0,2)) = (-gx, -gy, 0)  (shape.py:420-433)
         if (has_goal_ring) heading = (double)ssa<double>(atan2(0.0 - goal[1], 0.0 - goal[0]));
 #pragma unroll
@@ -134,7 +144,7 @@ __device__ __forceinline__ void reset_env_role(const KParams<T> &p, int64_t i, i
     } else if (role <= 4) {                                                    // pillars, :919-946
         const int k = role - 1;
         if (k < n_pillars) {
-            double theta = U(9) * 2 * PI;
+            double theta = (has_goal_ring ? u89[1] : U(9)) * 2 * PI;
             for (int q = 0; q < k; q++) theta += 2 * PI / 4;
             const double half = 2.0 * (double)p.max_dist_from_goal / 2.0;
             double s, c;

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -q -x --durations=3 ) > gpurun_out/r2_tests18.log 2>&1
-tail -4 gpurun_out/r2_tests18.log
-VARIANTS="b200 r8 r8b" bash profiles/tools/ab.sh --quick
+( time python -m pytest tests -m gpu -q -x --durations=3 ) > gpurun_out/r2_tests19.log 2>&1
+tail -4 gpurun_out/r2_tests19.log
+VARIANTS="b200" bash profiles/tools/ab.sh
