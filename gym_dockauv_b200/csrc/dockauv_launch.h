@@ -21,7 +21,7 @@ cudaError_t launch_reset(const KParams<T> &k, const uint8_t *mask_dev, cudaStrea
 #define DOCKAUV_FUSE_CULL 1         // pipeline layout: the cull + finish code runs inside the dynamics launch ...
 #endif
 #ifndef DOCKAUV_FUSE_MAX_OBSF
-#define DOCKAUV_FUSE_MAX_OBSF 20    // ... when an env has at most this many float4 obstacle records: 40 KB of shared memory per CTA, four CTAs per SM stay resident
+#define DOCKAUV_FUSE_MAX_OBSF 20    // ... when an env has at most this many float4 obstacle records: 80 KB of shared memory per 256-thread CTA, two CTAs per SM stay resident
 #endif
 // whether the dynamics launch of the pipeline layout takes the cull + finish code in, and how many launches one step over
 // one env range is

@@ -1,26 +1,30 @@
 // dockauv_step_pipe.cuh -- layout DOCKAUV_LAYOUT_PIPELINE (default): one batched step as specialised launches.
 //
 //   1. dynamics     dynamics_kernel: thread per env.  Current, command filter, RKF45, angle wrap, navigation errors,
-//                   obs[0:16], done conditions 0..2, the reward terms that need no radar.  Leaves one 16-word record
-//                   per env (KParams::rec): post-step attitude sines / cosines, position relative to the goal, the
-//                   reward terms already combined in numpy's summation order, delta_d, condition bits.
-//   2. cull+finish  cull_finish_kernel: thread per env.  Walks over the env's obstacles in FLOAT (float4 records
-//                   relative to the goal, written at reset; cull_pair_rec): body collision (re-decided in T when within
-//                   2 mm of the threshold) and the range / field-of-view culls.  Envs with something in view (24 % on
-//                   the C4 workload) are appended to a compact list.  Done flag, condition bits and counters are final
-//                   here for EVERY env (coalesced stores); an env with nothing in view is finished completely -- all ray
-//                   cells read max_dist, r_oa = 0: reward, running return, statistics -- and goes on a second list if
-//                   its episode ended.  No shared memory, no barrier.
-//   3. rays+finish  rays_finish_kernel: persistent grid, one warp per LISTED env (lanes = rays), data of the next list
-//                   entry in flight while the current one is cast (radar_env, dockauv_rays.cuh); the warp then writes the
-//                   reward with its obstacle-avoidance term and the running return (skipped for obstacle-free scenarios).
-//   4. episode end  episode_end_kernel: thread per ENDED env (~1 % of the batch, compacted by launches 2 and 3):
-//                   terminal-observation row, zero row, re-initialisation.  Tiny; overlaps the other half's launches.
+//      + cull        obs[0:16], done conditions 0..2, the reward terms that need no radar -- a 16-word record per env
+//      + finish      (post-step attitude sines / cosines, position relative to the goal, the reward terms already combined
+//                   in numpy's summation order, delta_d, condition bits) that stays in REGISTERS for the second half of the
+//                   thread (FUSE): the walk over the env's obstacles in FLOAT (float4 records relative to the goal, written
+//                   at reset, waiting in shared memory since the start of the thread; cull_pair_rec): body collision
+//                   (re-decided in T when within 2 mm of the threshold) and the range / field-of-view culls.  Envs with
+//                   something in view (24 % on the C4 workload) are appended to a compact list and their record goes to
+//                   KParams::rec.  Done flag, condition bits and counters are final here for EVERY env (coalesced stores);
+//                   an env with nothing in view is finished completely -- all ray cells read max_dist, r_oa = 0: reward,
+//                   running return, statistics -- and goes on a second list if its episode ended.
+//                   (Obstacle-free scenarios: FIN, the env is finished right after the dynamics.  More float records than
+//                   fit in shared memory, or coordinates too large for them: the cull + finish code runs as a launch of its
+//                   own, cull_finish_kernel, on records read back from KParams::rec.)
+//   2. rays+finish  rays_thread_kernel: persistent grid.  The listed envs with one or two obstacles in view with LANES =
+//                   ENVS (tiles of 128), the others by one warp each (lanes = rays, next entry in flight while the current
+//                   one is cast; radar_env, dockauv_rays.cuh) on the first CTAs of the same launch; then the reward with its
+//                   obstacle-avoidance term and the running return.
+//   3. episode end  episode_end_kernel: the ENDED envs (~1 % of the batch, compacted by launches 1 and 2): terminal-
+//                   observation row, zero row, re-initialisation (warp = reset role, lane = env).
 //
-// Each launch has its own register budget and occupancy, the ray warps never idle on envs with nothing in view, and no
-// env is touched by a launch that has nothing to do for it (round 1 had a fourth launch that re-read every env's
-// hand-off just to finish it).  Results are identical to the other layouts (same device functions, same order of
-// operations per env); debug outputs are served by the fused kernel.
+// Each launch has its own register budget and occupancy, the ray code never idles on envs with nothing in view, and no
+// env is touched by a launch that has nothing to do for it.  Results are identical to the other layouts (same device
+// functions, same order of operations per env; the ray tiles rotate obstacle records into the body frame instead of rays
+// into NED, which moves ray distances in their last bits); debug outputs are served by the single-launch kernel.
 #pragma once
 #include "dockauv_step_warp.cuh"
 
