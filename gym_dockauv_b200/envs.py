@@ -1,6 +1,6 @@
 """Batched docking environments: the reference's gym.Env contract (gym_dockauv/envs/docking3d.py:31-402),
 vectorised over N independent envs that live in HBM and are stepped by a short sequence of sm_100a kernel launches
-(dynamics, cull, rays, finish; include/dockauv.h).
+(dynamics + cull + finish, rays + finish, episode end; include/dockauv.h).
 
     env = ObstaclesDocking3d(env_config, num_envs=1 << 20, device="cuda:0")
     obs = env.reset(seed=0)                      # f32 [N, n_obs], all zeros like the reference's reset()
@@ -343,7 +343,7 @@ class BaseDocking3d:
             self.refresh_obstacles()
 
     def refresh_obstacles(self):
-        """Call after writing ``self.capsules``, ``self.spheres`` or ``self.goal`` directly: the cull launch reads a
+        """Call after writing ``self.capsules``, ``self.spheres`` or ``self.goal`` directly: the cull code reads a
         float copy of the obstacles relative to the goal that the library keeps (dockauv_refresh_obstacles);
         ``reset`` and ``set_state`` do it themselves."""
         _capi.check(self._lib.dockauv_refresh_obstacles(self._handle, self._stream()))
@@ -370,7 +370,7 @@ class BaseDocking3d:
 
     def last_step_ms(self):
         """(ms of the most recent timed step, [ms of each of its launches]) -- the per-launch list is empty for the
-        single-launch layouts; pipeline layout: dynamics, cull, rays, finish."""
+        single-launch layouts; pipeline layout: dynamics + cull + finish, rays + finish (with obstacles), episode end."""
         ms = C.c_float()
         _capi.check(self._lib.dockauv_last_step_ms(self._handle, C.byref(ms)))
         per = (C.c_float * 8)()

@@ -99,9 +99,9 @@ extern "C" {
 #define DOCKAUV_LAYOUT_AUTO 0
 #define DOCKAUV_LAYOUT_THREAD_PER_ENV 1   /* one thread does everything for one env */
 #define DOCKAUV_LAYOUT_WARP_RAYS 2        /* one launch: dynamics thread-per-env, radar one warp per env (lanes = rays) */
-#define DOCKAUV_LAYOUT_PIPELINE 4         /* dynamics (thread per env), cull + finish of the envs with nothing in view (thread per
-                                             env), rays + finish (one warp per env that has an obstacle in view, from a compact
-                                             list), episode end (thread per finished env, from a compact list) */
+#define DOCKAUV_LAYOUT_PIPELINE 4         /* dynamics + cull + finish of the envs with nothing in view (thread per env), rays +
+                                             finish (a thread or a warp per env that has an obstacle in view, from compact
+                                             lists), episode end (per finished env, from a compact list) */
 
 /* indices into the stats vector (sums since the last clear; reduce over ranks with one all-reduce) */
 #define DOCKAUV_STAT_EPISODES 0
@@ -238,7 +238,7 @@ DOCKAUV_API int dockauv_set_seed(DockauvHandle *h, uint64_t seed);
 /* Re-initialise envs whose mask byte is non-zero (all envs if mask_dev == NULL). */
 DOCKAUV_API int dockauv_reset(DockauvHandle *h, const uint8_t *mask_dev, void *stream);
 
-/* The cull launch reads a float copy of the obstacles relative to the goal, which the library keeps next to the bound
+/* The cull code reads a float copy of the obstacles relative to the goal, which the library keeps next to the bound
  * buffers: dockauv_bind and every reset (dockauv_reset, auto-reset inside a step) write it.  A caller that writes the
  * bound `capsules`, `spheres` or `goal` buffers ITSELF (exact-state injection: the reference's env.capsules = [...] /
  * env.goal_location = ..., docking3d.py:860-946) calls this afterwards, on the stream that did the writes. */
@@ -312,7 +312,8 @@ DOCKAUV_API int dockauv_rollout_captures(DockauvHandle *h, int64_t *n_captures);
 DOCKAUV_API int dockauv_enable_timing(DockauvHandle *h, int enabled);
 DOCKAUV_API int dockauv_last_step_ms(DockauvHandle *h, float *ms);
 /* Per-launch CUDA-event times (ms) of the most recent timed dockauv_step of a multi-launch layout, in launch order
- * (DOCKAUV_LAYOUT_PIPELINE: dynamics, cull + finish, rays + finish (only with obstacles), episode end); *n_launches = 0
+ * (DOCKAUV_LAYOUT_PIPELINE: dynamics + cull + finish [, cull + finish when it runs as a launch of its own], rays + finish
+ * (only with obstacles), episode end); *n_launches = 0
  * for the single-launch layouts. */
 DOCKAUV_API int dockauv_last_step_launch_ms(DockauvHandle *h, float *ms, int capacity, int *n_launches);
 
