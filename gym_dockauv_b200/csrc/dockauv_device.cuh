@@ -459,15 +459,6 @@ __device__ __forceinline__ void rkf45_step(const KParams<T> &p, T *y, const T *t
             }
         }
     }
-#ifdef DOCKAUV_RK_FOLD
-    // tuning variant: from here on the velocity components carry y inside the running sums (y[3..8] is dead two stages
-    // earlier); the attitude components keep their increments, which sincos_shift needs
-#pragma unroll
-    for (int i = 3; i < 9; i++) {
-        d5[i] = parked<ST>(y, i) + d5[i];
-        dw[i] = parked<ST>(y, i) + dw[i];
-    }
-#endif
     stage_trig<T, true, ST>(tr0, dy, tr);
     {
         T k4[9];
@@ -476,11 +467,7 @@ __device__ __forceinline__ void rkf45_step(const KParams<T> &p, T *y, const T *t
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             d5[i] = d5[i] + d * k4[i];
-#ifdef DOCKAUV_RK_FOLD
-            yt[i] = i < 3 ? parked<ST>(y, i) + d5[i] : d5[i];
-#else
             yt[i] = parked<ST>(y, i) + d5[i];
-#endif
             dw[i] = dw[i] + dwc * k4[i];
         }
     }
@@ -492,11 +479,7 @@ __device__ __forceinline__ void rkf45_step(const KParams<T> &p, T *y, const T *t
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             dw[i] = dw[i] + e * k5[i];
-#ifdef DOCKAUV_RK_FOLD
-            y[i * ST] = i < 3 ? parked<ST>(y, i) + dw[i] : dw[i];
-#else
             y[i * ST] = parked<ST>(y, i) + dw[i];
-#endif
         }
     }
     stage_trig<T, true, ST>(tr0, dw, tr1);
@@ -735,7 +718,11 @@ __device__ __forceinline__ void cull_pair_rec(const KParams<T> &p, const float p
         for (int c = 0; c < 3; c++) db[c] = Rm[c] * d[0] + Rm[3 + c] * d[1] + Rm[6 + c] * d[2];
         const float uy = ty * db[0], uz = tz * db[0];
         auto clip = [&](float alpha, float beta) {        // keep { t : alpha t <= beta }
-            const float q = __fdividef(beta, alpha);
+            // one MUFU instead of __fdividef's six instructions (25 quotients per env): q only decides with 1e-3 of slack, and
+            // where alpha flushes to zero the plane simply does not clip (the conservative direction: more stays in view)
+            float ra;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(alpha));
+            const float q = beta * ra;
             t_hi = fminf(t_hi, alpha > 0.0f ? q + 1e-3f : 3.0e38f);
             t_lo = fmaxf(t_lo, alpha < 0.0f ? q - 1e-3f : -3.0e38f);
             empty |= (alpha == 0.0f) && (beta < 0.0f);

@@ -205,25 +205,7 @@ __device__ __forceinline__ void dynamics_env(const KParams<T> &p, const int64_t 
         dyn_tau<T, VEH, NU>(p, u, tau);
     }
     T pacc[3], tr1[6];
-#ifdef DOCKAUV_DYN_SMEM
-    // tuning variant: the values that live through the whole integration but are read once per stage (pre-step state,
-    // its sines / cosines, the generalised force) parked in shared memory, [word][thread]
-    {
-        __shared__ T s_park[21 * kDynThreads];
-        T *sp = s_park + threadIdx.x;
-#pragma unroll
-        for (int c = 0; c < 9; c++) sp[c * kDynThreads] = y[c];
-#pragma unroll
-        for (int c = 0; c < 6; c++) sp[(9 + c) * kDynThreads] = tr0[c];
-#pragma unroll
-        for (int c = 0; c < 6; c++) sp[(15 + c) * kDynThreads] = tau[c];
-        rkf45_step<T, VEH, SPM, CUR, kDynThreads>(p, sp, sp + 9 * kDynThreads, sp + 15 * kDynThreads, nu_c, pacc, tr1);
-#pragma unroll
-        for (int c = 0; c < 9; c++) y[c] = sp[c * kDynThreads];
-    }
-#else
     rkf45_step<T, VEH, SPM, CUR>(p, y, tr0, tau, nu_c, pacc, tr1);
-#endif
 #pragma unroll
     for (int c = 0; c < 3; c++) y[c] = ssa<T>(y[c]);
     // position and goal are only needed from here on: they have been waiting in shared memory

@@ -9,7 +9,10 @@ from tests.golden_utils import rel_err
 
 pytestmark = pytest.mark.gpu
 
+# (8 capsule + 8 sphere slots = 24 float records per env: more than the dynamics launch takes in, so the cull + finish code
+# runs as a launch of its own; every other obstacle case runs it fused)
 CASES = [("ObstaclesDocking3d", dict(n_synthetic_spheres=3)), ("ObstaclesCurrentDocking3d", dict(n_synthetic_spheres=8)),
+         ("ObstaclesDocking3d", dict(n_synthetic_spheres=8, n_capsules=8)),
          ("ObstaclesNoCapDocking3d", {}), ("CapsuleCurrentDocking3d", {}), ("SimpleCurrentDocking3d", {}),
          ("SimpleDocking3d", {})]
 
@@ -60,5 +63,29 @@ def test_all_layouts_agree_on_odd_batch(name, kw):
     od, rd, dd, _ = es[1].step(torch.as_tensor(a, device="cuda"))
     assert np.array_equal(dh, dd.cpu().numpy().astype(bool)) and np.array_equal(oh, od.cpu().numpy())
     assert rel_err(rh, rd.cpu().numpy()) < 1e-12
+    for e in es:
+        e.close()
+
+
+def test_exact_cull_matches_float_cull():
+    """Handles whose coordinates are too large for float obstacle records (max_dist_from_goal + max_dist > 2 km) cull in
+    double in a launch of their own: same flags / observations / rewards as the thread-per-env kernel."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
+    cfg = dict(BASE_CONFIG)
+    cfg["radar"] = dict(RADAR_64)
+    cfg["max_dist_from_goal"] = 2500.0
+    N = 777
+    es = [envs.ObstaclesDocking3d(cfg, num_envs=N, seed=5, n_synthetic_spheres=3, layout=l) for l in ("thread_per_env", "pipeline")]
+    for e in es:
+        e.reset()
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    for t in range(40):
+        a = torch.rand(N, 6, device="cuda", generator=gen) * 2 - 1
+        (o0, r0, d0, i0), (o1, r1, d1, i1) = [e.step(a) for e in es]
+        assert torch.equal(d0, d1) and torch.equal(i0["cond_bits"], i1["cond_bits"]) and torch.equal(o0, o1), t
+        assert rel_err(r1.cpu().numpy(), r0.cpu().numpy()) < 1e-12, t
+    assert rel_err(es[1].state.cpu().numpy(), es[0].state.cpu().numpy()) < 1e-12
     for e in es:
         e.close()
