@@ -1,1 +1,4 @@
-TAG=v2n bash profiles/tools/round_profile.sh
+mkdir -p gpurun_out
+( time python -m pytest tests -m gpu -q -x --durations=3 ) > gpurun_out/r2_tests24.log 2>&1
+tail -4 gpurun_out/r2_tests24.log
+VARIANTS="b200 nst" bash profiles/tools/ab.sh --quick
