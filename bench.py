@@ -369,9 +369,11 @@ def run_ours(args, rank, world, local_rank):
                 dist.all_reduce(reduced)
             n_reduces += 1
     torch.cuda.current_stream(dev).wait_stream(side)
+    ev_end = torch.cuda.Event(enable_timing=True)      # after the join with the side stream: the last all-reduce is inside the span
+    ev_end.record()
     barrier()
     clk_timed_end = sampler.mark()
-    total_ms = evs[0].elapsed_time(evs[-1])
+    total_ms = evs[0].elapsed_time(ev_end)
     step_ms = np.array([evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)])
     launches = env.launch_count() - launches0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
