@@ -348,6 +348,15 @@ def run_ours(args, rank, world, local_rank):
         env.step(pool[k % len(pool)])
     for k in range(args.warmup):
         env.step(pool[k % len(pool)])
+    side = torch.cuda.Stream(dev)
+    if world > 1:
+        # warm-up of the collective too (the first all-reduce of a communicator pays its lazy set-up: ~1.4 ms at 4 GPUs), on
+        # the stream the timed ones use
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                dist.all_reduce(env.stats_tensor().clone())
+        torch.cuda.current_stream(dev).wait_stream(side)
     env.clear_stats()
     barrier()
     clk_first = sampler.mark()
@@ -355,7 +364,6 @@ def run_ours(args, rank, world, local_rank):
     # ---- the timed region: K steps; one statistics all-reduce per rollout on a side stream, at least one
     rollout = max(1, min(args.rollout, args.steps))
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    side = torch.cuda.Stream(dev)
     reduced, n_reduces = None, 0
     evs[0].record()
     for k in range(args.steps):
