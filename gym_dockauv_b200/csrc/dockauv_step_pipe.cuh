@@ -119,6 +119,19 @@ struct RecIO<float> {
     }
 };
 
+#ifndef DOCKAUV_PDL
+#define DOCKAUV_PDL 1               // ray and episode-end launches as programmatic dependents of the launch before them
+#endif
+// Launch as a PROGRAMMATIC DEPENDENT of the previous launch in the stream: the grid is set up while that launch drains and
+// its threads wait in grid_dependency_wait() until everything the previous launch wrote is visible (no launch before it
+// triggers early, so the wait is for its completion; an early trigger at the top of the launch before -- dependents set up
+// during its last wave -- measured no faster).  What it saves is part of the launch-to-launch gap: 22.5 -> 22.3 us per
+// 65,536-env SimpleDocking3d step, 0.391 -> 0.390 ms per 1M-env C4 step.
+__device__ __forceinline__ void grid_dependency_wait() {
+#if DOCKAUV_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 // one word global -> shared without a register in between (completion: cp_async_wait_all); dst = shared-window address
 template <typename T>
 __device__ __forceinline__ void cp_async_word(unsigned dst_shared, const T *src) {
@@ -877,6 +890,7 @@ __global__ void __launch_bounds__(kTpeThreads, DOCKAUV_MINB_TPE) rays_thread_ker
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(16) T s_tab[kTpeMaxCells * 4 * 4];      // slot = 4 * cell + q: rb[3], bw; bw < 0 marks zero padding
     static_assert(kTpeThreads == kRayWarps * 32, "the two ray mappings share one CTA shape");
+    grid_dependency_wait();
     if (blockIdx.x < warp_ctas) {
         rays_warp_loop<T, RPL>(p, smem_raw, blockIdx.x * kRayWarps + (threadIdx.x >> 5), warp_ctas * kRayWarps);
         return;
@@ -914,6 +928,7 @@ __global__ void __launch_bounds__(kTpeThreads, DOCKAUV_MINB_TPE) rays_thread_ker
 // eight LANES per env: the roles serialise inside the warp, same 70 us.
 template <typename T>
 __global__ void __launch_bounds__(kResetCta) episode_end_kernel(const __grid_constant__ KParams<T> p) {
+    grid_dependency_wait();
     const unsigned n_ended = p.view_count[3];
     const int n_obs = p.n_obs;
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
@@ -963,6 +978,26 @@ __global__ void __launch_bounds__(kResetCta) episode_end_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------- launcher
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kern)(KArgs...), unsigned blocks, unsigned threads, size_t smem, cudaStream_t st, Args... args) {
+#if DOCKAUV_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+#else
+    kern<<<blocks, threads, smem, st>>>(args...);
+    return cudaGetLastError();
+#endif
+}
+
 template <typename T, int VEH, int NU, bool FIN, bool FUSE>
 static cudaError_t launch_dynamics(const KParams<T> &k, unsigned blocks, cudaStream_t st) {
     const bool cur = k.has_current != 0, spm = k.sparse_minv != 0;
@@ -1037,11 +1072,11 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
             if (k.n_rays <= 64) {
                 auto kern = rays_thread_kernel<T, DOCKAUV_TPE_SPLIT, 2>;
                 if (smem > 40 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-                kern<<<(unsigned)(wb + tb), kTpeThreads, smem, st>>>(kc, (unsigned)wb);
+                if ((e = launch_dependent(kern, (unsigned)(wb + tb), kTpeThreads, smem, st, kc, (unsigned)wb)) != cudaSuccess) return e;
             } else {
                 auto kern = rays_thread_kernel<T, DOCKAUV_TPE_SPLIT, 8>;
                 if (smem > 40 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-                kern<<<(unsigned)(wb + tb), kTpeThreads, smem, st>>>(kc, (unsigned)wb);
+                if ((e = launch_dependent(kern, (unsigned)(wb + tb), kTpeThreads, smem, st, kc, (unsigned)wb)) != cudaSuccess) return e;
             }
         } else {
             // ---- rays: warp per env for every listed env (persistent grid)
@@ -1066,8 +1101,7 @@ static cudaError_t launch_step_pipe(const KParams<T> &k, cudaStream_t st, cudaEv
         int64_t blocks = n / 1024 + 1;
         const int64_t cap = (int64_t)(k.sm_count > 0 ? k.sm_count : 148) * 4;
         if (blocks > cap) blocks = cap;
-        episode_end_kernel<T><<<(unsigned)blocks, kResetCta, 0, st>>>(kc);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = launch_dependent(episode_end_kernel<T>, (unsigned)blocks, kResetCta, 0, st, kc)) != cudaSuccess) return e;
         mark();
     }
     if (n_marks) *n_marks = n_mark;
