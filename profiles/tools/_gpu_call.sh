@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-VARIANTS="b200 pdl2 npdl" bash profiles/tools/ab.sh
+( time python -m pytest tests -m gpu -q -x --durations=3 ) > gpurun_out/r2_tests26.log 2>&1
+tail -3 gpurun_out/r2_tests26.log
+TAG=v2p bash profiles/tools/round_profile.sh
