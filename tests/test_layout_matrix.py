@@ -89,3 +89,30 @@ def test_exact_cull_matches_float_cull():
     assert rel_err(es[1].state.cpu().numpy(), es[0].state.cpu().numpy()) < 1e-12
     for e in es:
         e.close()
+
+
+@pytest.mark.parametrize("kw", [dict(n_synthetic_spheres=3), dict(n_synthetic_spheres=8, n_capsules=8)])
+def test_list_counts_match_the_step_outputs(kw):
+    """dockauv_last_list_counts after a step: the ended count is the number of done flags, the listed count the number of
+    envs with a pooled ray cell below 1 or more (listed = something in view, a superset of real hits) -- with the cull code
+    inside the dynamics launch (counters saved and zeroed by the episode-end launch) and as a launch of its own."""
+    import torch
+    from gym_dockauv_b200 import envs
+    from gym_dockauv_b200.config import BASE_CONFIG, RADAR_64
+    cfg = dict(BASE_CONFIG)
+    cfg["radar"] = dict(RADAR_64)
+    N = 40000                      # one launch group; also stepped in two parts below
+    for n in (N, 1 << 18):
+        env = envs.ObstaclesDocking3d(cfg, num_envs=n, seed=2, **kw)
+        env.reset()
+        env.t_steps += 990          # episodes end inside the run
+        gen = torch.Generator(device="cuda").manual_seed(1)
+        for t in range(14):
+            obs, _, done, info = env.step(torch.rand(n, 6, device="cuda", generator=gen) * 2 - 1)
+            n_listed, n_ended = env.last_list_counts()
+            assert n_ended == int(done.sum()), (n, t)
+            # observation rows of finished envs are zeroed; among the others a cell below 1 needs an obstacle in view
+            hit = int(((obs[:, 16:] < 1.0).any(1) & ~done.bool()).sum())
+            assert hit <= n_listed <= n, (n, t, hit, n_listed)
+        assert env.get_stats()["episodes"] > 0
+        env.close()
