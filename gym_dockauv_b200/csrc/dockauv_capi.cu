@@ -247,7 +247,7 @@ static void fill_kparams(const DockauvParams &s, int64_t n_envs, KParams<T> &k) 
     sparse = false;
 #endif
     k.sparse_minv = sparse ? 1 : 0;
-    // the cull launch works on float records relative to the goal: every coordinate that matters is within
+    // the cull code works on float records relative to the goal: every coordinate that matters is within
     // max_dist_from_goal + max_dist of it; beyond ~2 km the float rounding would eat the 2 mm slack -> exact culls
     k.cull_exact = (s.max_dist_from_goal + s.radar_max_dist > 2000.0) ? 1 : 0;
     k.fov_ty = (T)ty;

@@ -628,7 +628,7 @@ __device__ __forceinline__ void obstacle_ray_record(const T pos[3], const T ob[7
     }
 }
 
-// Just the body-collision decision of obstacle_pair (same expressions, same bits): used by the cull launch for the
+// Just the body-collision decision of obstacle_pair (same expressions, same bits): used by the cull code for the
 // pairs its float pre-test leaves undecided.
 template <typename T>
 __device__ __forceinline__ bool obstacle_body_hit(const KParams<T> &p, const T pos[3], const T ob[7], bool is_cap) {
@@ -662,7 +662,7 @@ __device__ __forceinline__ bool obstacle_body_hit(const KParams<T> &p, const T p
     return dist <= rad + p.safety_radius;
 }
 
-// The culls and the body-collision pre-test of obstacle_pair in FLOAT, for the cull launch (FP64 runs at half rate, and
+// The culls and the body-collision pre-test of obstacle_pair in FLOAT, for the cull code (FP64 runs at half rate, and
 // the launch is bound by the instructions it issues: this function is written for instruction count).  Inputs are the
 // float obstacle record (KParams::obsf, relative to the goal, written by every reset) and the vehicle position relative to
 // the goal (formed in T by the dynamics launch, rounded once): every coordinate that matters is within

@@ -6,7 +6,7 @@
 namespace dockauv {
 
 // ------------------------------------------------------------------------------------------- reset
-// Float obstacle records of env i for the cull launch (KParams::obsf, see cull_pair_rec), from the obstacles and the
+// Float obstacle records of env i for the cull code (KParams::obsf, see cull_pair_rec), from the obstacles and the
 // goal as they are stored (T).  Capsule k -> slots 2k, 2k+1; sphere s -> slot 2 n_caps + s.
 template <typename T>
 __device__ __forceinline__ void store_capsule_record(const KParams<T> &p, int64_t i, int k, const T cap[7], const T goal[3]) {
@@ -93,7 +93,7 @@ __device__ __forceinline__ void reset_env_role(const KParams<T> &p, int64_t i, i
         goal[2] = (u89[0] - 0.5) * 4.0;
     }
     const T goal_t[3] = {(T)goal[0], (T)goal[1], (T)goal[2]};
-    // obstacle rows (T) + their float records for the cull launch
+    // obstacle rows (T) + their float records for the cull code
     auto put_capsule = [&](int k, const double cap[7]) {
         T c[7];
 #pragma unroll

@@ -35,7 +35,7 @@ inline int pipe_launches(const KParams<T> &k) {
     return pipe_fuses_cull(k) ? 3 : 4;          // dynamics (+ cull + finish) [, cull + finish], rays, episode end
 }
 
-// float obstacle records of the cull launch from the bound obstacle / goal buffers (no-op for handles without them)
+// float obstacle records of the cull code from the bound obstacle / goal buffers (no-op for handles without them)
 template <typename T>
 cudaError_t launch_refresh_obstacles(const KParams<T> &k, cudaStream_t st);
 

@@ -699,7 +699,7 @@ __device__ __forceinline__ void rays_warp_loop(const KParams<T> &p, unsigned cha
         // ---- cast rays against the in-view obstacles, pooled cells to the observation row
         const T oa_dot = radar_env<T, RPL, false, RayLaneShared<T, RPL>>(p, rl, R, poison, mask, s_pre, s_ray, lane, ie);
 
-        // ---- what the cull launch left open: the reward with its obstacle-avoidance term and the running return
+        // ---- what the cull code left open: the reward with its obstacle-avoidance term and the running return
         //      (every lane computes the same values from the staged record, lane 0 stores)
         const T r_oa = p.sum_beta_oa / oa_dot - T(1);      // docking3d.py:792 (IEEE division: the other layouts' bits)
         const T reward = step_reward<T>(p, s_ent[REC_A], s_ent[REC_B], s_ent[REC_R7], s_ent[REC_LPD], r_oa, cond);
@@ -711,7 +711,7 @@ __device__ __forceinline__ void rays_warp_loop(const KParams<T> &p, unsigned cha
             if (!(done && p.auto_reset)) p.ep_return[ie] = ep_ret;
         }
         if (done) {       // warp-uniform, ~1 % of the listed envs
-            const int32_t t_new = reinterpret_cast<const int32_t *>(s_ent + 20)[0];     // already incremented by the cull launch
+            const int32_t t_new = reinterpret_cast<const int32_t *>(s_ent + 20)[0];     // already incremented by the cull code
             double mine = 0.0;
             if (lane == DOCKAUV_STAT_EPISODES) mine = 1.0;
             else if (lane == DOCKAUV_STAT_SUM_RETURN) mine = (double)ep_ret;
@@ -857,7 +857,7 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
 #pragma unroll
     for (int s = 1; s < SPLIT; s <<= 1) oa_dot += __shfl_xor_sync(0xffffffffu, oa_dot, s);
     if (valid && part == 0) {
-        // ---- what the cull launch left open: the reward with its obstacle-avoidance term and the running return
+        // ---- what the cull code left open: the reward with its obstacle-avoidance term and the running return
         T wf[6];
         RecIO<T>::template load<4, 3>(rec, wf);       // prel_z, A, B, r7, lp_d, delta_d
         const T ep_before = p.ep_return[ie];
@@ -872,7 +872,7 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
             WarpStats bs;
             bs.done = true;
             bs.cond = cond;
-            bs.length = p.t_steps[ie];                // already incremented by the cull launch
+            bs.length = p.t_steps[ie];                // already incremented by the cull code
             bs.ep_return = (double)ep_ret;
             bs.delta_d = (double)wf[5];
             bs.nan = reward != reward;
