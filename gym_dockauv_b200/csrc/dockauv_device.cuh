@@ -33,6 +33,7 @@ struct Mth<double> {
     static constexpr double half_pi = 1.5707963267948966;
     static constexpr double inv_pi = 0.3183098861837907, inv_half_pi = 0.6366197723675814;
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
+    static __device__ __forceinline__ double min_normal() { return 2.2250738585072014e-308; }
     static __device__ __forceinline__ double nan() { return CUDART_NAN; }
     static __device__ __forceinline__ void sincos_(double x, double *s, double *c) {
         const double2 r = sincos_outlined(x);
@@ -88,6 +89,7 @@ struct Mth<float> {
     static constexpr float half_pi = 1.57079632679490f;
     static constexpr float inv_pi = 0.318309886183791f, inv_half_pi = 0.636619772367581f;
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+    static __device__ __forceinline__ float min_normal() { return 1.17549435e-38f; }
     static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
     static __device__ __forceinline__ void sincos_(float x, float *s, float *c) { sincosf(x, s, c); }
     static __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }

@@ -138,21 +138,23 @@ __device__ __forceinline__ T cast_capsule(const T rd[3], const T ba[3], const T 
 // cast_sphere, so hits give identical bits.  Must be called by all 32 lanes.
 //   A SPHERE goes through the same code as a capsule whose cylinder quadratic IS the sphere quadratic (sphere_as_capsule:
 //   ba = 0, baba = 1, baoa = 1/2, cc = |oc|^2 - r^2 -> a = 1, b = rd . oc, h = b^2 - cc, y = 1/2: always a "body" hit);
-//   `touch` marks such a record: a tangent ray (h == 0) counts as a hit there (shape.py:258 tests h < 0 for "miss") and
-//   the root is not multiplied by 1 / a.
+//   h_min of such a record is minus the smallest normal number: a tangent ray (h == 0) counts as a hit there (shape.py:258
+//   tests h < 0 for "miss"); a = 1 makes the rest of the capsule path the sphere's arithmetic bit for bit.
 template <typename T>
 __device__ __forceinline__ T cast_capsule_bf(const T rd[3], const T ba[3], const T oa[3], T baba, T baoa, T cc, T c2a, T c2b,
-                                             bool touch, T best) {
+                                             T h_min, T best) {
     const T bard = rd[0] * ba[0] + rd[1] * ba[1] + rd[2] * ba[2];
     const T rdoa = rd[0] * oa[0] + rd[1] * oa[1] + rd[2] * oa[2];
     const T a = baba - bard * bard;
     const T b = baba * rdoa - baoa * bard;
-    const T h = touch ? Mth<T>::fma_(b, b, -cc) : (b * b - a * cc);
+    // (a sphere record has a = 1 exactly: a cc = cc, 1 / a = 1, so this is the sphere's fma(b, b, -c) and its root as it is --
+    // no per-lane select on the obstacle type, which was a tenth of this launch's instructions)
+    const T h = Mth<T>::fma_(b, b, -Mth<T>::mul_(a, cc));
     const T sq = Mth<T>::sqrt_pos(h > T(0) ? h : T(1));
     const T root = -b - (h > T(0) ? sq : T(0));
-    const T t = touch ? root : root * Mth<T>::rcp_(a);
+    const T t = root * Mth<T>::rcp_(a);
     const T y = baoa + t * bard;
-    const bool cand = touch ? (h >= T(0)) : (h > T(0));
+    const bool cand = h > h_min;      // h_min = 0: capsule (shape.py:352 h > 0); -min_normal: sphere (shape.py:258 misses on h < 0 only)
     const bool body = y > T(0) && y < baba;
     T v = t;
     bool okv = cand && body;

@@ -798,6 +798,9 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
 #endif
         }
     }
+    T h_min[NOB];      // see cast_capsule_bf
+#pragma unroll
+    for (int o = 0; o < NOB; o++) h_min[o] = sph[o] ? -Mth<T>::min_normal() : T(0);
     // ---- this lane's run of pooled cells: multiples of four, so the row is written in 16-byte pieces
     const int cpp = (((n_rr + SPLIT - 1) / SPLIT) + 3) & ~3;
     const int c_begin = part * cpp;
@@ -828,7 +831,7 @@ __device__ __forceinline__ void rays_thread_tile(const KParams<T> &p, const T *s
 #pragma unroll
             for (int o = 0; o < NOB; o++) {
                 const T ba[3] = {w[o][0], w[o][1], w[o][2]}, oa[3] = {w[o][3], w[o][4], w[o][5]};
-                best = cast_capsule_bf<T>(rd, ba, oa, w[o][6], w[o][7], w[o][8], w[o][9], w[o][10], sph[o], best);
+                best = cast_capsule_bf<T>(rd, ba, oa, w[o][6], w[o][7], w[o][8], w[o][9], w[o][10], h_min[o], best);
             }
             dq[q] = best > dmax ? dmax : best;        // clamp (sensor.py:117)
         }
